@@ -1,0 +1,280 @@
+// K0: BN254 Fq / Fr Montgomery arithmetic on 8 x 32-bit limbs (R = 2^256).
+//
+// Replaces halo2curves 0.3.1 `bn256::{Fq,Fr}` (un-vendored; Cargo.lock:1803-1826) at the call
+// sites listed in SURVEY.md 8c.  Values are kept fully reduced in [0, p) in Montgomery form.
+//
+// mul(): interleaved (CIOS-style) multiply+reduce with the products split over two accumulators
+// ("aligned" columns 2k,2k+1 and "offset" columns 2k+1,2k+2) so that every 32x32 partial product is
+// one 64-bit multiply-accumulate with a predicate carry in and out.  ptxas turns each
+// mad.lo.cc/madc.hi.cc pair into a single IMAD.WIDE.U32.X: 139 IMAD* + 37 IADD3 per modmul on
+// sm_100a (cuobjdump count).  Both moduli are 254-bit, so the top accumulator pair
+// never overflows.
+#pragma once
+#include "ptx_arith.cuh"
+
+struct FqParams {
+  HD static constexpr u32 mod(int i) {
+    constexpr u32 m[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return m[i];
+  }
+  HD static constexpr u32 one(int i) {
+    constexpr u32 m[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return m[i];
+  }
+  HD static constexpr u32 r2(int i) {
+    constexpr u32 m[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+    return m[i];
+  }
+  static constexpr u32 M0 = 0xe4866389u;
+};
+
+struct FrParams {
+  HD static constexpr u32 mod(int i) {
+    constexpr u32 m[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return m[i];
+  }
+  HD static constexpr u32 one(int i) {
+    constexpr u32 m[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return m[i];
+  }
+  HD static constexpr u32 r2(int i) {
+    constexpr u32 m[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+    return m[i];
+  }
+  static constexpr u32 M0 = 0xefffffffu;
+};
+
+template <class P>
+struct Fe {
+  u32 v[8];
+
+  HD static Fe zero() {
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = 0;
+    return r;
+  }
+  HD static Fe one() {
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = P::one(i);
+    return r;
+  }
+  HD static Fe modulus() {
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = P::mod(i);
+    return r;
+  }
+  HD bool is_zero() const {
+    u32 o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= v[i];
+    return o == 0;
+  }
+  HD bool operator==(const Fe& b) const {
+    u32 o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= v[i] ^ b.v[i];
+    return o == 0;
+  }
+  HD bool operator!=(const Fe& b) const { return !(*this == b); }
+
+  // r = a - p if a >= p else a     (a < 2p, possibly with a carry word `hi`)
+  HD static void reduce_once(u32* a, u32 hi = 0) {
+    u32 s[8];
+    s[0] = ptx::sub_cc(a[0], P::mod(0));
+#pragma unroll
+    for (int i = 1; i < 8; i++) s[i] = ptx::subc_cc(a[i], P::mod(i));
+    u32 br = ptx::subc(hi, 0);  // hi - borrow: 0xffffffff iff a < p (and hi == 0)
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = br ? a[i] : s[i];
+  }
+
+  HD friend Fe operator+(const Fe& a, const Fe& b) {
+    Fe r;
+    r.v[0] = ptx::add_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) r.v[i] = ptx::addc_cc(a.v[i], b.v[i]);
+    // 2p < 2^255: no carry out of the top limb
+    reduce_once(r.v);
+    return r;
+  }
+  HD friend Fe operator-(const Fe& a, const Fe& b) {
+    Fe r;
+    r.v[0] = ptx::sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) r.v[i] = ptx::subc_cc(a.v[i], b.v[i]);
+    u32 br = ptx::subc(0, 0);  // 0xffffffff iff borrow
+    u32 t[8];
+    t[0] = ptx::add_cc(r.v[0], P::mod(0) & br);
+#pragma unroll
+    for (int i = 1; i < 7; i++) t[i] = ptx::addc_cc(r.v[i], P::mod(i) & br);
+    t[7] = ptx::addc(r.v[7], P::mod(7) & br);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = t[i];
+    return r;
+  }
+  HD Fe neg() const { return zero() - *this; }
+  HD Fe dbl() const { return *this + *this; }
+
+  // ---- Montgomery multiplication -------------------------------------------------------------
+  // acc pair (j, j+1) = a[j] * bi               (j = 0,2,4,6; a is a pointer to the first limb used)
+  HD static void mul_row(u32* acc, const u32* a, u32 bi) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      acc[j] = ptx::mul_lo(a[j], bi);
+      acc[j + 1] = ptx::mul_hi(a[j], bi);
+    }
+  }
+  // acc pairs += a[j] * bi with one carry chain; leaves the carry-out in CC
+  HD static void cmad_row(u32* acc, const u32* a, u32 bi) {
+    acc[0] = ptx::mad_lo_cc(a[0], bi, acc[0]);
+    acc[1] = ptx::madc_hi_cc(a[0], bi, acc[1]);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) {
+      acc[j] = ptx::madc_lo_cc(a[j], bi, acc[j]);
+      acc[j + 1] = ptx::madc_hi_cc(a[j], bi, acc[j + 1]);
+    }
+  }
+  HD static void cmad_row_mod(u32* acc, int off, u32 mi) {
+    acc[0] = ptx::mad_lo_cc(P::mod(off), mi, acc[0]);
+    acc[1] = ptx::madc_hi_cc(P::mod(off), mi, acc[1]);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) {
+      acc[j] = ptx::madc_lo_cc(P::mod(off + j), mi, acc[j]);
+      acc[j + 1] = ptx::madc_hi_cc(P::mod(off + j), mi, acc[j + 1]);
+    }
+  }
+  // odd[j] = odd[j+2] + (a[j] * bi) words, continuing the carry in CC (shift right by two limbs)
+  HD static void madc_row_rshift(u32* odd, const u32* a, u32 bi) {
+#pragma unroll
+    for (int j = 0; j < 6; j += 2) {
+      odd[j] = ptx::madc_lo_cc(a[j], bi, odd[j + 2]);
+      odd[j + 1] = ptx::madc_hi_cc(a[j], bi, odd[j + 3]);
+    }
+    odd[6] = ptx::madc_lo_cc(a[6], bi, 0);
+    odd[7] = ptx::madc_hi(a[6], bi, 0);
+  }
+  // one row: T = (T + a*bi + m*p) / 2^32.  `al` holds columns (2k,2k+1), `of` columns (2k+1,2k+2).
+  // On exit the roles of the two arrays are swapped (the caller alternates them).
+  HD static void mad_row_redc(u32* al, u32* of, const u32* a, u32 bi, bool first) {
+    if (first) {
+      mul_row(of, a + 1, bi);
+      mul_row(al, a, bi);
+    } else {
+      al[0] = ptx::add_cc(al[0], of[1]);
+      madc_row_rshift(of, a + 1, bi);
+      cmad_row(al, a, bi);
+      of[7] = ptx::addc(of[7], 0);
+    }
+    u32 mi = al[0] * P::M0;
+    cmad_row_mod(of, 1, mi);
+    cmad_row_mod(al, 0, mi);
+    of[7] = ptx::addc(of[7], 0);
+  }
+
+  HD friend Fe operator*(const Fe& a, const Fe& b) {
+    u32 al[8], of[8];
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      mad_row_redc(al, of, a.v, b.v[i], i == 0);
+      mad_row_redc(of, al, a.v, b.v[i + 1], false);
+    }
+    // after the last row of[0] == 0 and the pending one-limb shift folds of[1..7] onto al[0..6]
+    Fe r;
+    r.v[0] = ptx::add_cc(al[0], of[1]);
+#pragma unroll
+    for (int j = 1; j < 7; j++) r.v[j] = ptx::addc_cc(al[j], of[j + 1]);
+    r.v[7] = ptx::addc(al[7], 0);
+    reduce_once(r.v);
+    return r;
+  }
+  HD Fe sqr() const { return (*this) * (*this); }
+
+  // canonical <-> Montgomery
+  HD Fe to_mont() const {
+    Fe r2;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r2.v[i] = P::r2(i);
+    return (*this) * r2;
+  }
+  HD Fe from_mont() const {
+    Fe o = zero();
+    o.v[0] = 1;
+    return (*this) * o;
+  }
+  // canonical value < p ?
+  HD static bool is_canonical(const u32* a) {
+    ptx::sub_cc(a[0], P::mod(0));
+#pragma unroll
+    for (int i = 1; i < 8; i++) ptx::subc_cc(a[i], P::mod(i));
+    return ptx::subc(0, 0) != 0;
+  }
+
+  // a^e for a public 256-bit exponent (left-to-right binary; the exponent is uniform across a warp)
+  HD Fe pow(const u32* e) const {
+    Fe r = one();
+    bool started = false;
+    for (int w = 7; w >= 0; w--) {
+      for (int b = 31; b >= 0; b--) {
+        if (started) r = r.sqr();
+        if ((e[w] >> b) & 1) {
+          r = started ? r * (*this) : *this;
+          started = true;
+        }
+      }
+    }
+    return r;
+  }
+  // Fermat inversion a^(p-2); 0 -> 0 (== the `unwrap_or_else(|| value.clone())` of loader.rs:247)
+  HD Fe inv() const {
+    u32 e[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) e[i] = P::mod(i);
+    e[0] -= 2;  // both moduli end in ...47 / ...01: no borrow
+    return pow(e);
+  }
+  // sqrt for p = 3 mod 4 (Fq only): candidate a^((p+1)/4); caller checks y*y == a
+  HD Fe sqrt_candidate() const {
+    u32 e[8];
+    // (p+1)/4
+    u32 c = 1;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      u64 t = (u64)P::mod(i) + c;
+      e[i] = (u32)t;
+      c = (u32)(t >> 32);
+    }
+#pragma unroll
+    for (int i = 0; i < 7; i++) e[i] = (e[i] >> 2) | (e[i + 1] << 30);
+    e[7] >>= 2;
+    return pow(e);
+  }
+};
+
+typedef Fe<FqParams> Fq;
+typedef Fe<FrParams> Fr;
+
+// 32-byte little-endian canonical <-> limbs
+HD void fe_load_le(u32* v, const uint8_t* b) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) v[i] = (u32)b[4 * i] | ((u32)b[4 * i + 1] << 8) | ((u32)b[4 * i + 2] << 16) | ((u32)b[4 * i + 3] << 24);
+}
+HD void fe_store_le(uint8_t* b, const u32* v) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    b[4 * i] = (uint8_t)v[i];
+    b[4 * i + 1] = (uint8_t)(v[i] >> 8);
+    b[4 * i + 2] = (uint8_t)(v[i] >> 16);
+    b[4 * i + 3] = (uint8_t)(v[i] >> 24);
+  }
+}
+
+// Fq canonical value -> Fr (integer value mod r; `fe_to_fe`, util/arithmetic.rs:256-258).
+// p < 2r so one conditional subtraction suffices.  Input/outputs canonical (non-Montgomery) limbs.
+HD void fq_canon_to_fr_canon(u32* out, const u32* in) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) out[i] = in[i];
+  Fr::reduce_once(out);
+}
