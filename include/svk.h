@@ -1,0 +1,76 @@
+/* libsvk -- C ABI of the B200-native batch verifier for the NativeLoader KZG/PLONK path of
+ * snark-verifier.  Plain pointers and sizes only.  Every entry point cites the reference
+ * interface it replaces (paths relative to the reference root).
+ *
+ * Data layout at the ABI: field elements are 32-byte little-endian CANONICAL values
+ * (= halo2curves `to_repr()`), never Montgomery.  Batches are arrays of structs.
+ * Return value: 0 on success, < 0 for CUDA / argument faults (see svk_last_error).  Verification
+ * outcomes are reported per item in status / ok arrays, never through the return code, and the
+ * process is never aborted.
+ *
+ * `*_dev` variants take DEVICE pointers (inputs already resident in HBM) and enqueue on the
+ * context's stream without synchronising; the plain variants take HOST pointers, copy in, run,
+ * copy out and synchronise.
+ */
+#ifndef SVK_H
+#define SVK_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct svk_ctx svk_ctx;
+
+typedef struct { uint8_t b[32]; } svk_fe;                 /* Fr or Fq, LE canonical */
+typedef struct { svk_fe x, y; } svk_g1;                   /* G1Affine; identity = all zero */
+typedef struct { svk_fe x_c0, x_c1, y_c0, y_c1; } svk_g2; /* G2Affine over Fq2 = c0 + c1 u */
+typedef struct { svk_g1 lhs, rhs; } svk_acc;              /* KzgAccumulator  (pcs/kzg/accumulator.rs:6-26) */
+typedef struct { svk_g1 g1; svk_g2 g2; svk_g2 s_g2; } svk_deciding_key; /* KzgDecidingKey (pcs/kzg/decider.rs:6-36) */
+
+/* per-item status = `Error` of snark-verifier/src/lib.rs:21-30 */
+enum {
+  SVK_OK = 0,
+  SVK_INVALID_INSTANCES = 1, /* Error::InvalidInstances   verifier/plonk/proof.rs:66-69 */
+  SVK_INVALID_PROTOCOL = 2,  /* Error::InvalidProtocol    verifier/plonk/proof.rs:216,223,232,273 */
+  SVK_ASSERTION_FAILURE = 3, /* Error::AssertionFailure   pcs/kzg/decider.rs:67 */
+  SVK_TRANSCRIPT = 4         /* Error::Transcript         system/halo2/transcript/halo2.rs:214-260 */
+};
+/* sub-codes stored in bits 8.. of a status word when the low byte is SVK_TRANSCRIPT */
+enum { SVK_T_EOF = 1, SVK_T_SCALAR_RANGE = 2, SVK_T_POINT_INVALID = 3, SVK_T_POINT_IDENTITY = 4 };
+
+enum { SVK_MOS_BDFG21 = 0 /* SHPLONK, pcs/kzg/multiopen/bdfg21.rs */, SVK_MOS_GWC19 = 1 /* pcs/kzg/multiopen/gwc19.rs */ };
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* One context = one device + one stream.  Calls on one context are serialised by the caller.
+ * Fails (returns < 0, *out = NULL) when no sm_100 GPU is present: there is no CPU fallback. */
+int svk_create(int device, svk_ctx** out);
+void svk_destroy(svk_ctx* ctx);
+const char* svk_last_error(svk_ctx* ctx);
+/* Use an external CUDA stream (cudaStream_t as void*), e.g. torch's current stream. */
+int svk_set_stream(svk_ctx* ctx, void* cuda_stream);
+int svk_sync(svk_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py `gpu_launches`). */
+uint64_t svk_launch_count(svk_ctx* ctx);
+
+/* ---- KzgDecidingKey -------------------------------------------------------------------------
+ * `KzgDecidingKey::new(g1, g2, s_g2)` (pcs/kzg/decider.rs:15-24) + halo2curves `G2Prepared::from`
+ * (decider.rs:64): validates the G2 points, precomputes the line tables of g2 and -s_g2 and
+ * uploads them.  Returns a key id >= 0. */
+int svk_dk_load(svk_ctx* ctx, const svk_deciding_key* dk);
+
+/* ---- AccumulationDecider::decide / decide_all (pcs/kzg/decider.rs:60-81) ----------------------
+ * out_ok[i] = 1 iff e(lhs_i, g2) * e(rhs_i, -s_g2) == 1.  No fail-fast: every accumulator gets
+ * its own answer (`decide_all` == all ones). */
+int svk_kzg_decide_batch(svk_ctx* ctx, int dk, size_t n, const svk_acc* accs, uint8_t* out_ok);
+int svk_kzg_decide_batch_dev(svk_ctx* ctx, int dk, size_t n, const void* d_accs, void* d_out_ok);
+
+/* ---- micro-benchmark of the integer-multiply roofline (DESIGN.md "IMAD peak") ------------------
+ * Runs `iters` dependent Montgomery multiplications per thread on every SM; returns modmul/s. */
+int svk_bench_modmul_peak(svk_ctx* ctx, int iters, double* out_modmul_per_s, double* out_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

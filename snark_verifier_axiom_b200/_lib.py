@@ -1,0 +1,42 @@
+"""ctypes binding of libsvk.so (include/svk.h).  Loading fails loudly when the library is missing;
+`Context()` fails loudly when no sm_100 GPU is present -- there is no CPU fallback."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsvk.so")
+
+
+class SvkError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise SvkError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` (make -C csrc)")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, sz, i32, u8p = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_char_p
+    lib.svk_create.argtypes = [i32, ctypes.POINTER(vp)]
+    lib.svk_destroy.argtypes = [vp]
+    lib.svk_destroy.restype = None
+    lib.svk_last_error.argtypes = [vp]
+    lib.svk_last_error.restype = ctypes.c_char_p
+    lib.svk_set_stream.argtypes = [vp, vp]
+    lib.svk_sync.argtypes = [vp]
+    lib.svk_launch_count.argtypes = [vp]
+    lib.svk_launch_count.restype = ctypes.c_uint64
+    lib.svk_dk_load.argtypes = [vp, u8p]
+    lib.svk_kzg_decide_batch.argtypes = [vp, i32, sz, vp, vp]
+    lib.svk_kzg_decide_batch_dev.argtypes = [vp, i32, sz, vp, vp]
+    lib.svk_bench_modmul_peak.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    return lib
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = _load()
+    return _LIB

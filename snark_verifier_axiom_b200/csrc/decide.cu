@@ -1,0 +1,89 @@
+// K5/K6 kernel: batched KzgAs::decide (snark-verifier/src/pcs/kzg/decider.rs:60-81).
+// v1 mapping: one accumulator per thread; the G2 line tables and Frobenius constants are read
+// uniformly by all threads (broadcast loads, L1/L2 resident: 2 x 102 x 128 B).
+#include "svk_ctx.h"
+
+__device__ __forceinline__ G1Affine load_g1_canon(const uint8_t* p) {
+  G1Affine a;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3];
+  a.x.v[0] = w0.x; a.x.v[1] = w0.y; a.x.v[2] = w0.z; a.x.v[3] = w0.w;
+  a.x.v[4] = w1.x; a.x.v[5] = w1.y; a.x.v[6] = w1.z; a.x.v[7] = w1.w;
+  a.y.v[0] = w2.x; a.y.v[1] = w2.y; a.y.v[2] = w2.z; a.y.v[3] = w2.w;
+  a.y.v[4] = w3.x; a.y.v[5] = w3.y; a.y.v[6] = w3.z; a.y.v[7] = w3.w;
+  return a;
+}
+
+// status: bit0 = accept.  A point that is not a canonical on-curve encoding makes the reference's
+// `G1Affine` unconstructible; such accumulators are reported as reject.
+__global__ void __launch_bounds__(64) k_decide(size_t n, const uint8_t* accs, uint8_t* out_ok, const G2Line* t_g2,
+                                               const G2Line* t_neg_sg2, const PairingConsts* consts) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Affine lhs = load_g1_canon(accs + i * 128);
+  G1Affine rhs = load_g1_canon(accs + i * 128 + 64);
+  bool ok = Fq::is_canonical(lhs.x.v) && Fq::is_canonical(lhs.y.v) && Fq::is_canonical(rhs.x.v) && Fq::is_canonical(rhs.y.v);
+  if (!lhs.is_identity()) { lhs.x = lhs.x.to_mont(); lhs.y = lhs.y.to_mont(); }
+  if (!rhs.is_identity()) { rhs.x = rhs.x.to_mont(); rhs.y = rhs.y.to_mont(); }
+  ok = ok && g1_on_curve(lhs) && g1_on_curve(rhs);
+  bool acc = false;
+  if (ok) acc = kzg_decide(lhs, rhs, t_g2, t_neg_sg2, *consts);
+  out_ok[i] = acc ? 1 : 0;
+}
+
+int svk_decide_launch(svk_ctx* ctx, int dk, size_t n, const void* d_accs, void* d_ok) {
+  if (dk < 0 || dk >= (int)ctx->dks.size()) return svk_fail(ctx, "bad deciding-key id %d", dk);
+  if (n == 0) return 0;
+  const DkDevice& k = ctx->dks[dk];
+  unsigned block = 64;
+  unsigned grid = (unsigned)((n + block - 1) / block);
+  k_decide<<<grid, block, 0, ctx->stream>>>(n, (const uint8_t*)d_accs, (uint8_t*)d_ok, k.d_lines_g2, k.d_lines_neg_sg2,
+                                            ctx->d_pairing_consts);
+  ctx->launches++;
+  SVK_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ---- integer-multiply roofline micro-benchmark ------------------------------------------------
+__global__ void __launch_bounds__(256) k_modmul_peak(u32* out, int iters) {
+  // 2 independent dependent-chains per thread (ILP 2), 8 warps per SM sub-partition
+  Fq a, b, c, d;
+  u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { a.v[i] = t * 2654435761u + i; b.v[i] = t ^ (0x9e3779b9u * (i + 1)); c.v[i] = t + 77 * i; d.v[i] = ~t - i; }
+  a.v[7] &= 0x0fffffffu; b.v[7] &= 0x0fffffffu; c.v[7] &= 0x0fffffffu; d.v[7] &= 0x0fffffffu;
+  for (int k = 0; k < iters; k++) {
+    a = a * b;
+    c = c * d;
+    b = b * a;
+    d = d * c;
+  }
+  Fq r = a + b + c + d;
+  u32 x = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) x ^= r.v[i];
+  if (x == 0x12345678u) out[0] = x;  // keep the chain alive
+}
+
+int svk_modmul_peak_launch(svk_ctx* ctx, int iters, double* out_rate, double* out_ms) {
+  void* d_out;
+  if (svk_scratch(ctx, 7, 256, &d_out)) return -1;
+  int blocks = ctx->sm_count * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  SVK_CUDA(ctx, cudaEventCreate(&e0));
+  SVK_CUDA(ctx, cudaEventCreate(&e1));
+  k_modmul_peak<<<blocks, threads, 0, ctx->stream>>>((u32*)d_out, 16);  // warm-up
+  SVK_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+  k_modmul_peak<<<blocks, threads, 0, ctx->stream>>>((u32*)d_out, iters);
+  SVK_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+  ctx->launches += 2;
+  SVK_CUDA(ctx, cudaEventSynchronize(e1));
+  float ms = 0;
+  SVK_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  double muls = (double)blocks * threads * 4.0 * iters;
+  *out_rate = muls / (ms * 1e-3);
+  *out_ms = ms;
+  return 0;
+}

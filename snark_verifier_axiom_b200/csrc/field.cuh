@@ -213,7 +213,7 @@ struct Fe {
   }
 
   // a^e for a public 256-bit exponent (left-to-right binary; the exponent is uniform across a warp)
-  HD Fe pow(const u32* e) const {
+  HDN Fe pow(const u32* e) const {
     Fe r = one();
     bool started = false;
     for (int w = 7; w >= 0; w--) {

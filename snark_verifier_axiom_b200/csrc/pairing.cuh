@@ -43,7 +43,7 @@ HD int ate_bit(int i) {  // bit i of 6x+2
 
 // ---- Frobenius on Fq12: coefficient of w^i is conj^k(c_i) * gamma_{k,i};
 // w-power layout: c0.c0 = w^0, c1.c0 = w^1, c0.c1 = w^2, c1.c1 = w^3, c0.c2 = w^4, c1.c2 = w^5
-HD Fq12 fq12_frob1(const Fq12& f, const PairingConsts& k) {
+HDN Fq12 fq12_frob1(const Fq12& f, const PairingConsts& k) {
   Fq12 r;
   r.c0.c0 = f.c0.c0.conj();
   r.c1.c0 = f.c1.c0.conj() * k.g1[0];
@@ -53,7 +53,7 @@ HD Fq12 fq12_frob1(const Fq12& f, const PairingConsts& k) {
   r.c1.c2 = f.c1.c2.conj() * k.g1[4];
   return r;
 }
-HD Fq12 fq12_frob2(const Fq12& f, const PairingConsts& k) {
+HDN Fq12 fq12_frob2(const Fq12& f, const PairingConsts& k) {
   Fq12 r;
   r.c0.c0 = f.c0.c0;
   r.c1.c0 = f.c1.c0.mul_fq(k.g2[0]);
@@ -63,7 +63,7 @@ HD Fq12 fq12_frob2(const Fq12& f, const PairingConsts& k) {
   r.c1.c2 = f.c1.c2.mul_fq(k.g2[4]);
   return r;
 }
-HD Fq12 fq12_frob3(const Fq12& f, const PairingConsts& k) {
+HDN Fq12 fq12_frob3(const Fq12& f, const PairingConsts& k) {
   Fq12 r;
   r.c0.c0 = f.c0.c0.conj();
   r.c1.c0 = f.c1.c0.conj() * k.g3[0];
@@ -76,7 +76,7 @@ HD Fq12 fq12_frob3(const Fq12& f, const PairingConsts& k) {
 
 // ---- Miller loop over two (G1, fixed G2) pairs sharing the squarings.
 // A pair whose G1 point is the identity contributes 1 (its lines are skipped).
-HD Fq12 miller_loop_2(const G1Affine& p1, const G2Line* t1, const G1Affine& p2, const G2Line* t2) {
+HDN Fq12 miller_loop_2(const G1Affine& p1, const G2Line* t1, const G1Affine& p2, const G2Line* t2) {
   Fq12 f = Fq12::one();
   bool use1 = !p1.is_identity(), use2 = !p2.is_identity();
   int li = 0;
@@ -100,7 +100,7 @@ HD Fq12 miller_loop_2(const G1Affine& p1, const G2Line* t1, const G1Affine& p2, 
 }
 
 // f^x for the BN parameter x (63 bits), f in the cyclotomic subgroup
-HD Fq12 fq12_pow_x(const Fq12& f) {
+HDN Fq12 fq12_pow_x(const Fq12& f) {
   Fq12 r = f;
   for (int i = 61; i >= 0; i--) {  // bit 62 is the MSB
     r = r.sqr();
@@ -112,7 +112,7 @@ HD Fq12 fq12_pow_x(const Fq12& f) {
 
 // f^((p^12 - 1)/r) exactly:  easy part (p^6-1)(p^2+1), then
 // hard = (p^4-p^2+1)/r = p^3 + (6x^2+1) p^2 + (-36x^3-18x^2-12x+1) p + (-36x^3-30x^2-18x-2)
-HD Fq12 final_exponentiation(const Fq12& f0, const PairingConsts& k) {
+HDN Fq12 final_exponentiation(const Fq12& f0, const PairingConsts& k) {
   Fq12 t = f0.conj() * f0.inv();      // ^(p^6 - 1)
   Fq12 f = fq12_frob2(t, k) * t;      // ^(p^2 + 1)   -> cyclotomic subgroup: inverse == conj
   Fq12 fx = fq12_pow_x(f);

@@ -15,8 +15,10 @@ typedef uint64_t u64;
 
 #if defined(__CUDACC__)
 #define HD __host__ __device__ __forceinline__
+#define HDN inline __host__ __device__ __noinline__
 #else
 #define HD inline
+#define HDN inline
 #endif
 
 namespace ptx {

@@ -1,0 +1,62 @@
+// Internal context shared by the libsvk translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/svk.h"
+#include "pairing.cuh"
+
+struct DkDevice {
+  G2Line* d_lines_g2 = nullptr;       // SVK_N_LINES
+  G2Line* d_lines_neg_sg2 = nullptr;  // SVK_N_LINES
+  G1Affine g1;                        // svk.g (Montgomery)
+  svk_g1 g1_canon;
+};
+
+struct svk_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  uint64_t launches = 0;
+  int sm_count = 0;
+  PairingConsts* d_pairing_consts = nullptr;
+  std::vector<DkDevice> dks;
+  // scratch buffers (grown on demand, reused across calls)
+  void* scratch[8] = {nullptr};
+  size_t scratch_sz[8] = {0};
+  std::vector<struct ProtocolDevice*> protocols;
+};
+
+inline int svk_fail(svk_ctx* ctx, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return -1;
+}
+
+#define SVK_CUDA(ctx, call)                                                                      \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess) return svk_fail(ctx, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+inline int svk_scratch(svk_ctx* ctx, int slot, size_t bytes, void** out) {
+  if (ctx->scratch_sz[slot] < bytes) {
+    if (ctx->scratch[slot]) cudaFree(ctx->scratch[slot]);
+    ctx->scratch[slot] = nullptr;
+    ctx->scratch_sz[slot] = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    SVK_CUDA(ctx, cudaMalloc(&ctx->scratch[slot], want));
+    ctx->scratch_sz[slot] = want;
+  }
+  *out = ctx->scratch[slot];
+  return 0;
+}

@@ -15,19 +15,19 @@ struct Fq2 {
   HD Fq2 neg() const { return {c0.neg(), c1.neg()}; }
   HD Fq2 dbl() const { return {c0.dbl(), c1.dbl()}; }
   HD Fq2 conj() const { return {c0, c1.neg()}; }
-  // Karatsuba: 3 Fq mul
-  HD friend Fq2 operator*(const Fq2& a, const Fq2& b) {
+  // Karatsuba: 3 Fq mul.  Not inlined: keeps the pairing kernels' code size (and ptxas time) bounded.
+  HDN friend Fq2 operator*(const Fq2& a, const Fq2& b) {
     Fq t0 = a.c0 * b.c0;
     Fq t1 = a.c1 * b.c1;
     Fq t2 = (a.c0 + a.c1) * (b.c0 + b.c1);
     return {t0 - t1, t2 - t0 - t1};
   }
   // complex squaring: 2 Fq mul
-  HD Fq2 sqr() const {
+  HDN Fq2 sqr() const {
     Fq t = c0 * c1;
     return {(c0 + c1) * (c0 - c1), t.dbl()};
   }
-  HD Fq2 mul_fq(const Fq& s) const { return {c0 * s, c1 * s}; }
+  HDN Fq2 mul_fq(const Fq& s) const { return {c0 * s, c1 * s}; }
   // * xi = (9 + u): (9a - b) + (9b + a) u
   HD Fq2 mul_xi() const {
     Fq a8 = c0.dbl().dbl().dbl();
@@ -49,7 +49,7 @@ struct Fq6 {
   HD friend Fq6 operator-(const Fq6& a, const Fq6& b) { return {a.c0 - b.c0, a.c1 - b.c1, a.c2 - b.c2}; }
   HD Fq6 neg() const { return {c0.neg(), c1.neg(), c2.neg()}; }
   // Karatsuba / Toom-like: 6 Fq2 mul
-  HD friend Fq6 operator*(const Fq6& a, const Fq6& b) {
+  HDN friend Fq6 operator*(const Fq6& a, const Fq6& b) {
     Fq2 t0 = a.c0 * b.c0;
     Fq2 t1 = a.c1 * b.c1;
     Fq2 t2 = a.c2 * b.c2;
@@ -61,9 +61,9 @@ struct Fq6 {
   HD Fq6 sqr() const { return (*this) * (*this); }
   // * v
   HD Fq6 mul_v() const { return {c2.mul_xi(), c0, c1}; }
-  HD Fq6 mul_fq(const Fq& s) const { return {c0.mul_fq(s), c1.mul_fq(s), c2.mul_fq(s)}; }
+  HDN Fq6 mul_fq(const Fq& s) const { return {c0.mul_fq(s), c1.mul_fq(s), c2.mul_fq(s)}; }
   // * (b0 + b1 v): 5 Fq2 mul
-  HD Fq6 mul_by_01(const Fq2& b0, const Fq2& b1) const {
+  HDN Fq6 mul_by_01(const Fq2& b0, const Fq2& b1) const {
     Fq2 t0 = c0 * b0;
     Fq2 t1 = c1 * b1;
     Fq2 r0 = (c2 * b1).mul_xi() + t0;
@@ -71,7 +71,7 @@ struct Fq6 {
     Fq2 r2 = c2 * b0 + t1;
     return {r0, r1, r2};
   }
-  HD Fq6 inv() const {
+  HDN Fq6 inv() const {
     Fq2 t0 = c0.sqr() - (c1 * c2).mul_xi();
     Fq2 t1 = c2.sqr().mul_xi() - c0 * c1;
     Fq2 t2 = c1.sqr() - c0 * c2;
@@ -87,25 +87,25 @@ struct Fq12 {
   HD bool operator==(const Fq12& b) const { return c0 == b.c0 && c1 == b.c1; }
   HD bool is_one() const { return *this == one(); }
   // 3 Fq6 mul = 54 Fq mul
-  HD friend Fq12 operator*(const Fq12& a, const Fq12& b) {
+  HDN friend Fq12 operator*(const Fq12& a, const Fq12& b) {
     Fq6 t0 = a.c0 * b.c0;
     Fq6 t1 = a.c1 * b.c1;
     Fq6 r1 = (a.c0 + a.c1) * (b.c0 + b.c1) - t0 - t1;
     return {t0 + t1.mul_v(), r1};
   }
   // complex squaring: 2 Fq6 mul = 36 Fq mul
-  HD Fq12 sqr() const {
+  HDN Fq12 sqr() const {
     Fq6 ab = c0 * c1;
     Fq6 t = (c0 + c1) * (c0 + c1.mul_v()) - ab - ab.mul_v();
     return {t, ab + ab};
   }
   HD Fq12 conj() const { return {c0, c1.neg()}; }
-  HD Fq12 inv() const {
+  HDN Fq12 inv() const {
     Fq6 d = (c0.sqr() - c1.sqr().mul_v()).inv();
     return {c0 * d, (c1 * d).neg()};
   }
   // * line  l = l0 + (l1 + l2 v) w   with l0 in Fq, l1, l2 in Fq2   (36 Fq mul)
-  HD Fq12 mul_by_line(const Fq& l0, const Fq2& l1, const Fq2& l2) const {
+  HDN Fq12 mul_by_line(const Fq& l0, const Fq2& l1, const Fq2& l2) const {
     Fq6 t0 = c0.mul_fq(l0);
     Fq6 t1 = c1.mul_by_01(l1, l2);
     Fq2 s0 = l1;
