@@ -21,6 +21,12 @@ typedef uint64_t u64;
 #define HDN inline
 #endif
 
+#if !defined(__CUDACC__)
+// host-only builds (tests/host): minimal stand-ins for the CUDA vector type used by the loaders
+struct uint4 { u32 x, y, z, w; };
+inline uint4 make_uint4(u32 x, u32 y, u32 z, u32 w) { return uint4{x, y, z, w}; }
+#endif
+
 namespace ptx {
 
 #if defined(__CUDA_ARCH__)

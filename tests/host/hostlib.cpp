@@ -99,3 +99,73 @@ int host_pairing(const u32* p1_xy, const u32* q1, const u32* p2_xy, const u32* q
   return kzg_decide(P1, P2, t1.data(), t2.data(), k) ? 1 : 0;
 }
 }
+
+#include "../../snark_verifier_axiom_b200/csrc/poseidon_host.h"
+extern "C" {
+// state/in: canonical limbs; n_in in {0,1,2}; returns 0 ok
+int host_poseidon_permute(const u32* state_in, int n_in, const u32* in0, const u32* in1, u32* state_out) {
+  static PoseidonConsts k;
+  static bool init = false;
+  if (!init) { if (!svk_host::make_poseidon_consts(k)) return -1; init = true; }
+  PoseidonState st;
+  for (int i = 0; i < 3; i++) { memcpy(st.s[i].v, state_in + 8 * i, 32); st.s[i] = st.s[i].to_mont(); }
+  Fr a, b; memcpy(a.v, in0, 32); memcpy(b.v, in1, 32); a = a.to_mont(); b = b.to_mont();
+  poseidon_permute(st, k, n_in, a, b);
+  for (int i = 0; i < 3; i++) { Fr o = st.s[i].from_mont(); memcpy(state_out + 8 * i, o.v, 32); }
+  return 0;
+}
+}
+
+#include "../../snark_verifier_axiom_b200/csrc/compiler.h"
+extern "C" {
+// Compile + run the tape for ONE proof on the host (same code the kernels run).
+// terms_out: per term 3 ints (which: 0 lhs / 1 rhs, base id, slot); returns #terms or <0.
+// info_out: [n_regs, n_ops, n_perm, n_challenges, n_scalar_slots, proof_len, err_word, verify_valid, n_fr_mul, n_points]
+int host_compile_run(const uint8_t* blob, size_t blob_len, int mos, const uint8_t* proof, u32 proof_len,
+                     const uint8_t* instances, u32 n_instances, u32* challenges_out, u32* scalars_out,
+                     int* terms_out, int max_terms, long long* info_out, char* errbuf, int errbuf_len) {
+  static PoseidonConsts pk;
+  static bool init = false;
+  if (!init) { svk_host::make_poseidon_consts(pk); init = true; }
+  try {
+    svk_host::CompiledProtocol cp = svk_host::compile_protocol(blob, blob_len, mos);
+    std::vector<u32> regs((size_t)cp.n_regs * 8 + 8, 0);
+    u32 err = SVK_NO_ERR;
+    for (auto& pr : cp.points) {
+      G1Affine pt; u32 xc[8], yc[8];
+      Fr fx = Fr::zero(), fy = Fr::zero();
+      if (pr.byte_offset + 32 > proof_len) tape_note_error(err, pr.byte_offset, SVK_T_EOF);
+      else {
+        int rc = g1_decompress(proof + pr.byte_offset, pt, xc, yc);
+        if (rc == 1) tape_note_error(err, pr.byte_offset, SVK_T_POINT_INVALID);
+        else if (rc == 2) tape_note_error(err, pr.byte_offset, SVK_T_POINT_IDENTITY);
+        else {
+          fq_canon_to_fr_canon(fx.v, xc); fq_canon_to_fr_canon(fy.v, yc);
+          fx = fx.to_mont(); fy = fy.to_mont();
+        }
+      }
+      memcpy(&regs[(size_t)pr.val_x * 8], fx.v, 32);
+      memcpy(&regs[(size_t)pr.val_y * 8], fy.v, 32);
+    }
+    RegFile rf{regs.data(), 1, 0};
+    TapeIo io{proof, proof_len, instances, n_instances, scalars_out, challenges_out, cp.n_challenges};
+    PoseidonState st;
+    poseidon_init(st, pk);
+    u32 end = cp.verify_valid ? (u32)cp.ops.size() : cp.read_ops_end;
+    tape_exec(cp.ops.data(), 0, end, cp.aux.data(), cp.consts.data(), pk, rf, io, st, err);
+    int nt = 0;
+    for (int which = 0; which < 2; which++)
+      for (auto& t : (which ? cp.rhs : cp.lhs)) {
+        if (nt >= max_terms) return -3;
+        terms_out[3 * nt] = which; terms_out[3 * nt + 1] = t.base; terms_out[3 * nt + 2] = t.slot; nt++;
+      }
+    long long info[10] = {cp.n_regs, (long long)cp.ops.size(), cp.n_perm, cp.n_challenges, cp.n_scalar_slots, cp.proof_len, err,
+                          cp.verify_valid, (long long)cp.n_fr_mul, (long long)cp.points.size()};
+    memcpy(info_out, info, sizeof info);
+    return nt;
+  } catch (svk_host::CompileError& e) {
+    snprintf(errbuf, errbuf_len, "%s", e.what());
+    return e.kind == SVK_INVALID_PROTOCOL ? -2 : -1;
+  }
+}
+}

@@ -38,3 +38,50 @@ def np_u8(b):
 
 def ptr(arr):
     return arr.ctypes.data_as(ctypes.c_void_p)
+
+
+def to_product_protocol(op):
+    """oracle.plonk.PlonkProtocol (tuple expressions) -> snark_verifier_axiom_b200.protocol.PlonkProtocol"""
+    from snark_verifier_axiom_b200 import protocol as pp
+
+    E = pp.Expression
+
+    def conv(e):
+        t = e[0]
+        if t == "const":
+            return E.Constant(e[1])
+        if t == "identity":
+            return E.CommonPolynomialIdentity()
+        if t == "lagrange":
+            return E.CommonPolynomialLagrange(e[1])
+        if t == "poly":
+            return E.Polynomial(pp.Query(e[1], e[2]))
+        if t == "challenge":
+            return E.Challenge(e[1])
+        if t == "neg":
+            return E.Negated(conv(e[1]))
+        if t == "sum":
+            return E.Sum(conv(e[1]), conv(e[2]))
+        if t == "product":
+            return E.Product(conv(e[1]), conv(e[2]))
+        if t == "scaled":
+            return E.Scaled(conv(e[1]), e[2])
+        if t == "distribute_powers":
+            return E.DistributePowers([conv(x) for x in e[1]], conv(e[2]))
+        raise ValueError(t)
+
+    lin = {None: None, "WithoutConstant": 1, "MinusVanishingTimesQuotient": 2}[op.linearization]
+    return pp.PlonkProtocol(
+        domain=pp.Domain(op.domain.k, op.domain.gen),
+        preprocessed=list(op.preprocessed),
+        num_instance=list(op.num_instance),
+        num_witness=list(op.num_witness),
+        num_challenge=list(op.num_challenge),
+        evaluations=[pp.Query(p, r) for p, r in op.evaluations],
+        queries=[pp.Query(p, r) for p, r in op.queries],
+        quotient=pp.QuotientPolynomial(op.quotient.chunk_degree, conv(op.quotient.numerator)),
+        transcript_initial_state=op.transcript_initial_state,
+        instance_committing_key=op.instance_committing_key,
+        linearization=lin,
+        accumulator_indices=[list(x) for x in op.accumulator_indices],
+    )
