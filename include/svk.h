@@ -66,6 +66,34 @@ int svk_dk_load(svk_ctx* ctx, const svk_deciding_key* dk);
 int svk_kzg_decide_batch(svk_ctx* ctx, int dk, size_t n, const svk_acc* accs, uint8_t* out_ok);
 int svk_kzg_decide_batch_dev(svk_ctx* ctx, int dk, size_t n, const void* d_accs, void* d_out_ok);
 
+/* ---- PlonkProtocol ingestion ---------------------------------------------------------------------
+ * Compiles a serialized `PlonkProtocol<G1Affine>` (verifier/plonk/protocol.rs:21-63; byte layout in
+ * snark_verifier_axiom_b200/protocol.py) for `PlonkSuccinctVerifier<KzgAs<Bn256, MOS>>` into a device
+ * "verifier tape" -- what `protocol.loaded(&loader)` + the generic verifier do per call in the
+ * reference (protocol.rs:106-130, verifier/plonk.rs:58-92) is done once here.  `dk` supplies
+ * `svk.g` (pcs/kzg.rs:21-37).  Returns a protocol id >= 0.  A protocol whose expressions the
+ * reference would reject with Error::InvalidProtocol still compiles; its proofs get that status. */
+int svk_protocol_compile(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos, int dk);
+/* out[12] = { proof_len, n_instances, n_challenges, n_regs, n_ops, n_poseidon_perms, verify_valid,
+ *             n_fr_mul, n_lhs_terms, n_rhs_terms, n_points, n_scalar_slots } */
+int svk_protocol_info(svk_ctx* ctx, int proto, uint32_t* out);
+
+/* ---- PlonkSuccinctVerifier::{read_proof, verify} (verifier/plonk.rs:32-93) over a batch ----------
+ * For each of the n proofs (proof i = proofs + i*proof_stride, length proof_lens[i] or proof_stride
+ * when proof_lens == NULL; trailing bytes are ignored like the reference's reader):
+ *   out_acc[i]        = the KzgAccumulator {lhs, rhs} (zeros when status != 0)
+ *   out_challenges[i] = every squeezed challenge in order (n_challenges each; may be NULL)
+ *   out_status[i]     = SVK_OK / SVK_INVALID_INSTANCES / SVK_INVALID_PROTOCOL /
+ *                       SVK_TRANSCRIPT | subcode << 8
+ * instances: n * n_instances field elements (all instance columns of a proof, concatenated);
+ * n_instances != sum(protocol.num_instance) => SVK_INVALID_INSTANCES for every proof (proof.rs:66-69). */
+int svk_plonk_succinct_verify_batch(svk_ctx* ctx, int proto, size_t n, const svk_fe* instances, uint32_t n_instances,
+                                    const uint8_t* proofs, size_t proof_stride, const uint32_t* proof_lens, svk_acc* out_acc,
+                                    svk_fe* out_challenges, int32_t* out_status);
+int svk_plonk_succinct_verify_batch_dev(svk_ctx* ctx, int proto, size_t n, const void* d_instances, uint32_t n_instances,
+                                        const void* d_proofs, size_t proof_stride, const void* d_proof_lens, void* d_out_acc,
+                                        void* d_out_challenges, void* d_out_status);
+
 /* ---- micro-benchmark of the integer-multiply roofline (DESIGN.md "IMAD peak") ------------------
  * Runs `iters` dependent Montgomery multiplications per thread on every SM; returns modmul/s. */
 int svk_bench_modmul_peak(svk_ctx* ctx, int iters, double* out_modmul_per_s, double* out_ms);

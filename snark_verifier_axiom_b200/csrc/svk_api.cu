@@ -1,13 +1,29 @@
 // libsvk C-ABI entry points (include/svk.h): context, deciding key, decide.
 #include <cstring>
 
+#include "compiler.h"
 #include "pairing_host.h"
+#include "poseidon_host.h"
 #include "svk_ctx.h"
+#include "svk_protocol.h"
 
 int svk_decide_launch(svk_ctx* ctx, int dk, size_t n, const void* d_accs, void* d_ok);
 int svk_modmul_peak_launch(svk_ctx* ctx, int iters, double* out_rate, double* out_ms);
+int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const uint8_t* d_instances, u32 n_instances_given,
+                               const uint8_t* d_proofs, size_t proof_stride, const u32* d_proof_lens, uint8_t* d_out_acc,
+                               u32* d_out_challenges, int32_t* d_out_status);
 
 static thread_local std::string g_create_err;
+
+template <class T>
+static int upload(svk_ctx* ctx, T** d, const std::vector<T>& v) {
+  *d = nullptr;
+  size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+  SVK_CUDA(ctx, cudaMalloc(d, bytes));
+  if (!v.empty()) SVK_CUDA(ctx, cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 
 extern "C" {
 
@@ -36,6 +52,10 @@ int svk_create(int device, svk_ctx** out) {
       cudaMemcpy(ctx->d_pairing_consts, &k, sizeof k, cudaMemcpyHostToDevice) != cudaSuccess) {
     delete ctx; g_create_err = "pairing constants upload failed"; return -1;
   }
+  if (!svk_host::make_poseidon_consts(ctx->h_poseidon) || cudaMalloc(&ctx->d_poseidon, sizeof(PoseidonConsts)) != cudaSuccess ||
+      cudaMemcpy(ctx->d_poseidon, &ctx->h_poseidon, sizeof(PoseidonConsts), cudaMemcpyHostToDevice) != cudaSuccess) {
+    delete ctx; g_create_err = "poseidon constants upload failed"; return -1;
+  }
   *out = ctx;
   return 0;
 }
@@ -47,6 +67,11 @@ void svk_destroy(svk_ctx* ctx) {
   for (auto& k : ctx->dks) { cudaFree(k.d_lines_g2); cudaFree(k.d_lines_neg_sg2); }
   for (int i = 0; i < 8; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   cudaFree(ctx->d_pairing_consts);
+  cudaFree(ctx->d_poseidon);
+  for (auto* p : ctx->protocols) {
+    cudaFree(p->d_ops); cudaFree(p->d_aux); cudaFree(p->d_consts); cudaFree(p->d_sched); cudaFree(p->d_lhs); cudaFree(p->d_rhs); cudaFree(p->d_fixed);
+    delete p;
+  }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -111,6 +136,118 @@ int svk_kzg_decide_batch(svk_ctx* ctx, int dk, size_t n, const svk_acc* accs, ui
   if (svk_decide_launch(ctx, dk, n, d_in, d_out)) return -1;
   SVK_CUDA(ctx, cudaMemcpyAsync(out_ok, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
   SVK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ---- PlonkProtocol ingestion --------------------------------------------------------------------
+int svk_protocol_compile(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos, int dk) {
+  SVK_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (dk < 0 || dk >= (int)ctx->dks.size()) return svk_fail(ctx, "bad deciding-key id %d", dk);
+  svk_host::CompiledProtocol cp;
+  try {
+    cp = svk_host::compile_protocol(blob, len, mos);
+  } catch (svk_host::CompileError& e) {
+    return svk_fail(ctx, "protocol compile: %s", e.what());
+  }
+  ProtocolDevice* pd = new ProtocolDevice();
+  pd->mos = mos;
+  pd->dk = dk;
+  pd->verify_valid = cp.verify_valid;
+  pd->invalid_reason = cp.invalid_reason;
+  pd->n_ops = (u32)cp.ops.size();
+  pd->read_ops_end = cp.read_ops_end;
+  pd->n_regs = cp.n_regs;
+  pd->n_instances = cp.n_instances;
+  pd->n_challenges = cp.n_challenges;
+  pd->n_scalar_slots = cp.n_scalar_slots;
+  pd->proof_len = cp.proof_len;
+  pd->n_perm = cp.n_perm;
+  pd->n_fr_mul = cp.n_fr_mul;
+  pd->num_instance = cp.num_instance;
+  pd->n_pre = (u32)cp.preprocessed.size();
+  for (auto& p : cp.points) pd->points.push_back({p.byte_offset, (u32)p.val_x, (u32)p.val_y});
+  std::vector<G1Affine> fixed;
+  for (auto& g : cp.preprocessed) {
+    G1Affine a = G1Affine::identity();
+    bool id = true;
+    for (int i = 0; i < 32; i++) id = id && g.x.b[i] == 0 && g.y.b[i] == 0;
+    if (!id) {
+      if (!load_fq_canon(a.x, g.x) || !load_fq_canon(a.y, g.y) || !g1_on_curve(a)) {
+        delete pd;
+        return svk_fail(ctx, "protocol: preprocessed commitment is not a canonical on-curve point");
+      }
+    }
+    fixed.push_back(a);
+  }
+  fixed.push_back(ctx->dks[dk].g1);
+  auto conv = [&](const std::vector<svk_host::MsmTerm>& in) {
+    std::vector<MsmTermDev> out;
+    for (auto& t : in) {
+      MsmTermDev d;
+      if (t.base == SVK_BASE_G) { d.fixed = 1; d.base = (int32_t)pd->n_pre; }
+      else if (t.base < (int)pd->n_pre) { d.fixed = 1; d.base = t.base; }
+      else { d.fixed = 0; d.base = t.base - (int)pd->n_pre; }
+      d.slot = t.slot;
+      out.push_back(d);
+    }
+    return out;
+  };
+  std::vector<MsmTermDev> lhs = conv(cp.lhs), rhs = conv(cp.rhs);
+  pd->n_lhs = (u32)lhs.size();
+  pd->n_rhs = (u32)rhs.size();
+  if (upload(ctx, &pd->d_ops, cp.ops) || upload(ctx, &pd->d_aux, cp.aux) || upload(ctx, &pd->d_consts, cp.consts) ||
+      upload(ctx, &pd->d_sched, pd->points) || upload(ctx, &pd->d_lhs, lhs) || upload(ctx, &pd->d_rhs, rhs) || upload(ctx, &pd->d_fixed, fixed)) {
+    delete pd;
+    return -1;
+  }
+  ctx->protocols.push_back(pd);
+  return (int)ctx->protocols.size() - 1;
+}
+
+int svk_protocol_info(svk_ctx* ctx, int proto, uint32_t* out) {
+  if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
+  ProtocolDevice* pd = ctx->protocols[proto];
+  out[0] = pd->proof_len; out[1] = pd->n_instances; out[2] = pd->n_challenges; out[3] = pd->n_regs; out[4] = pd->n_ops;
+  out[5] = (u32)pd->n_perm; out[6] = pd->verify_valid ? 1 : 0; out[7] = (u32)pd->n_fr_mul; out[8] = pd->n_lhs; out[9] = pd->n_rhs;
+  out[10] = (u32)pd->points.size(); out[11] = pd->n_scalar_slots;
+  return 0;
+}
+
+int svk_plonk_succinct_verify_batch_dev(svk_ctx* ctx, int proto, size_t n, const void* d_instances, uint32_t n_instances,
+                                        const void* d_proofs, size_t proof_stride, const void* d_proof_lens, void* d_out_acc,
+                                        void* d_out_challenges, void* d_out_status) {
+  SVK_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
+  return svk_succinct_verify_launch(ctx, ctx->protocols[proto], n, (const uint8_t*)d_instances, n_instances, (const uint8_t*)d_proofs,
+                                    proof_stride, (const u32*)d_proof_lens, (uint8_t*)d_out_acc, (u32*)d_out_challenges,
+                                    (int32_t*)d_out_status);
+}
+
+int svk_plonk_succinct_verify_batch(svk_ctx* ctx, int proto, size_t n, const svk_fe* instances, uint32_t n_instances,
+                                    const uint8_t* proofs, size_t proof_stride, const uint32_t* proof_lens, svk_acc* out_acc,
+                                    svk_fe* out_challenges, int32_t* out_status) {
+  SVK_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
+  if (n == 0) return 0;
+  ProtocolDevice* pd = ctx->protocols[proto];
+  cudaStream_t s = ctx->stream;
+  size_t inst_bytes = n * (size_t)n_instances * 32, proof_bytes = n * proof_stride, chal_bytes = n * (size_t)pd->n_challenges * 32;
+  uint8_t* d_io;
+  size_t off_inst = 0, off_proofs = (inst_bytes + 255) / 256 * 256, off_lens = off_proofs + (proof_bytes + 255) / 256 * 256,
+         off_acc = off_lens + (n * 4 + 255) / 256 * 256, off_chal = off_acc + n * 128, off_status = off_chal + (chal_bytes + 255) / 256 * 256,
+         total = off_status + n * 4;
+  if (svk_scratch(ctx, 0, total, (void**)&d_io)) return -1;
+  if (inst_bytes) SVK_CUDA(ctx, cudaMemcpyAsync(d_io + off_inst, instances, inst_bytes, cudaMemcpyHostToDevice, s));
+  SVK_CUDA(ctx, cudaMemcpyAsync(d_io + off_proofs, proofs, proof_bytes, cudaMemcpyHostToDevice, s));
+  if (proof_lens) SVK_CUDA(ctx, cudaMemcpyAsync(d_io + off_lens, proof_lens, n * 4, cudaMemcpyHostToDevice, s));
+  if (svk_succinct_verify_launch(ctx, pd, n, d_io + off_inst, n_instances, d_io + off_proofs, proof_stride,
+                                 proof_lens ? (const u32*)(d_io + off_lens) : nullptr, d_io + off_acc, (u32*)(d_io + off_chal),
+                                 (int32_t*)(d_io + off_status)))
+    return -1;
+  SVK_CUDA(ctx, cudaMemcpyAsync(out_acc, d_io + off_acc, n * 128, cudaMemcpyDeviceToHost, s));
+  if (out_challenges && chal_bytes) SVK_CUDA(ctx, cudaMemcpyAsync(out_challenges, d_io + off_chal, chal_bytes, cudaMemcpyDeviceToHost, s));
+  SVK_CUDA(ctx, cudaMemcpyAsync(out_status, d_io + off_status, n * 4, cudaMemcpyDeviceToHost, s));
+  SVK_CUDA(ctx, cudaStreamSynchronize(s));
   return 0;
 }
 

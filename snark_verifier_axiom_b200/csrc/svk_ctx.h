@@ -9,6 +9,7 @@
 
 #include "../../include/svk.h"
 #include "pairing.cuh"
+#include "poseidon.cuh"
 
 struct DkDevice {
   G2Line* d_lines_g2 = nullptr;       // SVK_N_LINES
@@ -25,6 +26,8 @@ struct svk_ctx {
   uint64_t launches = 0;
   int sm_count = 0;
   PairingConsts* d_pairing_consts = nullptr;
+  PoseidonConsts* d_poseidon = nullptr;
+  PoseidonConsts h_poseidon;
   std::vector<DkDevice> dks;
   // scratch buffers (grown on demand, reused across calls)
   void* scratch[8] = {nullptr};

@@ -1,0 +1,210 @@
+// K1/K2 kernels: batched `PlonkSuccinctVerifier::{read_proof, verify}`
+// (snark-verifier/src/verifier/plonk.rs:32-93) for N proofs of ONE protocol.
+//
+//   k_decompress   : every G1 point of every proof: halo2curves `G1Affine::from_bytes` (Fq sqrt) +
+//                    the [x mod r, y mod r] transcript encoding (transcript/halo2.rs:214-226, 247-260)
+//   k_tape         : one proof per thread runs the compiled verifier tape (tape.cuh)
+//   k_proof_msm    : the final `lhs.evaluate(Some(g))` / `rhs.evaluate(Some(g))` (util/msm.rs:70-77 ->
+//                    NativeLoader::multi_scalar_multiplication, loader/native.rs:61-71) with a group of
+//                    16 lanes per proof, windowed scalar multiplication per term, warp-shuffle
+//                    reduction of the partial sums, to_affine.
+//   k_status       : per-proof `Result` -> status word (include/svk.h)
+#include "compiler.h"
+#include "g1.cuh"
+#include "svk_ctx.h"
+#include "svk_protocol.h"
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_decompress(size_t n_items, u32 n_points, const PointSched* sched, const uint8_t* proofs,
+                                                    size_t proof_stride, const u32* proof_lens, u32* regs, G1Affine* pts, u32* err) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_items * n_points) return;
+  size_t item = idx % n_items;
+  u32 pi = (u32)(idx / n_items);
+  PointSched s = sched[pi];
+  u32 len = proof_lens ? proof_lens[item] : (u32)proof_stride;
+  G1Affine pt = G1Affine::identity();
+  Fr fx = Fr::zero(), fy = Fr::zero();
+  if (s.byte_offset + 32 > len) {
+    atomicMin(&err[item], (s.byte_offset << 8) | SVK_T_EOF);
+  } else {
+    u32 xc[8], yc[8];
+    int rc = g1_decompress(proofs + item * proof_stride + s.byte_offset, pt, xc, yc);
+    if (rc == 1) atomicMin(&err[item], (s.byte_offset << 8) | SVK_T_POINT_INVALID);
+    else if (rc == 2) atomicMin(&err[item], (s.byte_offset << 8) | SVK_T_POINT_IDENTITY);
+    else {
+      fq_canon_to_fr_canon(fx.v, xc);
+      fq_canon_to_fr_canon(fy.v, yc);
+      fx = fx.to_mont();
+      fy = fy.to_mont();
+    }
+  }
+  RegFile rf{regs, n_items, item};
+  rf.store(s.reg_x, fx);
+  rf.store(s.reg_y, fy);
+  pts[(size_t)pi * n_items + item] = pt;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_tape(size_t n_items, const TapeOp* ops, u32 n_ops, const uint16_t* aux, const Fr* consts,
+                                             const PoseidonConsts* pk, u32* regs, const uint8_t* proofs, size_t proof_stride,
+                                             const u32* proof_lens, const uint8_t* instances, u32 n_instances, u32* out_scalars,
+                                             u32* out_challenges, u32 n_challenges, u32* err) {
+  size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= n_items) return;
+  RegFile rf{regs, n_items, item};
+  TapeIo io;
+  io.proof = proofs + item * proof_stride;
+  io.proof_len = proof_lens ? proof_lens[item] : (u32)proof_stride;
+  io.instances = instances + item * (size_t)n_instances * 32;
+  io.n_instances = n_instances;
+  io.out_scalars = out_scalars;
+  io.out_challenges = out_challenges;
+  io.n_challenge_slots = n_challenges;
+  PoseidonState st;
+  poseidon_init(st, *pk);
+  u32 e = SVK_NO_ERR;
+  tape_exec(ops, 0, n_ops, aux, consts, *pk, rf, io, st, e);
+  if (e != SVK_NO_ERR) atomicMin(&err[item], e);
+}
+
+// ------------------------------------------------------------------------------------------------
+#define MSM_LANES 16
+
+__device__ __forceinline__ G1Jac shfl_down_jac(const G1Jac& p, int delta) {
+  G1Jac r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.X.v[i] = __shfl_down_sync(0xffffffffu, p.X.v[i], delta, MSM_LANES);
+    r.Y.v[i] = __shfl_down_sync(0xffffffffu, p.Y.v[i], delta, MSM_LANES);
+    r.Z.v[i] = __shfl_down_sync(0xffffffffu, p.Z.v[i], delta, MSM_LANES);
+  }
+  return r;
+}
+
+// s * P with 4-bit fixed windows; uniform control flow across lanes (table lookup instead of a branch).
+__device__ __noinline__ G1Jac g1_mul_window4(const G1Affine& p, const u32* k) {
+  G1Jac tbl[16];
+  tbl[0] = G1Jac::identity();
+  tbl[1] = G1Jac::from_affine(p);
+  tbl[2] = tbl[1].dbl();
+  for (int i = 3; i < 16; i++) tbl[i] = tbl[i - 1].add_affine(p);
+  G1Jac acc = G1Jac::identity();
+  for (int w = 63; w >= 0; w--) {
+    if (w != 63) acc = acc.dbl().dbl().dbl().dbl();
+    u32 d = (k[w >> 3] >> ((w & 7) * 4)) & 0xf;
+    acc = acc.add(tbl[d]);
+  }
+  return acc;
+}
+
+// terms: which = blockIdx.y (0 lhs, 1 rhs).  Output: out_acc[item] (svk_acc, canonical LE).
+__global__ void __launch_bounds__(128) k_proof_msm(size_t n_items, const MsmTermDev* terms_lhs, u32 n_lhs, const MsmTermDev* terms_rhs,
+                                                   u32 n_rhs, const G1Affine* fixed_bases, const G1Affine* pts, const u32* scalars,
+                                                   const u32* err, uint8_t* out_acc) {
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t item = gid / MSM_LANES;
+  u32 lane = (u32)(gid % MSM_LANES);
+  bool active = item < n_items;
+  size_t it = active ? item : n_items - 1;  // keep whole warps in the shuffles
+  const MsmTermDev* terms = blockIdx.y ? terms_rhs : terms_lhs;
+  u32 n_terms = blockIdx.y ? n_rhs : n_lhs;
+  bool bad = err[it] != SVK_NO_ERR;
+  G1Jac acc = G1Jac::identity();
+  if (!bad) {
+    for (u32 t = lane; t < n_terms; t += MSM_LANES) {
+      MsmTermDev td = terms[t];
+      G1Affine base = td.fixed ? fixed_bases[td.base] : pts[(size_t)td.base * n_items + it];
+      if (td.slot < 0) {
+        acc = acc.add_affine(base);
+      } else {
+        u32 k[8];
+        const uint4* sp = reinterpret_cast<const uint4*>(scalars + ((size_t)td.slot * n_items + it) * 8);
+        uint4 lo = sp[0], hi = sp[1];
+        k[0] = lo.x; k[1] = lo.y; k[2] = lo.z; k[3] = lo.w; k[4] = hi.x; k[5] = hi.y; k[6] = hi.z; k[7] = hi.w;
+        acc = acc.add(g1_mul_window4(base, k));
+      }
+    }
+  }
+#pragma unroll
+  for (int d = MSM_LANES / 2; d >= 1; d >>= 1) {
+    G1Jac o = shfl_down_jac(acc, d);
+    if (lane < (u32)d) acc = acc.add(o);
+  }
+  if (active && lane == 0) {
+    G1Affine a = bad ? G1Affine::identity() : acc.to_affine();
+    Fq x = a.x.from_mont(), y = a.y.from_mont();
+    uint4* o = reinterpret_cast<uint4*>(out_acc + item * 128 + (blockIdx.y ? 64 : 0));
+    o[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+    o[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+    o[2] = make_uint4(y.v[0], y.v[1], y.v[2], y.v[3]);
+    o[3] = make_uint4(y.v[4], y.v[5], y.v[6], y.v[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mode: 0 normal, 1 InvalidInstances for all, 2 InvalidProtocol unless the read failed
+__global__ void k_status(size_t n_items, const u32* err, int mode, int32_t* status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_items) return;
+  u32 e = err[i];
+  int32_t s = SVK_OK;
+  if (mode == 1) s = SVK_INVALID_INSTANCES;
+  else if (e != SVK_NO_ERR) s = ((e & 0xff) == 0) ? SVK_INVALID_INSTANCES : (SVK_TRANSCRIPT | (int32_t)((e & 0xff) << 8));
+  else if (mode == 2) s = SVK_INVALID_PROTOCOL;
+  status[i] = s;
+}
+
+__global__ void k_fill_u32(size_t n, u32* p, u32 v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const uint8_t* d_instances, u32 n_instances_given,
+                               const uint8_t* d_proofs, size_t proof_stride, const u32* d_proof_lens, uint8_t* d_out_acc,
+                               u32* d_out_challenges, int32_t* d_out_status) {
+  if (n == 0) return 0;
+  cudaStream_t s = ctx->stream;
+  u32 *d_err, *d_regs, *d_scalars, *d_chal_scratch;
+  G1Affine* d_pts;
+  size_t n_pts = pd->points.size();
+  if (svk_scratch(ctx, 2, n * 4, (void**)&d_err)) return -1;
+  if (svk_scratch(ctx, 3, (size_t)pd->n_regs * n * 32 + 32, (void**)&d_regs)) return -1;
+  if (svk_scratch(ctx, 4, n_pts * n * sizeof(G1Affine) + 64, (void**)&d_pts)) return -1;
+  if (svk_scratch(ctx, 5, (size_t)pd->n_scalar_slots * n * 32 + 32, (void**)&d_scalars)) return -1;
+  if (!d_out_challenges) {
+    if (svk_scratch(ctx, 6, (size_t)pd->n_challenges * n * 32 + 32, (void**)&d_chal_scratch)) return -1;
+    d_out_challenges = d_chal_scratch;
+  }
+  unsigned b = 256;
+  k_fill_u32<<<(unsigned)((n + b - 1) / b), b, 0, s>>>(n, d_err, SVK_NO_ERR);
+  ctx->launches++;
+  int mode = 0;
+  if (n_instances_given != pd->n_instances) mode = 1;  // proof.rs:66-69
+  else if (!pd->verify_valid) mode = 2;
+  if (mode != 1) {
+    if (n_pts) {
+      size_t total = n * n_pts;
+      k_decompress<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(n, (u32)n_pts, pd->d_sched, d_proofs, proof_stride, d_proof_lens, d_regs,
+                                                                  d_pts, d_err);
+      ctx->launches++;
+    }
+    u32 n_ops = pd->verify_valid ? pd->n_ops : pd->read_ops_end;
+    k_tape<<<(unsigned)((n + 31) / 32), 32, 0, s>>>(n, pd->d_ops, n_ops, pd->d_aux, pd->d_consts, ctx->d_poseidon, d_regs, d_proofs, proof_stride,
+                                                   d_proof_lens, d_instances, pd->n_instances, d_scalars, d_out_challenges, pd->n_challenges,
+                                                   d_err);
+    ctx->launches++;
+  }
+  if (mode == 0) {
+    dim3 grid((unsigned)((n * MSM_LANES + 127) / 128), 2);
+    k_proof_msm<<<grid, 128, 0, s>>>(n, pd->d_lhs, pd->n_lhs, pd->d_rhs, pd->n_rhs, pd->d_fixed, d_pts, d_scalars, d_err, d_out_acc);
+    ctx->launches++;
+  } else {
+    SVK_CUDA(ctx, cudaMemsetAsync(d_out_acc, 0, n * 128, s));
+  }
+  k_status<<<(unsigned)((n + b - 1) / b), b, 0, s>>>(n, d_err, mode, d_out_status);
+  ctx->launches++;
+  SVK_CUDA(ctx, cudaGetLastError());
+  return 0;
+}

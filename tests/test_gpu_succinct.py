@@ -1,0 +1,95 @@
+"""GPU parity: svk_plonk_succinct_verify_batch vs the oracle's PlonkSuccinctVerifier
+(snark-verifier/src/verifier/plonk.rs:32-93) on trapdoor-forged StandardPlonk k=8 proofs:
+transcript challenges, accumulators and per-proof status, SHPLONK and GWC."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import api, forge
+from oracle.transcript import VerifyError
+
+from .util import dk_bytes, g1_from, np_u8, ptr, to_product_protocol
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    from snark_verifier_axiom_b200._lib import lib
+
+    L = lib()
+    c = ctypes.c_void_p()
+    assert L.svk_create(0, ctypes.byref(c)) == 0, L.svk_last_error(None)
+    S = forge.Setup(0)
+    kid = L.svk_dk_load(c, dk_bytes(S.dk))
+    assert kid >= 0
+    blob = to_product_protocol(S.protocol).to_bytes()
+    yield L, c, S, kid, blob
+    L.svk_destroy(c)
+
+
+def oracle_result(S, inst, pf, scheme):
+    try:
+        accs, proof = api.succinct_verify(S.dk.svk, S.protocol, inst, pf, scheme, want_proof=True)
+    except VerifyError as e:
+        return api.STATUS[e.kind], None, None
+    ch = [c.v for c in proof.challenges] + [proof.z.v]
+    if scheme == "bdfg21":
+        ch += [proof.pcs.mu.v, proof.pcs.gamma.v, proof.pcs.z_prime.v]
+    else:
+        ch += [proof.pcs.v.v, proof.pcs.u.v]
+    return 0, (accs[0].lhs.pt, accs[0].rhs.pt), ch
+
+
+@pytest.mark.parametrize("scheme,mos", [("bdfg21", 0), ("gwc19", 1)])
+def test_succinct_verify_matches_oracle(env, scheme, mos):
+    L, c, S, kid, blob = env
+    pid = L.svk_protocol_compile(c, blob, len(blob), mos, kid)
+    assert pid >= 0, L.svk_last_error(c)
+    info = (ctypes.c_uint32 * 12)()
+    assert L.svk_protocol_info(c, pid, info) == 0
+    plen, n_inst, n_ch = info[0], info[1], info[2]
+    assert plen == (896 if scheme == "bdfg21" else 928) and n_inst == 1
+    n = 37  # ragged vs the 16-lane groups / 32-thread blocks
+    insts, proofs = forge.forge_batch(S, scheme, n, seed0=100)
+    proofs = [bytearray(p) for p in proofs]
+    # corruptions: evaluation flip (still decodes), scalar >= r, invalid point, identity point
+    proofs[3][9 * 32 + 5] ^= 1
+    proofs[5][9 * 32 : 10 * 32] = b"\xff" * 32
+    from oracle import bn254
+
+    bad_x = next(x for x in range(1, 100) if not bn254.g1_from_bytes(x.to_bytes(32, "little"))[0])
+    proofs[7][0:32] = bad_x.to_bytes(32, "little")  # x^3 + 3 is a non-residue -> invalid point encoding
+    proofs[9][32:64] = bytes(32)
+    stride = plen + 32  # trailing bytes are ignored
+    buf = np.zeros((n, stride), dtype=np.uint8)
+    for i, p in enumerate(proofs):
+        buf[i, :plen] = np.frombuffer(bytes(p), dtype=np.uint8)
+        buf[i, plen:] = 0xAB
+    inst_buf = np_u8(b"".join(int(x).to_bytes(32, "little") for col in insts for x in col[0]))
+    out_acc = np.zeros((n, 128), dtype=np.uint8)
+    out_ch = np.zeros((n, n_ch, 32), dtype=np.uint8)
+    out_st = np.full(n, -7, dtype=np.int32)
+    rc = L.svk_plonk_succinct_verify_batch(c, pid, n, ptr(inst_buf), 1, ptr(buf), stride, None, ptr(out_acc), ptr(out_ch), ptr(out_st))
+    assert rc == 0, L.svk_last_error(c)
+    for i in range(n):
+        st, acc, ch = oracle_result(S, insts[i], bytes(proofs[i]), scheme)
+        assert (out_st[i] & 0xFF) == st, (i, out_st[i], st)
+        if st == 0:
+            got = (g1_from(out_acc[i, :64].tobytes()), g1_from(out_acc[i, 64:].tobytes()))
+            assert got == acc, i
+            got_ch = [int.from_bytes(out_ch[i, j].tobytes(), "little") for j in range(n_ch)]
+            assert got_ch == ch, i
+        else:
+            assert not out_acc[i].any()
+    # short proofs -> Transcript(EOF); wrong instance count -> InvalidInstances for all
+    lens = np.full(n, plen, dtype=np.uint32)
+    lens[2] = plen - 1
+    lens[4] = 40
+    rc = L.svk_plonk_succinct_verify_batch(c, pid, n, ptr(inst_buf), 1, ptr(buf), stride, ptr(lens), ptr(out_acc), ptr(out_ch), ptr(out_st))
+    assert rc == 0
+    assert (out_st[2] & 0xFF) == 4 and (out_st[2] >> 8) == 1 and (out_st[4] & 0xFF) == 4 and out_st[0] == 0
+    inst2 = np.zeros(n * 2 * 32, dtype=np.uint8)
+    rc = L.svk_plonk_succinct_verify_batch(c, pid, n, ptr(inst2), 2, ptr(buf), stride, None, ptr(out_acc), ptr(out_ch), ptr(out_st))
+    assert rc == 0 and (out_st == 1).all()
