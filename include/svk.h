@@ -94,6 +94,34 @@ int svk_plonk_succinct_verify_batch_dev(svk_ctx* ctx, int proto, size_t n, const
                                         const void* d_proofs, size_t proof_stride, const void* d_proof_lens, void* d_out_acc,
                                         void* d_out_challenges, void* d_out_status);
 
+/* ---- KzgAs accumulation (pcs/kzg/accumulation.rs:17-63, 97-137, 139-196) ------------------------
+ * `KzgAs::create_proof` / `read_proof`+`verify` with `KzgAsProvingKey::default()` (zk = false, the
+ * SDK's use at snark-verifier-sdk/src/halo2/aggregation.rs:235-245): a fresh Poseidon transcript
+ * absorbs every accumulator, r = squeeze, out = (sum r^i lhs_i, sum r^i rhs_i).
+ * group_size 0 (or >= n): exactly that flat fold.  group_size m >= 2: consecutive groups of m are
+ * folded independently (fresh transcript each), then the group results, until one remains.
+ * out_r: challenge of the last (root) fold call.  out_status: 0, or SVK_TRANSCRIPT|sub<<8 when an
+ * accumulator point is the identity / not a canonical curve point (reference: Err / unrepresentable). */
+int svk_kzg_as_fold(svk_ctx* ctx, size_t n, const svk_acc* accs, size_t group_size, svk_acc* out_acc, svk_fe* out_r,
+                    int32_t* out_status);
+int svk_kzg_as_fold_dev(svk_ctx* ctx, size_t n, const void* d_accs, size_t group_size, void* d_out_acc, void* d_out_r,
+                        void* d_out_status);
+
+/* ---- PlonkVerifier::verify (verifier/plonk.rs:98-135) over a batch: succinct-verify every proof,
+ * fold the accumulators (above), decide the folded accumulator with ONE pairing.
+ * out_ok = 1 iff every proof's status is 0 and the folded accumulator is accepted.
+ * locate_failures != 0: when all proofs read fine but the folded pairing fails, every accumulator is
+ * decided on its own and the offenders get SVK_ASSERTION_FAILURE (what per-proof
+ * `PlonkVerifier::verify` would have returned).
+ * _dev: d_out_accs n*128 B, d_out_status n*4 B, d_out_folded 256 B =
+ *       { svk_acc folded; svk_fe r; int32 fold_status; uint8 decide_ok; uint8 ok }. */
+int svk_plonk_verify_batch(svk_ctx* ctx, int proto, size_t n, const svk_fe* instances, uint32_t n_instances, const uint8_t* proofs,
+                           size_t proof_stride, const uint32_t* proof_lens, size_t group_size, int locate_failures,
+                           int32_t* out_status, svk_acc* out_folded, uint8_t* out_ok);
+int svk_plonk_verify_batch_dev(svk_ctx* ctx, int proto, size_t n, const void* d_instances, uint32_t n_instances, const void* d_proofs,
+                               size_t proof_stride, const void* d_proof_lens, size_t group_size, void* d_out_accs, void* d_out_status,
+                               void* d_out_folded);
+
 /* ---- micro-benchmark of the integer-multiply roofline (DESIGN.md "IMAD peak") ------------------
  * Runs `iters` dependent Montgomery multiplications per thread on every SM; returns modmul/s. */
 int svk_bench_modmul_peak(svk_ctx* ctx, int iters, double* out_modmul_per_s, double* out_ms);

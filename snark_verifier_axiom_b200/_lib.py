@@ -33,6 +33,10 @@ def _load():
     lib.svk_protocol_info.argtypes = [vp, i32, u32p]
     lib.svk_plonk_succinct_verify_batch.argtypes = [vp, i32, sz, vp, ctypes.c_uint32, vp, sz, vp, vp, vp, vp]
     lib.svk_plonk_succinct_verify_batch_dev.argtypes = [vp, i32, sz, vp, ctypes.c_uint32, vp, sz, vp, vp, vp, vp]
+    lib.svk_kzg_as_fold.argtypes = [vp, sz, vp, sz, vp, vp, vp]
+    lib.svk_kzg_as_fold_dev.argtypes = [vp, sz, vp, sz, vp, vp, vp]
+    lib.svk_plonk_verify_batch.argtypes = [vp, i32, sz, vp, ctypes.c_uint32, vp, sz, vp, sz, i32, vp, vp, vp]
+    lib.svk_plonk_verify_batch_dev.argtypes = [vp, i32, sz, vp, ctypes.c_uint32, vp, sz, vp, sz, vp, vp, vp]
     lib.svk_bench_modmul_peak.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     return lib
 

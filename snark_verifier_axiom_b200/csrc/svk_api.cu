@@ -9,6 +9,9 @@
 
 int svk_decide_launch(svk_ctx* ctx, int dk, size_t n, const void* d_accs, void* d_ok);
 int svk_modmul_peak_launch(svk_ctx* ctx, int iters, double* out_rate, double* out_ms);
+int svk_fold_launch(svk_ctx* ctx, size_t n, const uint8_t* d_accs, size_t group_size, uint8_t* d_out_acc, u32* d_out_r, int32_t* d_status);
+int svk_batch_verdict_launch(svk_ctx* ctx, size_t n, const int32_t* d_status, const int32_t* d_fold_status, const uint8_t* d_decide_ok,
+                             uint8_t* d_out_ok);
 int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const uint8_t* d_instances, u32 n_instances_given,
                                const uint8_t* d_proofs, size_t proof_stride, const u32* d_proof_lens, uint8_t* d_out_acc,
                                u32* d_out_challenges, int32_t* d_out_status);
@@ -65,7 +68,7 @@ void svk_destroy(svk_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto& k : ctx->dks) { cudaFree(k.d_lines_g2); cudaFree(k.d_lines_neg_sg2); }
-  for (int i = 0; i < 8; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+  for (int i = 0; i < 16; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   cudaFree(ctx->d_pairing_consts);
   cudaFree(ctx->d_poseidon);
   for (auto* p : ctx->protocols) {
@@ -248,6 +251,87 @@ int svk_plonk_succinct_verify_batch(svk_ctx* ctx, int proto, size_t n, const svk
   if (out_challenges && chal_bytes) SVK_CUDA(ctx, cudaMemcpyAsync(out_challenges, d_io + off_chal, chal_bytes, cudaMemcpyDeviceToHost, s));
   SVK_CUDA(ctx, cudaMemcpyAsync(out_status, d_io + off_status, n * 4, cudaMemcpyDeviceToHost, s));
   SVK_CUDA(ctx, cudaStreamSynchronize(s));
+  return 0;
+}
+
+// ---- KzgAs fold ------------------------------------------------------------------------------------
+int svk_kzg_as_fold_dev(svk_ctx* ctx, size_t n, const void* d_accs, size_t group_size, void* d_out_acc, void* d_out_r, void* d_out_status) {
+  SVK_CUDA(ctx, cudaSetDevice(ctx->device));
+  return svk_fold_launch(ctx, n, (const uint8_t*)d_accs, group_size, (uint8_t*)d_out_acc, (u32*)d_out_r, (int32_t*)d_out_status);
+}
+
+int svk_kzg_as_fold(svk_ctx* ctx, size_t n, const svk_acc* accs, size_t group_size, svk_acc* out_acc, svk_fe* out_r, int32_t* out_status) {
+  SVK_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (n == 0) return svk_fail(ctx, "fold of zero accumulators");
+  uint8_t* d;
+  if (svk_scratch(ctx, 0, n * 128 + 256, (void**)&d)) return -1;
+  uint8_t* d_out = d + n * 128;  // 128 acc + 32 r + 4 status
+  cudaStream_t s = ctx->stream;
+  SVK_CUDA(ctx, cudaMemcpyAsync(d, accs, n * 128, cudaMemcpyHostToDevice, s));
+  if (svk_fold_launch(ctx, n, d, group_size, d_out, (u32*)(d_out + 128), (int32_t*)(d_out + 160))) return -1;
+  SVK_CUDA(ctx, cudaMemcpyAsync(out_acc, d_out, 128, cudaMemcpyDeviceToHost, s));
+  if (out_r) SVK_CUDA(ctx, cudaMemcpyAsync(out_r, d_out + 128, 32, cudaMemcpyDeviceToHost, s));
+  SVK_CUDA(ctx, cudaMemcpyAsync(out_status, d_out + 160, 4, cudaMemcpyDeviceToHost, s));
+  SVK_CUDA(ctx, cudaStreamSynchronize(s));
+  return 0;
+}
+
+// ---- PlonkVerifier::verify over a batch: succinct verify each, fold, ONE pairing -------------------
+// d_work: >= n*128 (accumulators) + 512 bytes of device scratch owned by the caller of the _dev variant
+int svk_plonk_verify_batch_dev(svk_ctx* ctx, int proto, size_t n, const void* d_instances, uint32_t n_instances, const void* d_proofs,
+                               size_t proof_stride, const void* d_proof_lens, size_t group_size, void* d_out_accs, void* d_out_status,
+                               void* d_out_folded /* 128 acc + 32 r + 4 fold status + 1 decide + 1 ok */) {
+  SVK_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
+  if (n == 0) return svk_fail(ctx, "empty batch");
+  ProtocolDevice* pd = ctx->protocols[proto];
+  uint8_t* f = (uint8_t*)d_out_folded;
+  if (svk_succinct_verify_launch(ctx, pd, n, (const uint8_t*)d_instances, n_instances, (const uint8_t*)d_proofs, proof_stride,
+                                 (const u32*)d_proof_lens, (uint8_t*)d_out_accs, nullptr, (int32_t*)d_out_status))
+    return -1;
+  if (svk_fold_launch(ctx, n, (const uint8_t*)d_out_accs, group_size, f, (u32*)(f + 128), (int32_t*)(f + 160))) return -1;
+  if (svk_decide_launch(ctx, pd->dk, 1, f, f + 164)) return -1;
+  return svk_batch_verdict_launch(ctx, n, (const int32_t*)d_out_status, (const int32_t*)(f + 160), f + 164, f + 165);
+}
+
+int svk_plonk_verify_batch(svk_ctx* ctx, int proto, size_t n, const svk_fe* instances, uint32_t n_instances, const uint8_t* proofs,
+                           size_t proof_stride, const uint32_t* proof_lens, size_t group_size, int locate_failures, int32_t* out_status,
+                           svk_acc* out_folded, uint8_t* out_ok) {
+  SVK_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
+  if (n == 0) return svk_fail(ctx, "empty batch");
+  cudaStream_t s = ctx->stream;
+  size_t inst_bytes = n * (size_t)n_instances * 32, proof_bytes = n * proof_stride;
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  size_t off_proofs = al(inst_bytes), off_lens = off_proofs + al(proof_bytes), off_accs = off_lens + al(n * 4), off_status = off_accs + n * 128,
+         off_fold = off_status + al(n * 4), off_dec = off_fold + 256, total = off_dec + al(n);
+  uint8_t* d;
+  if (svk_scratch(ctx, 0, total, (void**)&d)) return -1;
+  if (inst_bytes) SVK_CUDA(ctx, cudaMemcpyAsync(d, instances, inst_bytes, cudaMemcpyHostToDevice, s));
+  SVK_CUDA(ctx, cudaMemcpyAsync(d + off_proofs, proofs, proof_bytes, cudaMemcpyHostToDevice, s));
+  if (proof_lens) SVK_CUDA(ctx, cudaMemcpyAsync(d + off_lens, proof_lens, n * 4, cudaMemcpyHostToDevice, s));
+  if (svk_plonk_verify_batch_dev(ctx, proto, n, d, n_instances, d + off_proofs, proof_stride, proof_lens ? d + off_lens : nullptr, group_size,
+                                 d + off_accs, d + off_status, d + off_fold))
+    return -1;
+  uint8_t folded[256];
+  SVK_CUDA(ctx, cudaMemcpyAsync(out_status, d + off_status, n * 4, cudaMemcpyDeviceToHost, s));
+  SVK_CUDA(ctx, cudaMemcpyAsync(folded, d + off_fold, 256, cudaMemcpyDeviceToHost, s));
+  SVK_CUDA(ctx, cudaStreamSynchronize(s));
+  if (out_folded) memcpy(out_folded, folded, 128);
+  *out_ok = folded[165];
+  if (!*out_ok && locate_failures) {
+    // every proof read fine but the folded pairing failed: decide each accumulator to name the culprits
+    bool all_ok = true;
+    for (size_t i = 0; i < n; i++) all_ok = all_ok && out_status[i] == 0;
+    if (all_ok) {
+      std::vector<uint8_t> oks(n);
+      if (svk_decide_launch(ctx, ctx->protocols[proto]->dk, n, d + off_accs, d + off_dec)) return -1;
+      SVK_CUDA(ctx, cudaMemcpyAsync(oks.data(), d + off_dec, n, cudaMemcpyDeviceToHost, s));
+      SVK_CUDA(ctx, cudaStreamSynchronize(s));
+      for (size_t i = 0; i < n; i++)
+        if (!oks[i]) out_status[i] = SVK_ASSERTION_FAILURE;
+    }
+  }
   return 0;
 }
 

@@ -1,0 +1,275 @@
+"""Host-side mirror of the reference's verification call surface, over libsvk (include/svk.h).
+
+Mirrored names (reference file:line):
+  KzgSuccinctVerifyingKey, KzgDecidingKey   snark-verifier/src/pcs/kzg.rs:21-37, pcs/kzg/decider.rs:6-36
+  KzgAccumulator                            snark-verifier/src/pcs/kzg/accumulator.rs:6-26
+  KzgAs.{create_proof, decide, decide_all}  snark-verifier/src/pcs/kzg/accumulation.rs:139-196, decider.rs:60-81
+  PlonkSuccinctVerifier / PlonkVerifier     snark-verifier/src/verifier/plonk.rs:32-135
+  Snark, SHPLONK, GWC                       snark-verifier-sdk/src/lib.rs:38-60
+  Error                                     snark-verifier/src/lib.rs:21-30
+The unit of work is a BATCH of snarks of one protocol (the B200 is a throughput device); a batch of
+one reproduces the reference's single-proof calls.  numpy arrays are host buffers; the `*_dev`
+methods take torch CUDA tensors (device memory + streams are PyTorch's job, nothing else is).
+"""
+import ctypes
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ._lib import SvkError, lib
+from .protocol import PlonkProtocol
+
+SHPLONK = BDFG21 = 0
+GWC = GWC19 = 1
+
+STATUS_NAMES = {0: "Ok", 1: "InvalidInstances", 2: "InvalidProtocol", 3: "AssertionFailure", 4: "Transcript"}
+
+
+class Error(Exception):
+    """snark-verifier/src/lib.rs:21-30"""
+
+    def __init__(self, status: int):
+        self.status = int(status)
+        self.kind = STATUS_NAMES.get(self.status & 0xFF, "Unknown")
+        super().__init__(f"{self.kind} (status 0x{self.status:x})")
+
+
+def _fe(v: int) -> bytes:
+    return int(v).to_bytes(32, "little")
+
+
+def _g1_bytes(pt) -> bytes:
+    return bytes(64) if pt is None else _fe(pt[0]) + _fe(pt[1])
+
+
+def _g1_from(b: bytes):
+    x, y = int.from_bytes(b[:32], "little"), int.from_bytes(b[32:64], "little")
+    return None if x == 0 and y == 0 else (x, y)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(ctypes.c_void_p)
+    return ctypes.c_void_p(a.data_ptr())  # torch tensor
+
+
+@dataclass
+class KzgSuccinctVerifyingKey:
+    g: Tuple[int, int]
+
+
+@dataclass
+class KzgDecidingKey:
+    svk: KzgSuccinctVerifyingKey
+    g2: Tuple[Tuple[int, int], Tuple[int, int]]
+    s_g2: Tuple[Tuple[int, int], Tuple[int, int]]
+
+    @classmethod
+    def new(cls, g1, g2, s_g2):
+        return cls(KzgSuccinctVerifyingKey(g1), g2, s_g2)
+
+    def to_bytes(self) -> bytes:
+        def g2b(q):
+            return _fe(q[0][0]) + _fe(q[0][1]) + _fe(q[1][0]) + _fe(q[1][1])
+
+        return _g1_bytes(self.svk.g) + g2b(self.g2) + g2b(self.s_g2)
+
+
+@dataclass
+class KzgAccumulator:
+    lhs: Optional[Tuple[int, int]]
+    rhs: Optional[Tuple[int, int]]
+
+    def to_bytes(self) -> bytes:
+        return _g1_bytes(self.lhs) + _g1_bytes(self.rhs)
+
+    @classmethod
+    def from_bytes(cls, b: bytes):
+        return cls(_g1_from(b[:64]), _g1_from(b[64:128]))
+
+
+@dataclass
+class Snark:
+    """snark-verifier-sdk/src/lib.rs:44-60 (the protocol is shared by the batch)"""
+
+    instances: List[List[int]]
+    proof: bytes
+
+
+class Context:
+    """One GPU + one stream (`svk_ctx`).  Raises SvkError when no B200 is present."""
+
+    def __init__(self, device: int = 0):
+        self._L = lib()
+        self._c = ctypes.c_void_p()
+        if self._L.svk_create(device, ctypes.byref(self._c)) != 0:
+            raise SvkError(self._L.svk_last_error(None).decode())
+        self.device = device
+
+    def close(self):
+        if self._c:
+            self._L.svk_destroy(self._c)
+            self._c = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise SvkError(self._L.svk_last_error(self._c).decode())
+        return rc
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self._L.svk_set_stream(self._c, ctypes.c_void_p(cuda_stream)))
+
+    def sync(self):
+        self._check(self._L.svk_sync(self._c))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.svk_launch_count(self._c))
+
+    def load_deciding_key(self, dk: KzgDecidingKey) -> int:
+        return self._check(self._L.svk_dk_load(self._c, dk.to_bytes()))
+
+    def compile_protocol(self, protocol: PlonkProtocol, mos: int, dk_id: int) -> int:
+        blob = protocol.to_bytes()
+        return self._check(self._L.svk_protocol_compile(self._c, blob, len(blob), mos, dk_id))
+
+    def protocol_info(self, pid: int) -> dict:
+        out = (ctypes.c_uint32 * 12)()
+        self._check(self._L.svk_protocol_info(self._c, pid, out))
+        keys = ["proof_len", "n_instances", "n_challenges", "n_regs", "n_ops", "n_poseidon_perms", "verify_valid", "n_fr_mul",
+                "n_lhs_terms", "n_rhs_terms", "n_points", "n_scalar_slots"]
+        return dict(zip(keys, [int(x) for x in out]))
+
+    def modmul_peak(self, iters: int = 4000):
+        rate, ms = ctypes.c_double(), ctypes.c_double()
+        self._check(self._L.svk_bench_modmul_peak(self._c, iters, ctypes.byref(rate), ctypes.byref(ms)))
+        return rate.value, ms.value
+
+
+class KzgAs:
+    """`KzgAs<Bn256, MOS>`: accumulation + deciding (the multi-open part lives in the compiled protocol)."""
+
+    def __init__(self, ctx: Context, dk: KzgDecidingKey):
+        self.ctx = ctx
+        self.dk = dk
+        self.dk_id = ctx.load_deciding_key(dk)
+
+    def create_proof(self, accumulators: Sequence[KzgAccumulator], group_size: int = 0):
+        """accumulation.rs:139-196 with zk = false -> (KzgAccumulator, r).  Raises Error like the
+        reference returns Err (identity point in an accumulator)."""
+        n = len(accumulators)
+        assert n > 0, "assert!(!instances.is_empty())"
+        buf = np.frombuffer(b"".join(a.to_bytes() for a in accumulators), dtype=np.uint8).copy()
+        out, r, st = np.zeros(128, np.uint8), np.zeros(32, np.uint8), np.zeros(1, np.int32)
+        L, c = self.ctx._L, self.ctx._c
+        self.ctx._check(L.svk_kzg_as_fold(c, n, _ptr(buf), group_size, _ptr(out), _ptr(r), _ptr(st)))
+        if st[0] != 0:
+            raise Error(st[0])
+        return KzgAccumulator.from_bytes(out.tobytes()), int.from_bytes(r.tobytes(), "little")
+
+    def decide_batch(self, accumulators: Sequence[KzgAccumulator]) -> List[bool]:
+        n = len(accumulators)
+        if n == 0:
+            return []
+        buf = np.frombuffer(b"".join(a.to_bytes() for a in accumulators), dtype=np.uint8).copy()
+        out = np.zeros(n, np.uint8)
+        self.ctx._check(self.ctx._L.svk_kzg_decide_batch(self.ctx._c, self.dk_id, n, _ptr(buf), _ptr(out)))
+        return [bool(x) for x in out]
+
+    def decide(self, accumulator: KzgAccumulator) -> None:
+        """decider.rs:60-68"""
+        if not self.decide_batch([accumulator])[0]:
+            raise Error(3)
+
+    def decide_all(self, accumulators: Sequence[KzgAccumulator]) -> None:
+        """decider.rs:70-81"""
+        assert len(accumulators) > 0, "assert!(!accumulators.is_empty())"
+        if not all(self.decide_batch(accumulators)):
+            raise Error(3)
+
+
+@dataclass
+class BatchResult:
+    ok: bool
+    status: np.ndarray  # int32 per proof
+    folded: Optional[KzgAccumulator]
+
+    def errors(self) -> List[Optional[Error]]:
+        return [None if s == 0 else Error(s) for s in self.status]
+
+
+class PlonkVerifier:
+    """`PlonkVerifier<KzgAs<Bn256, MOS>>` / `PlonkSuccinctVerifier<..>` for ONE protocol, over batches."""
+
+    def __init__(self, ctx: Context, dk: KzgDecidingKey, protocol: PlonkProtocol, mos: int = SHPLONK, kzg_as: Optional[KzgAs] = None):
+        self.ctx = ctx
+        self.kzg_as = kzg_as or KzgAs(ctx, dk)
+        self.mos = mos
+        self.pid = ctx.compile_protocol(protocol, mos, self.kzg_as.dk_id)
+        self.info = ctx.protocol_info(self.pid)
+        self.protocol = protocol
+
+    # ---- packing ------------------------------------------------------------------------------
+    def pack(self, snarks: Sequence[Snark]):
+        """-> (instances u8[n, n_inst*32], n_inst, proofs u8[n, stride], lens u32[n])"""
+        n = len(snarks)
+        n_inst = len([x for col in snarks[0].instances for x in col]) if n else 0
+        stride = max([len(s.proof) for s in snarks] + [32])
+        stride = (stride + 31) // 32 * 32
+        proofs = np.zeros((n, stride), np.uint8)
+        lens = np.zeros(n, np.uint32)
+        inst = np.zeros((n, max(n_inst, 1) * 32), np.uint8)
+        for i, s in enumerate(snarks):
+            flat = [x for col in s.instances for x in col]
+            if len(flat) != n_inst:
+                raise ValueError("all snarks of a batch must have the same instance shape")
+            proofs[i, : len(s.proof)] = np.frombuffer(s.proof, np.uint8)
+            lens[i] = len(s.proof)
+            if flat:
+                inst[i, : n_inst * 32] = np.frombuffer(b"".join(_fe(x) for x in flat), np.uint8)
+        return inst, n_inst, proofs, lens
+
+    # ---- PlonkSuccinctVerifier::{read_proof, verify} ------------------------------------------------
+    def succinct_verify(self, snarks: Sequence[Snark]):
+        """-> (accumulators [KzgAccumulator|None], challenges [[int]], status int32[n])"""
+        n = len(snarks)
+        inst, n_inst, proofs, lens = self.pack(snarks)
+        nch = self.info["n_challenges"]
+        acc = np.zeros((n, 128), np.uint8)
+        ch = np.zeros((n, max(nch, 1), 32), np.uint8)
+        st = np.zeros(n, np.int32)
+        L, c = self.ctx._L, self.ctx._c
+        self.ctx._check(L.svk_plonk_succinct_verify_batch(c, self.pid, n, _ptr(inst), n_inst, _ptr(proofs), proofs.shape[1], _ptr(lens),
+                                                          _ptr(acc), _ptr(ch), _ptr(st)))
+        accs = [KzgAccumulator.from_bytes(acc[i].tobytes()) if st[i] == 0 else None for i in range(n)]
+        chals = [[int.from_bytes(ch[i, j].tobytes(), "little") for j in range(nch)] for i in range(n)]
+        return accs, chals, st
+
+    # ---- PlonkVerifier::verify -----------------------------------------------------------------------
+    def verify(self, snarks: Sequence[Snark], group_size: int = 0, locate_failures: bool = True) -> BatchResult:
+        n = len(snarks)
+        inst, n_inst, proofs, lens = self.pack(snarks)
+        st = np.zeros(n, np.int32)
+        folded = np.zeros(128, np.uint8)
+        ok = np.zeros(1, np.uint8)
+        L, c = self.ctx._L, self.ctx._c
+        self.ctx._check(L.svk_plonk_verify_batch(c, self.pid, n, _ptr(inst), n_inst, _ptr(proofs), proofs.shape[1], _ptr(lens), group_size,
+                                                 1 if locate_failures else 0, _ptr(st), _ptr(folded), _ptr(ok)))
+        return BatchResult(bool(ok[0]), st, KzgAccumulator.from_bytes(folded.tobytes()) if ok[0] else None)
+
+    def verify_one(self, snark: Snark) -> None:
+        """The reference's single-proof `PlonkVerifier::verify(..)` -> Ok(()) or raises Error."""
+        r = self.verify([snark])
+        if r.status[0] != 0:
+            raise Error(r.status[0])
+        if not r.ok:
+            raise Error(3)

@@ -1,0 +1,79 @@
+"""GPU parity: KzgAs fold (flat + tree) and the composed PlonkVerifier::verify over a batch, through
+the host-side mirror (snark_verifier_axiom_b200.verifier) -- reads like the reference's own use at
+snark-verifier-sdk/src/halo2/aggregation.rs:216-245 + decider.rs:60-68."""
+import pytest
+
+from oracle import api, forge
+
+from .util import to_product_protocol
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    from snark_verifier_axiom_b200 import verifier as V
+
+    S = forge.Setup(0)
+    ctx = V.Context(0)
+    dk = V.KzgDecidingKey.new(S.dk.svk.g, S.dk.g2, S.dk.s_g2)
+    AS = V.KzgAs(ctx, dk)
+    proto = to_product_protocol(S.protocol)
+    pv = {m: V.PlonkVerifier(ctx, dk, proto, m, kzg_as=AS) for m in (V.SHPLONK, V.GWC)}
+    yield V, S, ctx, AS, pv
+    ctx.close()
+
+
+@pytest.mark.parametrize("scheme,mos", [("bdfg21", 0), ("gwc19", 1)])
+def test_batch_verify_and_fold(env, scheme, mos):
+    V, S, ctx, AS, pv = env
+    n = 21
+    insts, proofs = forge.forge_batch(S, scheme, n, seed0=500)
+    snarks = [V.Snark(i, p) for i, p in zip(insts, proofs)]
+    accs, chals, st = pv[mos].succinct_verify(snarks)
+    assert (st == 0).all()
+    oracle_accs = [api.succinct_verify(S.dk.svk, S.protocol, i, p, scheme)[0] for i, p in zip(insts, proofs)]
+    pairs = [(a.lhs.pt, a.rhs.pt) for a in oracle_accs]
+    assert [(a.lhs, a.rhs) for a in accs] == pairs
+    # fold: flat (the reference's aggregation.rs:235-245) and trees, root challenge + folded accumulator
+    for m in (0, 2, 4, 8):
+        (elhs, erhs), rs = api.fold(pairs, m)
+        got, r = AS.create_proof(accs, m)
+        assert (got.lhs, got.rhs) == (elhs, erhs), m
+        assert r == rs[-1], m
+        AS.decide(got)
+    # the composed path: one pairing for the batch
+    for m in (0, 4):
+        res = pv[mos].verify(snarks, group_size=m)
+        assert res.ok and (res.status == 0).all()
+        assert (res.folded.lhs, res.folded.rhs) == api.fold(pairs, m)[0]
+    pv[mos].verify_one(snarks[0])
+    # one corrupted evaluation: batch rejects and the offender is located
+    bad = bytearray(proofs[5])
+    bad[9 * 32 + 40] ^= 4
+    snarks2 = list(snarks)
+    snarks2[5] = V.Snark(insts[5], bytes(bad))
+    res = pv[mos].verify(snarks2, group_size=4)
+    assert not res.ok
+    assert [int(s) for s in res.status] == [3 if i == 5 else 0 for i in range(n)]
+    with pytest.raises(V.Error) as e:
+        pv[mos].verify_one(snarks2[5])
+    assert e.value.kind == "AssertionFailure"
+    assert api.status_of(api.verify, S.dk, S.protocol, insts[5], bytes(bad), scheme) == 3
+    # an undecodable proof: Transcript error, no fold
+    bad = bytearray(proofs[2])
+    bad[9 * 32 : 10 * 32] = b"\xff" * 32
+    snarks3 = list(snarks)
+    snarks3[2] = V.Snark(insts[2], bytes(bad))
+    res = pv[mos].verify(snarks3)
+    assert not res.ok and (res.status[2] & 0xFF) == 4 and res.status[0] == 0
+
+
+def test_fold_rejects_identity(env):
+    V, S, ctx, AS, pv = env
+    from oracle.forge import g_mul
+
+    a = V.KzgAccumulator(g_mul(5), g_mul(7))
+    with pytest.raises(V.Error) as e:
+        AS.create_proof([a, V.KzgAccumulator(None, g_mul(3))])
+    assert e.value.kind == "Transcript"
