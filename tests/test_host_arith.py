@@ -1,0 +1,166 @@
+"""Builds the DEVICE arithmetic headers for the host (PTX carry primitives emulated bit-exactly,
+csrc/ptx_arith.cuh) and checks the limb algorithms against the oracle: Montgomery field ops, G1 group
+law + decompression, optimal-ate pairing (exact Miller and Gt values), Poseidon spec + permutation
+(reference KAT), and the protocol compiler + tape VM (challenges and accumulators).  No GPU needed."""
+import ctypes
+import os
+import random
+import subprocess
+
+import pytest
+
+from oracle import api, bn254, forge, poseidon
+from oracle.bn254 import P, R
+
+from .util import to_product_protocol
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "host", "_hostlib.so")
+SRC = os.path.join(HERE, "host", "hostlib.cpp")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", SO, SRC], check=True, timeout=600)
+    return ctypes.CDLL(SO)
+
+
+def limbs(vals):
+    out = []
+    for v in vals:
+        out += [(v >> (32 * i)) & 0xFFFFFFFF for i in range(8)]
+    return (ctypes.c_uint32 * len(out))(*out)
+
+
+def rd(a, n):
+    return [sum(int(a[8 * j + i]) << (32 * i) for i in range(8)) for j in range(n)]
+
+
+def g1l(pt):
+    return limbs(pt if pt else (0, 0))
+
+
+def rd_g1(a):
+    x, y = rd(a, 2)
+    return None if x == 0 and y == 0 else (x, y)
+
+
+def test_field_ops(lib):
+    rng = random.Random(1)
+
+    def op(f, o, a, b=0):
+        out = (ctypes.c_uint32 * 8)()
+        lib.host_fe_op(f, o, limbs([a]), limbs([b]), out)
+        return rd(out, 1)[0]
+
+    for f, m in ((0, P), (1, R)):
+        Rm = (1 << 256) % m
+        Ri = pow(Rm, -1, m)
+        edge = [0, 1, 2, m - 1, m - 2, Rm, (1 << 254) % m, m >> 1]
+        vals = edge + [rng.randrange(m) for _ in range(60)]
+        for a in vals:
+            for b in rng.sample(vals, 6) + edge:
+                assert op(f, 0, a, b) == a * b * Ri % m
+                assert op(f, 1, a, b) == (a + b) % m and op(f, 2, a, b) == (a - b) % m
+            assert op(f, 3, a) == (-a) % m and op(f, 6, a) == a * Rm % m and op(f, 7, a) == a * Ri % m
+        for a in vals[:12]:
+            assert op(f, 4, a * Rm % m) == (pow(a, -1, m) * Rm % m if a else 0)
+        assert lib.host_is_canonical(f, limbs([m - 1])) == 1 and lib.host_is_canonical(f, limbs([m])) == 0
+    for a in [rng.randrange(P) for _ in range(8)]:
+        Rm = (1 << 256) % P
+        assert op(0, 5, a * Rm % P) == pow(a, (P + 1) // 4, P) * Rm % P
+
+
+def test_g1_ops(lib):
+    rng = random.Random(2)
+    Pt = bn254.g1_mul(bn254.G1_GEN, rng.randrange(bn254.R))
+    cases = [(0, None), (1, None), (1, Pt), (2, bn254.g1_neg(bn254.g1_mul(Pt, 2))), (R - 1, Pt), (5, bn254.g1_mul(Pt, 5)),
+             (rng.randrange(R), bn254.g1_mul(bn254.G1_GEN, 77))]
+    for k, q in cases:
+        exp = bn254.g1_add(bn254.g1_mul(Pt, k), q)
+        for repr_ in (0, 1):
+            out = (ctypes.c_uint32 * 16)()
+            lib.host_g1_muladd(repr_, g1l(Pt), limbs([k]), g1l(q), out)
+            assert rd_g1(out) == exp
+    for _ in range(8):
+        pt = bn254.g1_mul(bn254.G1_GEN, rng.randrange(1, R))
+        out = (ctypes.c_uint32 * 16)()
+        assert lib.host_g1_decompress(bn254.g1_to_bytes(pt), out) == 0 and rd_g1(out) == pt
+    assert lib.host_g1_decompress(bytes(32), (ctypes.c_uint32 * 16)()) == 2
+    assert lib.host_g1_decompress(P.to_bytes(32, "little"), (ctypes.c_uint32 * 16)()) == 1
+    for x in range(1, 30):
+        ok, pt = bn254.g1_from_bytes(x.to_bytes(32, "little"))
+        out = (ctypes.c_uint32 * 16)()
+        rc = lib.host_g1_decompress(x.to_bytes(32, "little"), out)
+        assert (rc == 0) == ok and (not ok or rd_g1(out) == pt)
+
+
+def test_pairing_exact(lib):
+    rng = random.Random(3)
+    s, d = rng.randrange(1, R), rng.randrange(1, R)
+    sg2 = bn254.g2_mul(bn254.G2_GEN, s)
+
+    def g2l(q):
+        return limbs([q[0][0], q[0][1], q[1][0], q[1][1]])
+
+    def rd12(a):
+        v = rd(a, 12)
+        f2 = [(v[2 * i], v[2 * i + 1]) for i in range(6)]
+        return ((f2[0], f2[1], f2[2]), (f2[3], f2[4], f2[5]))
+
+    G = bn254.G1_GEN
+    cases = [(bn254.g1_mul(G, s * d % R), bn254.g1_mul(G, d), 1), (bn254.g1_mul(G, (s * d + 1) % R), bn254.g1_mul(G, d), 0), (None, None, 1)]
+    for lhs, rhs, exp in cases:
+        gt, ml = (ctypes.c_uint32 * 96)(), (ctypes.c_uint32 * 96)()
+        rc = lib.host_pairing(g1l(lhs), g2l(bn254.G2_GEN), g1l(rhs), g2l(bn254.g2_neg(sg2)), gt, ml)
+        mlo = bn254.multi_miller_loop([(lhs, bn254.G2_GEN), (rhs, bn254.g2_neg(sg2))])
+        assert rd12(ml) == mlo and rd12(gt) == bn254.final_exponentiation(mlo) and rc == exp
+
+
+def test_poseidon_kat_and_random(lib):
+    out = (ctypes.c_uint32 * 24)()
+    assert lib.host_poseidon_permute(limbs([0, 1, 2]), 2, limbs([0]), limbs([0]), out) == 0
+    assert rd(out, 3)[0] == 7853200120776062878684798364095072458815029376092732009249414926327459813530  # tests.rs:51
+    sp = poseidon.spec()
+    rng = random.Random(4)
+    for _ in range(4):
+        st = [rng.randrange(R) for _ in range(3)]
+        a, b = rng.randrange(R), rng.randrange(R)
+        for n in (0, 1, 2):
+            lib.host_poseidon_permute(limbs(st), n, limbs([a]), limbs([b]), out)
+            assert rd(out, 3) == poseidon.permutation_optimized(sp, st, [a, b][:n])
+
+
+@pytest.mark.parametrize("scheme,mos", [("bdfg21", 0), ("gwc19", 1)])
+def test_compiler_and_tape(lib, scheme, mos):
+    S = forge.Setup(0)
+    blob = to_product_protocol(S.protocol).to_bytes()
+    inst, pf = forge.forge_proof(S, scheme, 7)
+    accs, proof = api.succinct_verify(S.dk.svk, S.protocol, inst, pf, scheme, want_proof=True)
+    ch, sc = (ctypes.c_uint32 * (8 * 32))(), (ctypes.c_uint32 * (8 * 64))()
+    terms, info, err = (ctypes.c_int * 300)(), (ctypes.c_longlong * 10)(), ctypes.create_string_buffer(256)
+    instb = b"".join(int(x).to_bytes(32, "little") for col in inst for x in col)
+    nt = lib.host_compile_run(blob, len(blob), mos, pf, len(pf), instb, len(instb) // 32, ch, sc, terms, 100, info, err, 256)
+    assert nt > 0, err.value
+    assert info[2] == (27 if scheme == "bdfg21" else 28) and info[5] == len(pf) and info[6] == 0xFFFFFFFF and info[7] == 1
+    exp_ch = [c.v for c in proof.challenges] + [proof.z.v]
+    exp_ch += [proof.pcs.mu.v, proof.pcs.gamma.v, proof.pcs.z_prime.v] if scheme == "bdfg21" else [proof.pcs.v.v, proof.pcs.u.v]
+    assert rd(ch, info[3]) == exp_ch
+    npre = len(S.protocol.preprocessed)
+    pts = [bn254.g1_from_bytes(pf[32 * i : 32 * i + 32])[1] for i in range(9)]
+    off = 26 * 32
+    pts += [bn254.g1_from_bytes(pf[off + 32 * i : off + 32 * i + 32])[1] for i in range(2 if scheme == "bdfg21" else 3)]
+    res = [None, None]
+    scal = rd(sc, info[4])
+    for t in range(nt):
+        which, base, slot = terms[3 * t], terms[3 * t + 1], terms[3 * t + 2]
+        b = bn254.G1_GEN if base == -1 else (S.protocol.preprocessed[base] if base < npre else pts[base - npre])
+        res[which] = bn254.g1_add(res[which], bn254.g1_mul(b, 1 if slot < 0 else scal[slot]))
+    assert res[0] == accs[0].lhs.pt and res[1] == accs[0].rhs.pt
+    # error paths through the same tape: scalar out of range, short proof
+    bad = bytearray(pf)
+    bad[9 * 32 : 10 * 32] = b"\xff" * 32
+    lib.host_compile_run(blob, len(blob), mos, bytes(bad), len(bad), instb, 1, ch, sc, terms, 100, info, err, 256)
+    assert info[6] == ((9 * 32) << 8 | 2)
+    lib.host_compile_run(blob, len(blob), mos, pf, 100, instb, 1, ch, sc, terms, 100, info, err, 256)
+    assert info[6] & 0xFF == 1
