@@ -54,6 +54,11 @@ int svk_sync(svk_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py `gpu_launches`). */
 uint64_t svk_launch_count(svk_ctx* ctx);
 
+/* Per-kernel device timing (CUDA events on the launching stream around every launch).  The report is
+ * a JSON object {"kernel": {"count": launches, "ms": total device ms}}; reading it resets it. */
+int svk_profile_enable(svk_ctx* ctx, int on);
+int svk_profile_report(svk_ctx* ctx, char* buf, size_t buf_len);
+
 /* ---- KzgDecidingKey -------------------------------------------------------------------------
  * `KzgDecidingKey::new(g1, g2, s_g2)` (pcs/kzg/decider.rs:15-24) + halo2curves `G2Prepared::from`
  * (decider.rs:64): validates the G2 points, precomputes the line tables of g2 and -s_g2 and

@@ -37,9 +37,9 @@ int svk_decide_launch(svk_ctx* ctx, int dk, size_t n, const void* d_accs, void* 
   const DkDevice& k = ctx->dks[dk];
   unsigned block = 64;
   unsigned grid = (unsigned)((n + block - 1) / block);
-  k_decide<<<grid, block, 0, ctx->stream>>>(n, (const uint8_t*)d_accs, (uint8_t*)d_ok, k.d_lines_g2, k.d_lines_neg_sg2,
-                                            ctx->d_pairing_consts);
-  ctx->launches++;
+  SVK_LAUNCH(ctx, "k_decide",
+             k_decide<<<grid, block, 0, ctx->stream>>>(n, (const uint8_t*)d_accs, (uint8_t*)d_ok, k.d_lines_g2, k.d_lines_neg_sg2,
+                                                       ctx->d_pairing_consts));
   SVK_CUDA(ctx, cudaGetLastError());
   return 0;
 }

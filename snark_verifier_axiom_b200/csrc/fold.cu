@@ -144,12 +144,12 @@ int svk_fold_launch(svk_ctx* ctx, size_t n, const uint8_t* d_accs, size_t group_
     size_t groups = (cnt + m - 1) / m;
     bool last = groups == 1;
     uint8_t* dst = last ? d_out_acc : bufs[which];
-    k_fold_sponge<<<(unsigned)((groups + 31) / 32), 32, 0, s>>>(cnt, m, cur, ctx->d_poseidon, d_scal, last ? d_out_r : nullptr, d_status);
+    SVK_LAUNCH(ctx, "k_fold_sponge",
+               k_fold_sponge<<<(unsigned)((groups + 31) / 32), 32, 0, s>>>(cnt, m, cur, ctx->d_poseidon, d_scal, last ? d_out_r : nullptr, d_status));
     unsigned L = 32;
     while (L < m && L < 256) L <<= 1;
     dim3 grid((unsigned)groups, 2);
-    k_group_msm<<<grid, L, L * sizeof(G1Jac), s>>>(cnt, m, cur, d_scal, dst, d_status);
-    ctx->launches += 2;
+    SVK_LAUNCH(ctx, "k_group_msm", k_group_msm<<<grid, L, L * sizeof(G1Jac), s>>>(cnt, m, cur, d_scal, dst, d_status));
     if (last) break;
     cur = dst;
     cnt = groups;
@@ -173,8 +173,7 @@ __global__ void k_batch_verdict(size_t n, const int32_t* status, const int32_t* 
 
 int svk_batch_verdict_launch(svk_ctx* ctx, size_t n, const int32_t* d_status, const int32_t* d_fold_status, const uint8_t* d_decide_ok,
                              uint8_t* d_out_ok) {
-  k_batch_verdict<<<1, 256, 0, ctx->stream>>>(n, d_status, d_fold_status, d_decide_ok, d_out_ok);
-  ctx->launches++;
+  SVK_LAUNCH(ctx, "k_batch_verdict", k_batch_verdict<<<1, 256, 0, ctx->stream>>>(n, d_status, d_fold_status, d_decide_ok, d_out_ok));
   SVK_CUDA(ctx, cudaGetLastError());
   return 0;
 }

@@ -91,6 +91,41 @@ int svk_sync(svk_ctx* ctx) { SVK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); 
 
 uint64_t svk_launch_count(svk_ctx* ctx) { return ctx->launches; }
 
+int svk_profile_enable(svk_ctx* ctx, int on) {
+  ctx->profile = on != 0;
+  return 0;
+}
+
+// JSON: {"kernel": {"count": c, "ms": total}, ...}; resets the statistics.  Returns bytes written or -1.
+int svk_profile_report(svk_ctx* ctx, char* buf, size_t buf_len) {
+  SVK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& pe : ctx->pending) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, pe.e0, pe.e1) == cudaSuccess) {
+      auto& st = ctx->stats[pe.name];
+      st.count++;
+      st.ms += ms;
+    }
+    cudaEventDestroy(pe.e0);
+    cudaEventDestroy(pe.e1);
+  }
+  ctx->pending.clear();
+  std::string out = "{";
+  bool first = true;
+  for (auto& kv : ctx->stats) {
+    char tmp[256];
+    snprintf(tmp, sizeof tmp, "%s\"%s\": {\"count\": %llu, \"ms\": %.6f}", first ? "" : ", ", kv.first.c_str(),
+             (unsigned long long)kv.second.count, kv.second.ms);
+    out += tmp;
+    first = false;
+  }
+  out += "}";
+  ctx->stats.clear();
+  if (out.size() + 1 > buf_len) return svk_fail(ctx, "profile buffer too small");
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return (int)out.size();
+}
+
 static bool load_fq_canon(Fq& out, const svk_fe& fe) {
   fe_load_le(out.v, fe.b);
   if (!Fq::is_canonical(out.v)) return false;

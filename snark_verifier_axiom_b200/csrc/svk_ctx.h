@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -18,7 +19,19 @@ struct DkDevice {
   svk_g1 g1_canon;
 };
 
+struct KernelStat {
+  uint64_t count = 0;
+  double ms = 0;
+};
+struct PendingEvent {
+  const char* name;
+  cudaEvent_t e0, e1;
+};
+
 struct svk_ctx {
+  bool profile = false;  // svk_profile_enable: CUDA events around every kernel launch
+  std::vector<PendingEvent> pending;
+  std::map<std::string, KernelStat> stats;
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -63,3 +76,21 @@ inline int svk_scratch(svk_ctx* ctx, int slot, size_t bytes, void** out) {
   *out = ctx->scratch[slot];
   return 0;
 }
+
+// Kernel launch wrapper: counts the launch and, when profiling is on, brackets it with CUDA events
+// on the launching stream (resolved in svk_profile_report).
+#define SVK_LAUNCH(ctx, name, ...)                                   \
+  do {                                                               \
+    PendingEvent pe_{name, nullptr, nullptr};                        \
+    if ((ctx)->profile) {                                            \
+      cudaEventCreate(&pe_.e0);                                      \
+      cudaEventCreate(&pe_.e1);                                      \
+      cudaEventRecord(pe_.e0, (ctx)->stream);                        \
+    }                                                                \
+    __VA_ARGS__;                                                     \
+    (ctx)->launches++;                                               \
+    if ((ctx)->profile) {                                            \
+      cudaEventRecord(pe_.e1, (ctx)->stream);                        \
+      (ctx)->pending.push_back(pe_);                                 \
+    }                                                                \
+  } while (0)

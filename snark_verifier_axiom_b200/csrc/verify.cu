@@ -178,33 +178,31 @@ int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const
     d_out_challenges = d_chal_scratch;
   }
   unsigned b = 256;
-  k_fill_u32<<<(unsigned)((n + b - 1) / b), b, 0, s>>>(n, d_err, SVK_NO_ERR);
-  ctx->launches++;
+  SVK_LAUNCH(ctx, "k_fill_u32", k_fill_u32<<<(unsigned)((n + b - 1) / b), b, 0, s>>>(n, d_err, SVK_NO_ERR));
   int mode = 0;
   if (n_instances_given != pd->n_instances) mode = 1;  // proof.rs:66-69
   else if (!pd->verify_valid) mode = 2;
   if (mode != 1) {
     if (n_pts) {
       size_t total = n * n_pts;
-      k_decompress<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(n, (u32)n_pts, pd->d_sched, d_proofs, proof_stride, d_proof_lens, d_regs,
-                                                                  d_pts, d_err);
-      ctx->launches++;
+      SVK_LAUNCH(ctx, "k_decompress",
+                 k_decompress<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(n, (u32)n_pts, pd->d_sched, d_proofs, proof_stride, d_proof_lens,
+                                                                             d_regs, d_pts, d_err));
     }
     u32 n_ops = pd->verify_valid ? pd->n_ops : pd->read_ops_end;
-    k_tape<<<(unsigned)((n + 31) / 32), 32, 0, s>>>(n, pd->d_ops, n_ops, pd->d_aux, pd->d_consts, ctx->d_poseidon, d_regs, d_proofs, proof_stride,
-                                                   d_proof_lens, d_instances, pd->n_instances, d_scalars, d_out_challenges, pd->n_challenges,
-                                                   d_err);
-    ctx->launches++;
+    SVK_LAUNCH(ctx, "k_tape",
+               k_tape<<<(unsigned)((n + 31) / 32), 32, 0, s>>>(n, pd->d_ops, n_ops, pd->d_aux, pd->d_consts, ctx->d_poseidon, d_regs, d_proofs,
+                                                              proof_stride, d_proof_lens, d_instances, pd->n_instances, d_scalars,
+                                                              d_out_challenges, pd->n_challenges, d_err));
   }
   if (mode == 0) {
     dim3 grid((unsigned)((n * MSM_LANES + 127) / 128), 2);
-    k_proof_msm<<<grid, 128, 0, s>>>(n, pd->d_lhs, pd->n_lhs, pd->d_rhs, pd->n_rhs, pd->d_fixed, d_pts, d_scalars, d_err, d_out_acc);
-    ctx->launches++;
+    SVK_LAUNCH(ctx, "k_proof_msm",
+               k_proof_msm<<<grid, 128, 0, s>>>(n, pd->d_lhs, pd->n_lhs, pd->d_rhs, pd->n_rhs, pd->d_fixed, d_pts, d_scalars, d_err, d_out_acc));
   } else {
     SVK_CUDA(ctx, cudaMemsetAsync(d_out_acc, 0, n * 128, s));
   }
-  k_status<<<(unsigned)((n + b - 1) / b), b, 0, s>>>(n, d_err, mode, d_out_status);
-  ctx->launches++;
+  SVK_LAUNCH(ctx, "k_status", k_status<<<(unsigned)((n + b - 1) / b), b, 0, s>>>(n, d_err, mode, d_out_status));
   SVK_CUDA(ctx, cudaGetLastError());
   return 0;
 }
