@@ -23,7 +23,11 @@ def succinct_verify(svk, protocol, instances, proof_bytes, scheme, loader=None, 
     """-> (accumulators, PlonkProof).  Raises VerifyError like the reference returns Err."""
     loader = loader or NativeLoader()
     AS = SCHEMES[scheme]
-    inst = [[loader.load_const(x) for x in col] for col in instances]
+    flat = 0
+    inst = []
+    for col in instances:
+        inst.append([loader.load_input(x, flat + j) for j, x in enumerate(col)])
+        flat += len(col)
     tr = PoseidonTranscript(loader, proof_bytes)
     proof = PlonkSuccinctVerifier.read_proof(svk, protocol, inst, tr, AS)
     accs = PlonkSuccinctVerifier.verify(svk, protocol, inst, proof, AS)

@@ -174,6 +174,16 @@ class NativeLoader:
             reg = tr.consts[value]
         return Scalar(value, self, reg)
 
+    def load_input(self, value, index):
+        """A per-proof input (an instance value): a plain Fr for NativeLoader; under tracing a fresh
+        register filled from input slot `index` by the replayer."""
+        tr = self.tracer
+        reg = None
+        if tr is not None:
+            reg = tr.new_s()
+            tr.emit("input", reg, index)
+        return Scalar(value, self, reg)
+
     def load_zero(self):
         return self.load_const(0)
 

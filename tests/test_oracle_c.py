@@ -1,0 +1,47 @@
+"""The C restatement of the reference CPU path (oracle/c) is bit-identical to the Python oracle:
+accumulators, statuses, folds (flat + tree), decide."""
+import numpy as np
+import pytest
+
+from oracle import api, bn254, forge
+from oracle.c import cref
+
+from .util import acc_bytes, g1_from
+
+
+@pytest.fixture(scope="module")
+def S():
+    return forge.Setup(0)
+
+
+@pytest.mark.parametrize("scheme", ["bdfg21", "gwc19"])
+def test_replay_matches_python_oracle(S, scheme):
+    tr = cref.Trace(S, scheme)
+    if scheme == "bdfg21":
+        assert tr.n_scalar_muls == 21 and tr.counts["inv"] == 19 and tr.counts["t_read_point"] == 11
+    n = 6
+    insts, proofs = forge.forge_batch(S, scheme, n, seed0=70)
+    proofs = [bytearray(p) for p in proofs]
+    proofs[1][9 * 32 + 7] ^= 2           # still decodes: different accumulator
+    proofs[2][9 * 32 : 10 * 32] = b"\xff" * 32  # scalar >= r
+    proofs[3][0:32] = bytes(32)          # identity point
+    proofs = [bytes(p) for p in proofs]
+    accs, st = cref.replay(tr, proofs, insts, threads=2)
+    pairs = []
+    for i in range(n):
+        want = api.status_of(api.succinct_verify, S.dk.svk, S.protocol, insts[i], proofs[i], scheme)
+        assert (st[i] & 0xFF) == want
+        if want == 0:
+            a = api.succinct_verify(S.dk.svk, S.protocol, insts[i], proofs[i], scheme)[0]
+            assert (g1_from(accs[i, :64].tobytes()), g1_from(accs[i, 64:].tobytes())) == (a.lhs.pt, a.rhs.pt)
+            pairs.append((a.lhs.pt, a.rhs.pt))
+    good = np.stack([accs[i] for i in range(n) if st[i] == 0])
+    for m in (0, 2):
+        acc, r, fst = cref.fold(good, m)
+        (el, er), rs = api.fold(pairs, m)
+        assert fst == 0 and (g1_from(acc[:64].tobytes()), g1_from(acc[64:].tobytes())) == (el, er) and r == rs[-1]
+    acc, r, _ = cref.fold(np.stack([accs[0], accs[4], accs[5]]), 0)
+    assert cref.decide(acc, S.dk) is True
+    acc_bad, _, _ = cref.fold(good, 0)  # contains the mutated proof's accumulator
+    assert cref.decide(acc_bad, S.dk) is False
+    assert cref.decide(np.frombuffer(acc_bytes(None, None), dtype=np.uint8), S.dk) is True
