@@ -294,20 +294,22 @@ def run_ours(args):
     h2d = int(h_i.nbytes + h_p.nbytes + h_l.nbytes)
     d2h = int(n * 4 + 256)
 
+    # ---- per-kernel device time (CUDA events around every launch, one batch in flight) -> roofline.
+    # Runs on EVERY rank: verify_dev contains the all_gather when world > 1.
+    sl = slots[0]
+    L, c = sl.ctx._L, sl.ctx._c
+    L.svk_profile_enable(c, 1)
+    prof_steps = 3
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for k in range(prof_steps):
+        with torch.cuda.stream(sl.stream):
+            flush.fill_(1)
+        sl.sv.verify_dev(d_inputs[k % n_copies][0], n_inst, d_inputs[k % n_copies][1], n)
+    buf = ctypes.create_string_buffer(1 << 16)
+    L.svk_profile_report(c, buf, len(buf))
+    L.svk_profile_enable(c, 0)
+    barrier()
     if rank == 0:
-        # ---- per-kernel device time (CUDA events around every launch, one batch in flight) -> roofline
-        sl = slots[0]
-        L, c = sl.ctx._L, sl.ctx._c
-        L.svk_profile_enable(c, 1)
-        prof_steps = 3
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-        for k in range(prof_steps):
-            with torch.cuda.stream(sl.stream):
-                flush.fill_(1)
-            sl.sv.verify_dev(d_inputs[k % n_copies][0], n_inst, d_inputs[k % n_copies][1], n)
-        buf = ctypes.create_string_buffer(1 << 16)
-        L.svk_profile_report(c, buf, len(buf))
-        L.svk_profile_enable(c, 0)
         prof = json.loads(buf.value.decode())
         peak, peak_ms = sl.ctx.modmul_peak(4000)
         info = pv.info

@@ -53,10 +53,10 @@ __global__ void __launch_bounds__(256) k_modmul_peak(u32* out, int iters) {
   for (int i = 0; i < 8; i++) { a.v[i] = t * 2654435761u + i; b.v[i] = t ^ (0x9e3779b9u * (i + 1)); c.v[i] = t + 77 * i; d.v[i] = ~t - i; }
   a.v[7] &= 0x0fffffffu; b.v[7] &= 0x0fffffffu; c.v[7] &= 0x0fffffffu; d.v[7] &= 0x0fffffffu;
   for (int k = 0; k < iters; k++) {
-    a = a * b;
-    c = c * d;
-    b = b * a;
-    d = d * c;
+    a = Fq::mul_inline(a, b);
+    c = Fq::mul_inline(c, d);
+    b = Fq::mul_inline(b, a);
+    d = Fq::mul_inline(d, c);
   }
   Fq r = a + b + c + d;
   u32 x = 0;

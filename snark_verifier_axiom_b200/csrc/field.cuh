@@ -174,7 +174,12 @@ struct Fe {
     of[7] = ptx::addc(of[7], 0);
   }
 
-  HD friend Fe operator*(const Fe& a, const Fe& b) {
+  // Fully inlined multiplication (176 SASS instructions).  Device code normally goes through the
+  // out-of-line copy below: with the product inlined at every call site the hot loops of the
+  // latency-bound kernels (one warp per SM sub-partition) overflow the instruction caches
+  // (ncu: `stalled_no_instruction` up to 2.3 per issue, profiles/r1_ncu_notes.md); a by-value call
+  // costs ~16 MOVs (arguments and result travel in registers, no local memory).
+  HD static Fe mul_inline(const Fe& a, const Fe& b) {
     u32 al[8], of[8];
 #pragma unroll
     for (int i = 0; i < 8; i += 2) {
@@ -190,6 +195,12 @@ struct Fe {
     reduce_once(r.v);
     return r;
   }
+#if defined(__CUDA_ARCH__)
+  static __device__ __noinline__ Fe mul_call(Fe a, Fe b) { return mul_inline(a, b); }
+  HD friend Fe operator*(const Fe& a, const Fe& b) { return mul_call(a, b); }
+#else
+  HD friend Fe operator*(const Fe& a, const Fe& b) { return mul_inline(a, b); }
+#endif
   HD Fe sqr() const { return (*this) * (*this); }
 
   // canonical <-> Montgomery

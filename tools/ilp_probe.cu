@@ -15,7 +15,7 @@ __global__ void k(u32* out, int iters) {
     for (int i = 0; i < 8; i++) { a[j].v[i] = t * 2654435761u + i + j; b[j].v[i] = (t ^ (0x9e3779b9u * (i + 1))) + j; if (i == 7) { a[j].v[i] &= 0x0fffffff; b[j].v[i] &= 0x0fffffff; } }
   for (int k2 = 0; k2 < iters; k2++) {
 #pragma unroll
-    for (int j = 0; j < ILP; j++) a[j] = a[j] * b[j];
+    for (int j = 0; j < ILP; j++) a[j] = Fq::mul_inline(a[j], b[j]);
   }
   u32 x = 0;
 #pragma unroll
