@@ -127,6 +127,17 @@ int svk_plonk_verify_batch_dev(svk_ctx* ctx, int proto, size_t n, const void* d_
                                size_t proof_stride, const void* d_proof_lens, size_t group_size, void* d_out_accs, void* d_out_status,
                                void* d_out_folded);
 
+/* ---- G1 multi-scalar multiplication -----------------------------------------------------------------
+ * `util::msm::multi_scalar_multiplication(scalars, bases)` (util/msm.rs:238-317), value-identical:
+ * out = sum_i scalars[i] * points[i] as a canonical affine point (identity = zeros).
+ * out_status: 0 ok, 1 a point is not a canonical curve point, 2 a scalar is >= r (both unrepresentable as
+ * halo2curves values; the offending terms are skipped). */
+int svk_msm_g1(svk_ctx* ctx, size_t n, const svk_fe* scalars, const svk_g1* points, svk_g1* out, int32_t* out_status);
+int svk_msm_g1_dev(svk_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out, void* d_status);
+/* Batched `base * scalar` (loader/native.rs:67): out[i] = scalars[i] * points[i % n_points]. */
+int svk_g1_mul_batch(svk_ctx* ctx, size_t n, const svk_fe* scalars, const svk_g1* points, size_t n_points, svk_g1* out);
+int svk_g1_mul_batch_dev(svk_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, size_t n_points, void* d_out);
+
 /* ---- micro-benchmark of the integer-multiply roofline (DESIGN.md "IMAD peak") ------------------
  * Runs `iters` dependent Montgomery multiplications per thread on every SM; returns modmul/s. */
 int svk_bench_modmul_peak(svk_ctx* ctx, int iters, double* out_modmul_per_s, double* out_ms);

@@ -39,6 +39,10 @@ def _load():
     lib.svk_kzg_as_fold_dev.argtypes = [vp, sz, vp, sz, vp, vp, vp]
     lib.svk_plonk_verify_batch.argtypes = [vp, i32, sz, vp, ctypes.c_uint32, vp, sz, vp, sz, i32, vp, vp, vp]
     lib.svk_plonk_verify_batch_dev.argtypes = [vp, i32, sz, vp, ctypes.c_uint32, vp, sz, vp, sz, vp, vp, vp]
+    lib.svk_msm_g1.argtypes = [vp, sz, vp, vp, vp, vp]
+    lib.svk_msm_g1_dev.argtypes = [vp, sz, vp, vp, vp, vp]
+    lib.svk_g1_mul_batch.argtypes = [vp, sz, vp, vp, sz, vp]
+    lib.svk_g1_mul_batch_dev.argtypes = [vp, sz, vp, vp, sz, vp]
     lib.svk_bench_modmul_peak.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     return lib
 

@@ -9,6 +9,8 @@
 
 int svk_decide_launch(svk_ctx* ctx, int dk, size_t n, const void* d_accs, void* d_ok);
 int svk_modmul_peak_launch(svk_ctx* ctx, int iters, double* out_rate, double* out_ms);
+int svk_msm_launch(svk_ctx* ctx, size_t n, const uint8_t* d_scalars, const uint8_t* d_points, uint8_t* d_out, int* d_status);
+int svk_g1_mul_batch_launch(svk_ctx* ctx, size_t n, const uint8_t* d_scalars, const uint8_t* d_points, size_t n_points, uint8_t* d_out);
 int svk_fold_launch(svk_ctx* ctx, size_t n, const uint8_t* d_accs, size_t group_size, uint8_t* d_out_acc, u32* d_out_r, int32_t* d_status);
 int svk_batch_verdict_launch(svk_ctx* ctx, size_t n, const int32_t* d_status, const int32_t* d_fold_status, const uint8_t* d_decide_ok,
                              uint8_t* d_out_ok);
@@ -367,6 +369,49 @@ int svk_plonk_verify_batch(svk_ctx* ctx, int proto, size_t n, const svk_fe* inst
         if (!oks[i]) out_status[i] = SVK_ASSERTION_FAILURE;
     }
   }
+  return 0;
+}
+
+// ---- MSM ------------------------------------------------------------------------------------------
+int svk_msm_g1_dev(svk_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out, void* d_status) {
+  SVK_CUDA(ctx, cudaSetDevice(ctx->device));
+  return svk_msm_launch(ctx, n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, (int*)d_status);
+}
+
+int svk_msm_g1(svk_ctx* ctx, size_t n, const svk_fe* scalars, const svk_g1* points, svk_g1* out, int32_t* out_status) {
+  SVK_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  uint8_t* d;
+  size_t off_p = (n * 32 + 255) / 256 * 256, off_o = off_p + (n * 64 + 255) / 256 * 256;
+  if (svk_scratch(ctx, 0, off_o + 256, (void**)&d)) return -1;
+  if (n) {
+    SVK_CUDA(ctx, cudaMemcpyAsync(d, scalars, n * 32, cudaMemcpyHostToDevice, s));
+    SVK_CUDA(ctx, cudaMemcpyAsync(d + off_p, points, n * 64, cudaMemcpyHostToDevice, s));
+  }
+  if (svk_msm_launch(ctx, n, d, d + off_p, d + off_o, (int*)(d + off_o + 64))) return -1;
+  SVK_CUDA(ctx, cudaMemcpyAsync(out, d + off_o, 64, cudaMemcpyDeviceToHost, s));
+  SVK_CUDA(ctx, cudaMemcpyAsync(out_status, d + off_o + 64, 4, cudaMemcpyDeviceToHost, s));
+  SVK_CUDA(ctx, cudaStreamSynchronize(s));
+  return 0;
+}
+
+int svk_g1_mul_batch_dev(svk_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, size_t n_points, void* d_out) {
+  SVK_CUDA(ctx, cudaSetDevice(ctx->device));
+  return svk_g1_mul_batch_launch(ctx, n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, n_points, (uint8_t*)d_out);
+}
+
+int svk_g1_mul_batch(svk_ctx* ctx, size_t n, const svk_fe* scalars, const svk_g1* points, size_t n_points, svk_g1* out) {
+  SVK_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (n == 0) return 0;
+  cudaStream_t s = ctx->stream;
+  uint8_t* d;
+  size_t off_p = (n * 32 + 255) / 256 * 256, off_o = off_p + (n_points * 64 + 255) / 256 * 256;
+  if (svk_scratch(ctx, 0, off_o + n * 64, (void**)&d)) return -1;
+  SVK_CUDA(ctx, cudaMemcpyAsync(d, scalars, n * 32, cudaMemcpyHostToDevice, s));
+  SVK_CUDA(ctx, cudaMemcpyAsync(d + off_p, points, n_points * 64, cudaMemcpyHostToDevice, s));
+  if (svk_g1_mul_batch_launch(ctx, n, d, d + off_p, n_points, d + off_o)) return -1;
+  SVK_CUDA(ctx, cudaMemcpyAsync(out, d + off_o, n * 64, cudaMemcpyDeviceToHost, s));
+  SVK_CUDA(ctx, cudaStreamSynchronize(s));
   return 0;
 }
 

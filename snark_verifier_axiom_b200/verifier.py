@@ -273,3 +273,28 @@ class PlonkVerifier:
             raise Error(r.status[0])
         if not r.ok:
             raise Error(3)
+
+
+# ---- EcPointLoader::multi_scalar_multiplication / util::msm (snark-verifier/src/util/msm.rs:238-317) ----
+def multi_scalar_multiplication(ctx: Context, scalars: Sequence[int], bases: Sequence[Optional[Tuple[int, int]]]):
+    """sum_i scalars[i] * bases[i] -> affine point (None = identity).  Pippenger bucket kernel (csrc/msm.cu)."""
+    assert len(scalars) == len(bases)
+    n = len(scalars)
+    sc = np.frombuffer(b"".join(_fe(s) for s in scalars), dtype=np.uint8).copy() if n else np.zeros(0, np.uint8)
+    pt = np.frombuffer(b"".join(_g1_bytes(p) for p in bases), dtype=np.uint8).copy() if n else np.zeros(0, np.uint8)
+    out, st = np.zeros(64, np.uint8), np.zeros(1, np.int32)
+    ctx._check(ctx._L.svk_msm_g1(ctx._c, n, _ptr(sc), _ptr(pt), _ptr(out), _ptr(st)))
+    if st[0] != 0:
+        raise ValueError(f"msm: invalid input (status {int(st[0])})")
+    return _g1_from(out.tobytes())
+
+
+def g1_mul_batch(ctx: Context, scalars: Sequence[int], bases: Sequence[Optional[Tuple[int, int]]]):
+    """[scalars[i] * bases[i % len(bases)]] -- batched `base * scalar` (loader/native.rs:67)."""
+    n = len(scalars)
+    sc = np.frombuffer(b"".join(_fe(s) for s in scalars), dtype=np.uint8).copy()
+    pt = np.frombuffer(b"".join(_g1_bytes(p) for p in bases), dtype=np.uint8).copy()
+    out = np.zeros(n * 64, np.uint8)
+    ctx._check(ctx._L.svk_g1_mul_batch(ctx._c, n, _ptr(sc), _ptr(pt), len(bases), _ptr(out)))
+    b = out.tobytes()
+    return [_g1_from(b[64 * i : 64 * i + 64]) for i in range(n)]
