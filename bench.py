@@ -317,7 +317,7 @@ def run_ours(args):
         work = {
             "k_tape": n * info["n_fr_mul"],
             "k_decompress": n * info["n_points"] * 372,
-            "k_proof_msm": n * ((info["n_lhs_terms"] - 1) * 2977 + 16 * 4 + 400),
+            "k_msm_var": n * info["msm_modmul_per_proof"],  # k_msm_var + k_msm_sum + k_to_affine together; k_msm_var carries > 80 % of it
         }
         kernels = {k: {"launches_per_step": v["count"] / prof_steps, "ms_per_step": v["ms"] / prof_steps} for k, v in prof.items()}
         name = max((k for k in prof if k in work), key=lambda k: prof[k]["ms"])

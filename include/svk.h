@@ -79,8 +79,8 @@ int svk_kzg_decide_batch_dev(svk_ctx* ctx, int dk, size_t n, const void* d_accs,
  * `svk.g` (pcs/kzg.rs:21-37).  Returns a protocol id >= 0.  A protocol whose expressions the
  * reference would reject with Error::InvalidProtocol still compiles; its proofs get that status. */
 int svk_protocol_compile(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos, int dk);
-/* out[12] = { proof_len, n_instances, n_challenges, n_regs, n_ops, n_poseidon_perms, verify_valid,
- *             n_fr_mul, n_lhs_terms, n_rhs_terms, n_points, n_scalar_slots } */
+/* out[16] = { proof_len, n_instances, n_challenges, n_regs, n_ops, n_poseidon_perms, verify_valid,
+ *             n_fr_mul, n_lhs_terms, n_rhs_terms, n_points, n_scalar_slots, msm_modmul_per_proof, 0, 0, 0 } */
 int svk_protocol_info(svk_ctx* ctx, int proto, uint32_t* out);
 
 /* ---- PlonkSuccinctVerifier::{read_proof, verify} (verifier/plonk.rs:32-93) over a batch ----------

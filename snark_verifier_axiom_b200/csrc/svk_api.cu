@@ -11,6 +11,7 @@ int svk_decide_launch(svk_ctx* ctx, int dk, size_t n, const void* d_accs, void* 
 int svk_modmul_peak_launch(svk_ctx* ctx, int iters, double* out_rate, double* out_ms);
 int svk_msm_launch(svk_ctx* ctx, size_t n, const uint8_t* d_scalars, const uint8_t* d_points, uint8_t* d_out, int* d_status);
 int svk_g1_mul_batch_launch(svk_ctx* ctx, size_t n, const uint8_t* d_scalars, const uint8_t* d_points, size_t n_points, uint8_t* d_out);
+int svk_fixed_tables_launch(svk_ctx* ctx, ProtocolDevice* pd);
 int svk_fold_launch(svk_ctx* ctx, size_t n, const uint8_t* d_accs, size_t group_size, uint8_t* d_out_acc, u32* d_out_r, int32_t* d_status);
 int svk_batch_verdict_launch(svk_ctx* ctx, size_t n, const int32_t* d_status, const int32_t* d_fold_status, const uint8_t* d_decide_ok,
                              uint8_t* d_out_ok);
@@ -29,6 +30,44 @@ static int upload(svk_ctx* ctx, T** d, const std::vector<T>& v) {
   return 0;
 }
 
+// Schedule of the per-proof MSM (verify.cu: k_msm_var + k_msm_sum).  Variable-base terms become k_msm_var items
+// (one full windowed scalar multiplication each, ~2977 M); in k_msm_sum every one of the 16 lanes of a proof
+// gets an EQUAL number of fixed-base table windows (11 M each; vk commitments and g), and the partial sums /
+// scalar == 1 bases are dealt round-robin.  Returns the algorithmic Fq mults per proof for this side.
+static size_t schedule_msm(const std::vector<MsmTermDev>& terms, std::vector<MsmWork>& var_items, std::vector<MsmWork>& work,
+                           std::vector<u32>& lane_off) {
+  const int L = SVK_MSM_LANES;
+  std::vector<std::vector<MsmWork>> lanes(L);
+  size_t total = 0;
+  int rr = 0;
+  std::vector<MsmTermDev> fixed_terms;
+  for (auto& t : terms) {
+    if (t.slot < 0) { lanes[rr++ % L].push_back({2, t.fixed, t.base, -1, 0, 0}); total += 11; }
+    else if (t.fixed) fixed_terms.push_back(t);
+    else {
+      lanes[rr++ % L].push_back({3, 0, (int32_t)var_items.size(), -1, 0, 0});
+      var_items.push_back({0, 0, t.base, t.slot, 0, 0});
+      total += 2977 + 16;
+    }
+  }
+  size_t fixed_windows = fixed_terms.size() * SVK_FIXED_WINDOWS;
+  size_t per = (fixed_windows + L - 1) / L;
+  size_t ti = 0, w = 0;
+  for (int l = 0; l < L && fixed_windows; l++) {
+    size_t room = std::min(per, fixed_windows);
+    while (room) {
+      size_t take = std::min<size_t>(room, SVK_FIXED_WINDOWS - w);
+      lanes[l].push_back({1, 1, fixed_terms[ti].base, fixed_terms[ti].slot, (int32_t)w, (int32_t)(w + take)});
+      total += take * 11;
+      room -= take; fixed_windows -= take; w += take;
+      if (w == SVK_FIXED_WINDOWS) { w = 0; ti++; }
+    }
+  }
+  work.clear(); lane_off.assign(L + 1, 0);
+  for (int l = 0; l < L; l++) { lane_off[l] = (u32)work.size(); work.insert(work.end(), lanes[l].begin(), lanes[l].end()); }
+  lane_off[L] = (u32)work.size();
+  return total + (L - 1) * 16 + 385;  // + shuffle-tree additions + to_affine
+}
 
 extern "C" {
 
@@ -74,7 +113,7 @@ void svk_destroy(svk_ctx* ctx) {
   cudaFree(ctx->d_pairing_consts);
   cudaFree(ctx->d_poseidon);
   for (auto* p : ctx->protocols) {
-    cudaFree(p->d_ops); cudaFree(p->d_aux); cudaFree(p->d_consts); cudaFree(p->d_sched); cudaFree(p->d_lhs); cudaFree(p->d_rhs); cudaFree(p->d_fixed);
+    cudaFree(p->d_ops); cudaFree(p->d_aux); cudaFree(p->d_consts); cudaFree(p->d_sched); cudaFree(p->d_lhs); cudaFree(p->d_rhs); cudaFree(p->d_fixed); cudaFree(p->d_fixed_tables); cudaFree(p->d_var_items); cudaFree(p->d_work_lhs); cudaFree(p->d_work_rhs); cudaFree(p->d_lane_off_lhs); cudaFree(p->d_lane_off_rhs);
     delete p;
   }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -235,11 +274,19 @@ int svk_protocol_compile(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos,
   std::vector<MsmTermDev> lhs = conv(cp.lhs), rhs = conv(cp.rhs);
   pd->n_lhs = (u32)lhs.size();
   pd->n_rhs = (u32)rhs.size();
+  std::vector<MsmWork> wl, wr, var_items;
+  std::vector<u32> ol, orr;
+  pd->msm_work_modmul = schedule_msm(lhs, var_items, wl, ol) + schedule_msm(rhs, var_items, wr, orr);
+  pd->n_var = (u32)var_items.size();
+  if (upload(ctx, &pd->d_var_items, var_items) || upload(ctx, &pd->d_work_lhs, wl) || upload(ctx, &pd->d_lane_off_lhs, ol) || upload(ctx, &pd->d_work_rhs, wr) ||
+      upload(ctx, &pd->d_lane_off_rhs, orr)) { delete pd; return -1; }
+  if (cudaMalloc(&pd->d_fixed_tables, fixed.size() * SVK_FIXED_WINDOWS * 16 * sizeof(G1Affine)) != cudaSuccess) { delete pd; return svk_fail(ctx, "fixed table alloc"); }
   if (upload(ctx, &pd->d_ops, cp.ops) || upload(ctx, &pd->d_aux, cp.aux) || upload(ctx, &pd->d_consts, cp.consts) ||
       upload(ctx, &pd->d_sched, pd->points) || upload(ctx, &pd->d_lhs, lhs) || upload(ctx, &pd->d_rhs, rhs) || upload(ctx, &pd->d_fixed, fixed)) {
     delete pd;
     return -1;
   }
+  if (svk_fixed_tables_launch(ctx, pd)) { delete pd; return -1; }
   ctx->protocols.push_back(pd);
   return (int)ctx->protocols.size() - 1;
 }
@@ -249,7 +296,7 @@ int svk_protocol_info(svk_ctx* ctx, int proto, uint32_t* out) {
   ProtocolDevice* pd = ctx->protocols[proto];
   out[0] = pd->proof_len; out[1] = pd->n_instances; out[2] = pd->n_challenges; out[3] = pd->n_regs; out[4] = pd->n_ops;
   out[5] = (u32)pd->n_perm; out[6] = pd->verify_valid ? 1 : 0; out[7] = (u32)pd->n_fr_mul; out[8] = pd->n_lhs; out[9] = pd->n_rhs;
-  out[10] = (u32)pd->points.size(); out[11] = pd->n_scalar_slots;
+  out[10] = (u32)pd->points.size(); out[11] = pd->n_scalar_slots; out[12] = (u32)pd->msm_work_modmul;
   return 0;
 }
 

@@ -14,6 +14,18 @@ struct MsmTermDev {
   int32_t slot;   // out_scalar slot, -1 => scalar is the constant 1
 };
 
+// One unit of per-proof MSM work, executed by one lane of the proof's lane group (k_proof_msm).
+struct MsmWork {
+  int32_t kind;   // 0: variable base, full 4-bit-window scalar mul (k_msm_var); 1: fixed base, table windows [w0, w1);
+                  // 2: add the base (scalar == 1); 3: add partial number `base` produced by k_msm_var
+  int32_t fixed;  // base lives in fixed_bases[] (1) or in the proof-point file (0)
+  int32_t base;
+  int32_t slot;
+  int32_t w0, w1;
+};
+#define SVK_MSM_LANES 16
+#define SVK_FIXED_WINDOWS 64  // 4-bit windows of a 256-bit scalar
+
 struct ProtocolDevice {
   int mos = 0;
   bool verify_valid = true;
@@ -30,6 +42,12 @@ struct ProtocolDevice {
   PointSched* d_sched = nullptr;
   MsmTermDev *d_lhs = nullptr, *d_rhs = nullptr;
   u32 n_lhs = 0, n_rhs = 0;
+  MsmWork *d_work_lhs = nullptr, *d_work_rhs = nullptr;  // lane schedules: items of lane l = work[lane_off[l] .. lane_off[l+1])
+  u32 *d_lane_off_lhs = nullptr, *d_lane_off_rhs = nullptr;
+  G1Affine* d_fixed_tables = nullptr;  // [n_pre + 1][64 windows][16 digits]: d * 2^(4w) * B, affine Montgomery
+  MsmWork* d_var_items = nullptr;      // variable-base terms of both sides; partial index = position here
+  u32 n_var = 0;
+  size_t msm_work_modmul = 0;          // algorithmic Fq mults per proof of the scheduled MSM (DESIGN.md work model)
   G1Affine* d_fixed = nullptr;  // preprocessed..., then g at index n_pre
   u32 n_pre = 0;
   int dk = -1;                  // deciding key whose g1 is baked in as `svk.g`

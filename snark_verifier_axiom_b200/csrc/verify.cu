@@ -4,10 +4,8 @@
 //   k_decompress   : every G1 point of every proof: halo2curves `G1Affine::from_bytes` (Fq sqrt) +
 //                    the [x mod r, y mod r] transcript encoding (transcript/halo2.rs:214-226, 247-260)
 //   k_tape         : one proof per thread runs the compiled verifier tape (tape.cuh)
-//   k_proof_msm    : the final `lhs.evaluate(Some(g))` / `rhs.evaluate(Some(g))` (util/msm.rs:70-77 ->
-//                    NativeLoader::multi_scalar_multiplication, loader/native.rs:61-71) with a group of
-//                    16 lanes per proof, windowed scalar multiplication per term, warp-shuffle
-//                    reduction of the partial sums, to_affine.
+//   k_msm_var / k_msm_sum / k_to_affine : the final `lhs.evaluate(Some(g))` / `rhs.evaluate(Some(g))`
+//                    (util/msm.rs:70-77 -> NativeLoader::multi_scalar_multiplication, loader/native.rs:61-71)
 //   k_status       : per-proof `Result` -> status word (include/svk.h)
 #include "compiler.h"
 #include "g1.cuh"
@@ -69,7 +67,7 @@ __global__ void __launch_bounds__(32) k_tape(size_t n_items, const TapeOp* ops, 
 }
 
 // ------------------------------------------------------------------------------------------------
-#define MSM_LANES 16
+#define MSM_LANES SVK_MSM_LANES
 
 __device__ __forceinline__ G1Jac shfl_down_jac(const G1Jac& p, int delta) {
   G1Jac r;
@@ -98,32 +96,75 @@ __device__ __noinline__ G1Jac g1_mul_window4(const G1Affine& p, const u32* k) {
   return acc;
 }
 
-// terms: which = blockIdx.y (0 lhs, 1 rhs).  Output: out_acc[item] (svk_acc, canonical LE).
-__global__ void __launch_bounds__(128) k_proof_msm(size_t n_items, const MsmTermDev* terms_lhs, u32 n_lhs, const MsmTermDev* terms_rhs,
-                                                   u32 n_rhs, const G1Affine* fixed_bases, const G1Affine* pts, const u32* scalars,
-                                                   const u32* err, uint8_t* out_acc) {
+// Fixed-base window tables: tables[(b * 64 + w) * 16 + d] = d * 2^(4w) * fixed_bases[b]  (d = 0: identity).
+// One (base, window) per thread; run once per compiled protocol.
+__global__ void __launch_bounds__(64) k_fixed_tables(u32 n_fixed, const G1Affine* fixed_bases, G1Affine* tables) {
+  u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_fixed * SVK_FIXED_WINDOWS) return;
+  u32 b = t / SVK_FIXED_WINDOWS, w = t % SVK_FIXED_WINDOWS;
+  G1Jac pw = G1Jac::from_affine(fixed_bases[b]);
+  for (u32 k = 0; k < 4 * w; k++) pw = pw.dbl();
+  G1Affine base = pw.to_affine();
+  G1Affine* out = tables + (size_t)t * 16;
+  out[0] = G1Affine::identity();
+  G1Jac acc = G1Jac::identity();
+  for (u32 d = 1; d < 16; d++) {
+    acc = acc.add_affine(base);
+    out[d] = acc.to_affine();
+  }
+}
+
+// ---- Per-proof MSM, split by uniformity of work (ncu on the first version -- one fused kernel, 16 lanes per
+// proof -- showed 10.5 of 32 lanes active per instruction: variable-base and fixed-base lanes serialised, and
+// the final Fermat inversion ran on 2 lanes; profiles/r1_ncu_notes.md):
+//   k_msm_var    one (variable-base term, proof) per thread, all lanes do the same 4-bit-window scalar
+//                multiplication; Jacobian partial -> partials[side][term][proof]
+//   k_msm_sum    16 lanes per (proof, side): an equal slice of the fixed-base table windows per lane (mixed
+//                additions only), plus the partials and the scalar == 1 bases; shuffle reduction -> sums[side][proof]
+//   k_to_affine  one (proof, side) per thread: Fermat inversion, canonical accumulator bytes
+__global__ void __launch_bounds__(128) k_msm_var(size_t n_items, const MsmWork* var_items, u32 n_var, const G1Affine* pts,
+                                                 const u32* scalars, G1Jac* partials) {
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_items * n_var) return;
+  size_t it = gid % n_items;
+  u32 vi = (u32)(gid / n_items);
+  MsmWork wk = var_items[vi];
+  u32 k[8];
+  const uint4* sp = reinterpret_cast<const uint4*>(scalars + ((size_t)wk.slot * n_items + it) * 8);
+  uint4 lo = sp[0], hi = sp[1];
+  k[0] = lo.x; k[1] = lo.y; k[2] = lo.z; k[3] = lo.w; k[4] = hi.x; k[5] = hi.y; k[6] = hi.z; k[7] = hi.w;
+  G1Affine base = pts[(size_t)wk.base * n_items + it];
+  partials[gid] = g1_mul_window4(base, k);
+}
+
+// work: per side, per lane a list of items of kind 1 (fixed-base window slice), 2 (add base), 3 (add partial #base)
+__global__ void __launch_bounds__(128) k_msm_sum(size_t n_items, const MsmWork* work_lhs, const u32* off_lhs, const MsmWork* work_rhs,
+                                                 const u32* off_rhs, const G1Affine* fixed_bases, const G1Affine* tables,
+                                                 const G1Affine* pts, const u32* scalars, const G1Jac* partials, G1Jac* sums) {
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t item = gid / MSM_LANES;
   u32 lane = (u32)(gid % MSM_LANES);
   bool active = item < n_items;
   size_t it = active ? item : n_items - 1;  // keep whole warps in the shuffles
-  const MsmTermDev* terms = blockIdx.y ? terms_rhs : terms_lhs;
-  u32 n_terms = blockIdx.y ? n_rhs : n_lhs;
-  bool bad = err[it] != SVK_NO_ERR;
+  const MsmWork* work = blockIdx.y ? work_rhs : work_lhs;
+  const u32* off = blockIdx.y ? off_rhs : off_lhs;
   G1Jac acc = G1Jac::identity();
-  if (!bad) {
-    for (u32 t = lane; t < n_terms; t += MSM_LANES) {
-      MsmTermDev td = terms[t];
-      G1Affine base = td.fixed ? fixed_bases[td.base] : pts[(size_t)td.base * n_items + it];
-      if (td.slot < 0) {
-        acc = acc.add_affine(base);
-      } else {
-        u32 k[8];
-        const uint4* sp = reinterpret_cast<const uint4*>(scalars + ((size_t)td.slot * n_items + it) * 8);
-        uint4 lo = sp[0], hi = sp[1];
-        k[0] = lo.x; k[1] = lo.y; k[2] = lo.z; k[3] = lo.w; k[4] = hi.x; k[5] = hi.y; k[6] = hi.z; k[7] = hi.w;
-        acc = acc.add(g1_mul_window4(base, k));
+  for (u32 wi = off[lane]; wi < off[lane + 1]; wi++) {
+    MsmWork wk = work[wi];
+    if (wk.kind == 1) {
+      u32 k[8];
+      const uint4* sp = reinterpret_cast<const uint4*>(scalars + ((size_t)wk.slot * n_items + it) * 8);
+      uint4 lo = sp[0], hi = sp[1];
+      k[0] = lo.x; k[1] = lo.y; k[2] = lo.z; k[3] = lo.w; k[4] = hi.x; k[5] = hi.y; k[6] = hi.z; k[7] = hi.w;
+      const G1Affine* tb = tables + (size_t)wk.base * SVK_FIXED_WINDOWS * 16;
+      for (int w = wk.w0; w < wk.w1; w++) {
+        u32 d = (k[w >> 3] >> ((w & 7) * 4)) & 0xf;
+        acc = acc.add_affine(tb[w * 16 + d]);
       }
+    } else if (wk.kind == 2) {
+      acc = acc.add_affine(wk.fixed ? fixed_bases[wk.base] : pts[(size_t)wk.base * n_items + it]);
+    } else {
+      acc = acc.add(partials[(size_t)wk.base * n_items + it]);
     }
   }
 #pragma unroll
@@ -131,15 +172,31 @@ __global__ void __launch_bounds__(128) k_proof_msm(size_t n_items, const MsmTerm
     G1Jac o = shfl_down_jac(acc, d);
     if (lane < (u32)d) acc = acc.add(o);
   }
-  if (active && lane == 0) {
-    G1Affine a = bad ? G1Affine::identity() : acc.to_affine();
-    Fq x = a.x.from_mont(), y = a.y.from_mont();
-    uint4* o = reinterpret_cast<uint4*>(out_acc + item * 128 + (blockIdx.y ? 64 : 0));
-    o[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
-    o[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
-    o[2] = make_uint4(y.v[0], y.v[1], y.v[2], y.v[3]);
-    o[3] = make_uint4(y.v[4], y.v[5], y.v[6], y.v[7]);
-  }
+  if (active && lane == 0) sums[(size_t)blockIdx.y * n_items + item] = acc;
+}
+
+__global__ void __launch_bounds__(128) k_to_affine(size_t n_items, const G1Jac* sums, const u32* err, uint8_t* out_acc) {
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= 2 * n_items) return;
+  size_t item = gid % n_items;
+  u32 side = (u32)(gid / n_items);
+  bool bad = err[item] != SVK_NO_ERR;
+  G1Affine a = bad ? G1Affine::identity() : sums[gid].to_affine();
+  Fq x = a.x.from_mont(), y = a.y.from_mont();
+  uint4* o = reinterpret_cast<uint4*>(out_acc + item * 128 + (side ? 64 : 0));
+  o[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  o[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+  o[2] = make_uint4(y.v[0], y.v[1], y.v[2], y.v[3]);
+  o[3] = make_uint4(y.v[4], y.v[5], y.v[6], y.v[7]);
+}
+
+int svk_fixed_tables_launch(svk_ctx* ctx, ProtocolDevice* pd) {
+  u32 n_fixed = pd->n_pre + 1;
+  u32 total = n_fixed * SVK_FIXED_WINDOWS;
+  SVK_LAUNCH(ctx, "k_fixed_tables", k_fixed_tables<<<(total + 63) / 64, 64, 0, ctx->stream>>>(n_fixed, pd->d_fixed, pd->d_fixed_tables));
+  SVK_CUDA(ctx, cudaGetLastError());
+  SVK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -196,9 +253,19 @@ int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const
                                                               d_out_challenges, pd->n_challenges, d_err));
   }
   if (mode == 0) {
+    G1Jac *d_partials, *d_sums;
+    if (svk_scratch(ctx, 7, (size_t)std::max<u32>(pd->n_var, 1) * n * sizeof(G1Jac), (void**)&d_partials)) return -1;
+    if (svk_scratch(ctx, 15, 2 * n * sizeof(G1Jac), (void**)&d_sums)) return -1;
+    if (pd->n_var) {
+      size_t total = n * pd->n_var;
+      SVK_LAUNCH(ctx, "k_msm_var",
+                 k_msm_var<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(n, pd->d_var_items, pd->n_var, d_pts, d_scalars, d_partials));
+    }
     dim3 grid((unsigned)((n * MSM_LANES + 127) / 128), 2);
-    SVK_LAUNCH(ctx, "k_proof_msm",
-               k_proof_msm<<<grid, 128, 0, s>>>(n, pd->d_lhs, pd->n_lhs, pd->d_rhs, pd->n_rhs, pd->d_fixed, d_pts, d_scalars, d_err, d_out_acc));
+    SVK_LAUNCH(ctx, "k_msm_sum",
+               k_msm_sum<<<grid, 128, 0, s>>>(n, pd->d_work_lhs, pd->d_lane_off_lhs, pd->d_work_rhs, pd->d_lane_off_rhs, pd->d_fixed,
+                                              pd->d_fixed_tables, d_pts, d_scalars, d_partials, d_sums));
+    SVK_LAUNCH(ctx, "k_to_affine", k_to_affine<<<(unsigned)((2 * n + 127) / 128), 128, 0, s>>>(n, d_sums, d_err, d_out_acc));
   } else {
     SVK_CUDA(ctx, cudaMemsetAsync(d_out_acc, 0, n * 128, s));
   }

@@ -143,10 +143,10 @@ class Context:
         return self._check(self._L.svk_protocol_compile(self._c, blob, len(blob), mos, dk_id))
 
     def protocol_info(self, pid: int) -> dict:
-        out = (ctypes.c_uint32 * 12)()
+        out = (ctypes.c_uint32 * 16)()
         self._check(self._L.svk_protocol_info(self._c, pid, out))
         keys = ["proof_len", "n_instances", "n_challenges", "n_regs", "n_ops", "n_poseidon_perms", "verify_valid", "n_fr_mul",
-                "n_lhs_terms", "n_rhs_terms", "n_points", "n_scalar_slots"]
+                "n_lhs_terms", "n_rhs_terms", "n_points", "n_scalar_slots", "msm_modmul_per_proof"]
         return dict(zip(keys, [int(x) for x in out]))
 
     def modmul_peak(self, iters: int = 4000):
