@@ -116,6 +116,7 @@ void svk_destroy(svk_ctx* ctx) {
     cudaFree(p->d_ops); cudaFree(p->d_aux); cudaFree(p->d_consts); cudaFree(p->d_sched); cudaFree(p->d_lhs); cudaFree(p->d_rhs); cudaFree(p->d_fixed); cudaFree(p->d_fixed_tables); cudaFree(p->d_var_items); cudaFree(p->d_work_lhs); cudaFree(p->d_work_rhs); cudaFree(p->d_lane_off_lhs); cudaFree(p->d_lane_off_rhs);
     delete p;
   }
+  if (ctx->done) cudaEventDestroy(ctx->done);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -334,7 +335,7 @@ int svk_plonk_succinct_verify_batch(svk_ctx* ctx, int proto, size_t n, const svk
   SVK_CUDA(ctx, cudaMemcpyAsync(out_acc, d_io + off_acc, n * 128, cudaMemcpyDeviceToHost, s));
   if (out_challenges && chal_bytes) SVK_CUDA(ctx, cudaMemcpyAsync(out_challenges, d_io + off_chal, chal_bytes, cudaMemcpyDeviceToHost, s));
   SVK_CUDA(ctx, cudaMemcpyAsync(out_status, d_io + off_status, n * 4, cudaMemcpyDeviceToHost, s));
-  SVK_CUDA(ctx, cudaStreamSynchronize(s));
+  if (svk_wait(ctx)) return -1;
   return 0;
 }
 
@@ -356,7 +357,7 @@ int svk_kzg_as_fold(svk_ctx* ctx, size_t n, const svk_acc* accs, size_t group_si
   SVK_CUDA(ctx, cudaMemcpyAsync(out_acc, d_out, 128, cudaMemcpyDeviceToHost, s));
   if (out_r) SVK_CUDA(ctx, cudaMemcpyAsync(out_r, d_out + 128, 32, cudaMemcpyDeviceToHost, s));
   SVK_CUDA(ctx, cudaMemcpyAsync(out_status, d_out + 160, 4, cudaMemcpyDeviceToHost, s));
-  SVK_CUDA(ctx, cudaStreamSynchronize(s));
+  if (svk_wait(ctx)) return -1;
   return 0;
 }
 
@@ -397,12 +398,12 @@ int svk_plonk_verify_batch(svk_ctx* ctx, int proto, size_t n, const svk_fe* inst
   if (svk_plonk_verify_batch_dev(ctx, proto, n, d, n_instances, d + off_proofs, proof_stride, proof_lens ? d + off_lens : nullptr, group_size,
                                  d + off_accs, d + off_status, d + off_fold))
     return -1;
-  uint8_t folded[256];
+  // results go straight into the caller's buffers (pinned buffers keep these copies asynchronous)
   SVK_CUDA(ctx, cudaMemcpyAsync(out_status, d + off_status, n * 4, cudaMemcpyDeviceToHost, s));
-  SVK_CUDA(ctx, cudaMemcpyAsync(folded, d + off_fold, 256, cudaMemcpyDeviceToHost, s));
-  SVK_CUDA(ctx, cudaStreamSynchronize(s));
-  if (out_folded) memcpy(out_folded, folded, 128);
-  *out_ok = folded[165];
+  uint8_t folded_local[128];
+  SVK_CUDA(ctx, cudaMemcpyAsync(out_folded ? (void*)out_folded : (void*)folded_local, d + off_fold, 128, cudaMemcpyDeviceToHost, s));
+  SVK_CUDA(ctx, cudaMemcpyAsync(out_ok, d + off_fold + 165, 1, cudaMemcpyDeviceToHost, s));
+  if (svk_wait(ctx)) return -1;
   if (!*out_ok && locate_failures) {
     // every proof read fine but the folded pairing failed: decide each accumulator to name the culprits
     bool all_ok = true;
@@ -411,7 +412,7 @@ int svk_plonk_verify_batch(svk_ctx* ctx, int proto, size_t n, const svk_fe* inst
       std::vector<uint8_t> oks(n);
       if (svk_decide_launch(ctx, ctx->protocols[proto]->dk, n, d + off_accs, d + off_dec)) return -1;
       SVK_CUDA(ctx, cudaMemcpyAsync(oks.data(), d + off_dec, n, cudaMemcpyDeviceToHost, s));
-      SVK_CUDA(ctx, cudaStreamSynchronize(s));
+      if (svk_wait(ctx)) return -1;
       for (size_t i = 0; i < n; i++)
         if (!oks[i]) out_status[i] = SVK_ASSERTION_FAILURE;
     }
@@ -438,7 +439,7 @@ int svk_msm_g1(svk_ctx* ctx, size_t n, const svk_fe* scalars, const svk_g1* poin
   if (svk_msm_launch(ctx, n, d, d + off_p, d + off_o, (int*)(d + off_o + 64))) return -1;
   SVK_CUDA(ctx, cudaMemcpyAsync(out, d + off_o, 64, cudaMemcpyDeviceToHost, s));
   SVK_CUDA(ctx, cudaMemcpyAsync(out_status, d + off_o + 64, 4, cudaMemcpyDeviceToHost, s));
-  SVK_CUDA(ctx, cudaStreamSynchronize(s));
+  if (svk_wait(ctx)) return -1;
   return 0;
 }
 
@@ -458,7 +459,7 @@ int svk_g1_mul_batch(svk_ctx* ctx, size_t n, const svk_fe* scalars, const svk_g1
   SVK_CUDA(ctx, cudaMemcpyAsync(d + off_p, points, n_points * 64, cudaMemcpyHostToDevice, s));
   if (svk_g1_mul_batch_launch(ctx, n, d, d + off_p, n_points, d + off_o)) return -1;
   SVK_CUDA(ctx, cudaMemcpyAsync(out, d + off_o, n * 64, cudaMemcpyDeviceToHost, s));
-  SVK_CUDA(ctx, cudaStreamSynchronize(s));
+  if (svk_wait(ctx)) return -1;
   return 0;
 }
 

@@ -35,6 +35,7 @@ struct svk_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaEvent_t done = nullptr;  // blocking-sync event: host-buffer calls sleep instead of spinning (many contexts, few cores)
   std::string err;
   uint64_t launches = 0;
   int sm_count = 0;
@@ -94,3 +95,11 @@ inline int svk_scratch(svk_ctx* ctx, int slot, size_t bytes, void** out) {
       (ctx)->pending.push_back(pe_);                                 \
     }                                                                \
   } while (0)
+
+// Wait for everything enqueued on the context stream without burning a core.
+inline int svk_wait(svk_ctx* ctx) {
+  if (!ctx->done) SVK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->done, cudaEventBlockingSync | cudaEventDisableTiming));
+  SVK_CUDA(ctx, cudaEventRecord(ctx->done, ctx->stream));
+  SVK_CUDA(ctx, cudaEventSynchronize(ctx->done));
+  return 0;
+}

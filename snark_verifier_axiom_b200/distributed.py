@@ -113,9 +113,13 @@ class ShardedBatchVerifier:
         """End-to-end call with HOST buffers: H2D of instances + proofs (+ lengths), the batch verification,
         D2H of the per-proof statuses and the verdict.  -> (ok, status int32[n])"""
         if self.world == 1 and isinstance(self.ops, LibsvkOps):
-            st = np.zeros(n, np.int32)
-            folded = np.zeros(128, np.uint8)
-            ok = np.zeros(1, np.uint8)
+            if getattr(self, "_h_n", 0) < n:  # pinned result buffers, reused: pageable targets make the copies synchronous
+                pin = self.device.type == "cuda"
+                self._h_st = torch.zeros(n, dtype=torch.int32, pin_memory=pin).numpy()
+                self._h_folded = torch.zeros(128, dtype=torch.uint8, pin_memory=pin).numpy()
+                self._h_ok = torch.zeros(8, dtype=torch.uint8, pin_memory=pin).numpy()
+                self._h_n = n
+            st, folded, ok = self._h_st[:n], self._h_folded, self._h_ok
             o = self.ops
             rc = o.L.svk_plonk_verify_batch(o.c, self.pv.pid, n, h_inst.ctypes.data_as(ctypes.c_void_p), n_inst,
                                             h_proofs.ctypes.data_as(ctypes.c_void_p), h_proofs.shape[1],
