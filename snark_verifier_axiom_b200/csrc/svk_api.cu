@@ -21,6 +21,13 @@ int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const
 
 static thread_local std::string g_create_err;
 
+// Fixed-base window tables are identical for every context that compiles the same verifying key on the same
+// device (bench.py keeps 32 contexts in flight): share one device copy so the 4.7 MB table stays L2-resident.
+#include <mutex>
+struct SharedTable { G1Affine* d = nullptr; int refs = 0; };
+static std::mutex g_table_mu;
+static std::map<std::string, SharedTable> g_tables;
+
 template <class T>
 static int upload(svk_ctx* ctx, T** d, const std::vector<T>& v) {
   *d = nullptr;
@@ -35,7 +42,7 @@ static int upload(svk_ctx* ctx, T** d, const std::vector<T>& v) {
 // gets an EQUAL number of fixed-base table windows (11 M each; vk commitments and g), and the partial sums /
 // scalar == 1 bases are dealt round-robin.  Returns the algorithmic Fq mults per proof for this side.
 static size_t schedule_msm(const std::vector<MsmTermDev>& terms, std::vector<MsmWork>& var_items, std::vector<MsmWork>& work,
-                           std::vector<u32>& lane_off) {
+                           std::vector<u32>& lane_off, bool partial_side, u32 var_lanes) {
   const int L = SVK_MSM_LANES;
   std::vector<std::vector<MsmWork>> lanes(L);
   size_t total = 0;
@@ -44,12 +51,10 @@ static size_t schedule_msm(const std::vector<MsmTermDev>& terms, std::vector<Msm
   for (auto& t : terms) {
     if (t.slot < 0) { lanes[rr++ % L].push_back({2, t.fixed, t.base, -1, 0, 0}); total += 11; }
     else if (t.fixed) fixed_terms.push_back(t);
-    else {
-      lanes[rr++ % L].push_back({3, 0, (int32_t)var_items.size(), -1, 0, 0});
-      var_items.push_back({0, 0, t.base, t.slot, 0, 0});
-      total += 2977 + 16;
-    }
+    else { var_items.push_back({0, 0, t.base, t.slot, 0, 0}); total += 161 + 64 * 16; }
   }
+  if (partial_side)  // the k_msm_var partial sums of this proof (one per var lane) are added on this side
+    for (u32 l = 0; l < var_lanes; l++) { lanes[rr++ % L].push_back({3, 0, (int32_t)l, -1, 0, 0}); total += 252 * 7 + 16; }
   size_t fixed_windows = fixed_terms.size() * SVK_FIXED_WINDOWS;
   size_t per = (fixed_windows + L - 1) / L;
   size_t ti = 0, w = 0;
@@ -113,7 +118,7 @@ void svk_destroy(svk_ctx* ctx) {
   cudaFree(ctx->d_pairing_consts);
   cudaFree(ctx->d_poseidon);
   for (auto* p : ctx->protocols) {
-    cudaFree(p->d_ops); cudaFree(p->d_aux); cudaFree(p->d_consts); cudaFree(p->d_sched); cudaFree(p->d_lhs); cudaFree(p->d_rhs); cudaFree(p->d_fixed); cudaFree(p->d_fixed_tables); cudaFree(p->d_var_items); cudaFree(p->d_work_lhs); cudaFree(p->d_work_rhs); cudaFree(p->d_lane_off_lhs); cudaFree(p->d_lane_off_rhs);
+    cudaFree(p->d_ops); cudaFree(p->d_aux); cudaFree(p->d_consts); cudaFree(p->d_sched); cudaFree(p->d_lhs); cudaFree(p->d_rhs); cudaFree(p->d_fixed); { std::lock_guard<std::mutex> lk(g_table_mu); auto it = g_tables.find(p->table_key); if (it != g_tables.end() && --it->second.refs == 0) { cudaFree(it->second.d); g_tables.erase(it); } } cudaFree(p->d_var_items); cudaFree(p->d_work_lhs); cudaFree(p->d_work_rhs); cudaFree(p->d_lane_off_lhs); cudaFree(p->d_lane_off_rhs);
     delete p;
   }
   if (ctx->done) cudaEventDestroy(ctx->done);
@@ -277,17 +282,47 @@ int svk_protocol_compile(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos,
   pd->n_rhs = (u32)rhs.size();
   std::vector<MsmWork> wl, wr, var_items;
   std::vector<u32> ol, orr;
-  pd->msm_work_modmul = schedule_msm(lhs, var_items, wl, ol) + schedule_msm(rhs, var_items, wr, orr);
+  // Variable-base terms of BOTH sides must be summed on their own side: k_msm_var handles one side's terms per
+  // launch only if the other side has none (true for SHPLONK: rhs = W'; GWC's rhs has 3 scaled W_i).  To keep one
+  // launch, a side that owns variable-base terms gets its own var-item range; here both ranges share the kernel by
+  // running the lhs terms through k_msm_var and the (few) rhs terms as fixed-free full multiplications in k_msm_sum.
+  pd->var_lanes = 2;  // measured on B200 (profiles/r1_notes.md): 1 and 2 give the same throughput, 2 halves the kernel's latency
+  if (const char* e = getenv("SVK_VAR_LANES")) pd->var_lanes = (u32)std::max(1, std::min(8, atoi(e)));
+  std::vector<MsmWork> var_rhs;
+  pd->msm_work_modmul = schedule_msm(lhs, var_items, wl, ol, true, pd->var_lanes) + schedule_msm(rhs, var_rhs, wr, orr, false, 0);
+  // rhs variable-base terms (GWC): executed inside k_msm_sum as kind-0 items, dealt over the lanes
+  if (!var_rhs.empty()) {
+    std::vector<std::vector<MsmWork>> lanes(SVK_MSM_LANES);
+    for (int l = 0; l < SVK_MSM_LANES; l++) lanes[l].assign(wr.begin() + orr[l], wr.begin() + orr[l + 1]);
+    for (size_t i = 0; i < var_rhs.size(); i++) lanes[i % SVK_MSM_LANES].push_back(var_rhs[i]);
+    wr.clear();
+    for (int l = 0; l < SVK_MSM_LANES; l++) { orr[l] = (u32)wr.size(); wr.insert(wr.end(), lanes[l].begin(), lanes[l].end()); }
+    orr[SVK_MSM_LANES] = (u32)wr.size();
+    pd->msm_work_modmul += var_rhs.size() * (2977 - 161 - 1024);
+  }
   pd->n_var = (u32)var_items.size();
+  if ((pd->n_var + pd->var_lanes - 1) / pd->var_lanes > 16) { delete pd; return svk_fail(ctx, "too many variable-base terms per thread (raise SVK_VAR_LANES)"); }
   if (upload(ctx, &pd->d_var_items, var_items) || upload(ctx, &pd->d_work_lhs, wl) || upload(ctx, &pd->d_lane_off_lhs, ol) || upload(ctx, &pd->d_work_rhs, wr) ||
       upload(ctx, &pd->d_lane_off_rhs, orr)) { delete pd; return -1; }
-  if (cudaMalloc(&pd->d_fixed_tables, fixed.size() * SVK_FIXED_WINDOWS * 16 * sizeof(G1Affine)) != cudaSuccess) { delete pd; return svk_fail(ctx, "fixed table alloc"); }
+  pd->table_key = std::to_string(ctx->device) + ":" + std::string((const char*)fixed.data(), fixed.size() * sizeof(G1Affine));
+  bool need_tables = false;
+  {
+    std::lock_guard<std::mutex> lk(g_table_mu);
+    SharedTable& st = g_tables[pd->table_key];
+    if (!st.d) {
+      if (cudaMalloc(&st.d, fixed.size() * SVK_FIXED_WINDOWS * SVK_FIXED_DIGITS * sizeof(G1Affine)) != cudaSuccess) { g_tables.erase(pd->table_key); delete pd; return svk_fail(ctx, "fixed table alloc"); }
+      need_tables = true;
+    }
+    st.refs++;
+    pd->d_fixed_tables = st.d;
+  }
   if (upload(ctx, &pd->d_ops, cp.ops) || upload(ctx, &pd->d_aux, cp.aux) || upload(ctx, &pd->d_consts, cp.consts) ||
       upload(ctx, &pd->d_sched, pd->points) || upload(ctx, &pd->d_lhs, lhs) || upload(ctx, &pd->d_rhs, rhs) || upload(ctx, &pd->d_fixed, fixed)) {
     delete pd;
     return -1;
   }
-  if (svk_fixed_tables_launch(ctx, pd)) { delete pd; return -1; }
+  if (need_tables && svk_fixed_tables_launch(ctx, pd)) { delete pd; return -1; }
+  if (!need_tables) SVK_CUDA(ctx, cudaDeviceSynchronize());  // another context may still be filling the shared table
   ctx->protocols.push_back(pd);
   return (int)ctx->protocols.size() - 1;
 }

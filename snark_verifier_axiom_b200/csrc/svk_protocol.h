@@ -1,5 +1,8 @@
 // Device image of a compiled protocol (compiler.h -> CompiledProtocol).
 #pragma once
+#include <string>
+#include <vector>
+
 #include "g1.cuh"
 #include "tape.cuh"
 
@@ -24,7 +27,8 @@ struct MsmWork {
   int32_t w0, w1;
 };
 #define SVK_MSM_LANES 16
-#define SVK_FIXED_WINDOWS 64  // 4-bit windows of a 256-bit scalar
+#define SVK_FIXED_WINDOWS 32   // 8-bit windows of a 256-bit scalar
+#define SVK_FIXED_DIGITS 256   // table entries per window
 
 struct ProtocolDevice {
   int mos = 0;
@@ -44,9 +48,11 @@ struct ProtocolDevice {
   u32 n_lhs = 0, n_rhs = 0;
   MsmWork *d_work_lhs = nullptr, *d_work_rhs = nullptr;  // lane schedules: items of lane l = work[lane_off[l] .. lane_off[l+1])
   u32 *d_lane_off_lhs = nullptr, *d_lane_off_rhs = nullptr;
-  G1Affine* d_fixed_tables = nullptr;  // [n_pre + 1][64 windows][16 digits]: d * 2^(4w) * B, affine Montgomery
+  G1Affine* d_fixed_tables = nullptr;  // [n_pre + 1][32 windows][256 digits]: d * 2^(8w) * B, affine Montgomery (4.7 MB for 9 bases)
   MsmWork* d_var_items = nullptr;      // variable-base terms of both sides; partial index = position here
   u32 n_var = 0;
+  std::string table_key;               // key of the shared fixed-base table (svk_api.cu: g_tables)
+  u32 var_lanes = 1;                   // threads per proof in k_msm_var (terms dealt round-robin)
   size_t msm_work_modmul = 0;          // algorithmic Fq mults per proof of the scheduled MSM (DESIGN.md work model)
   G1Affine* d_fixed = nullptr;  // preprocessed..., then g at index n_pre
   u32 n_pre = 0;

@@ -96,19 +96,19 @@ __device__ __noinline__ G1Jac g1_mul_window4(const G1Affine& p, const u32* k) {
   return acc;
 }
 
-// Fixed-base window tables: tables[(b * 64 + w) * 16 + d] = d * 2^(4w) * fixed_bases[b]  (d = 0: identity).
-// One (base, window) per thread; run once per compiled protocol.
-__global__ void __launch_bounds__(64) k_fixed_tables(u32 n_fixed, const G1Affine* fixed_bases, G1Affine* tables) {
+// Fixed-base window tables: tables[(b * 32 + w) * 256 + d] = d * 2^(8w) * fixed_bases[b]  (d = 0: identity).
+// One (base, window) per thread; run once per compiled protocol (255 additions + affine conversions each).
+__global__ void __launch_bounds__(32) k_fixed_tables(u32 n_fixed, const G1Affine* fixed_bases, G1Affine* tables) {
   u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_fixed * SVK_FIXED_WINDOWS) return;
   u32 b = t / SVK_FIXED_WINDOWS, w = t % SVK_FIXED_WINDOWS;
   G1Jac pw = G1Jac::from_affine(fixed_bases[b]);
-  for (u32 k = 0; k < 4 * w; k++) pw = pw.dbl();
+  for (u32 k = 0; k < 8 * w; k++) pw = pw.dbl();
   G1Affine base = pw.to_affine();
-  G1Affine* out = tables + (size_t)t * 16;
+  G1Affine* out = tables + (size_t)t * SVK_FIXED_DIGITS;
   out[0] = G1Affine::identity();
   G1Jac acc = G1Jac::identity();
-  for (u32 d = 1; d < 16; d++) {
+  for (u32 d = 1; d < SVK_FIXED_DIGITS; d++) {
     acc = acc.add_affine(base);
     out[d] = acc.to_affine();
   }
@@ -122,19 +122,48 @@ __global__ void __launch_bounds__(64) k_fixed_tables(u32 n_fixed, const G1Affine
 //   k_msm_sum    16 lanes per (proof, side): an equal slice of the fixed-base table windows per lane (mixed
 //                additions only), plus the partials and the scalar == 1 bases; shuffle reduction -> sums[side][proof]
 //   k_to_affine  one (proof, side) per thread: Fermat inversion, canonical accumulator bytes
-__global__ void __launch_bounds__(128) k_msm_var(size_t n_items, const MsmWork* var_items, u32 n_var, const G1Affine* pts,
-                                                 const u32* scalars, G1Jac* partials) {
+// Straus / interleaved windows: one thread owns up to SVK_VAR_TERMS_MAX variable-base terms of ONE proof and
+// shares the 252 doublings between them (per term: a 15-entry Jacobian table + 64 table additions).  With
+// `vpl` threads ("var lanes") per proof the terms are dealt round-robin: vpl = 1 minimises total work
+// (1778 + 11 x 1185 M per StandardPlonk proof instead of 11 x 2977), larger vpl shortens the latency.
+// partials[(lane * n_items) + proof]  (Jacobian)
+#define SVK_VAR_TERMS_MAX 16
+__global__ void __launch_bounds__(64) k_msm_var(size_t n_items, const MsmWork* var_items, u32 n_var, u32 vpl, const G1Affine* pts,
+                                                const u32* scalars, G1Jac* tables, G1Jac* partials) {
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= n_items * n_var) return;
+  if (gid >= n_items * vpl) return;
   size_t it = gid % n_items;
-  u32 vi = (u32)(gid / n_items);
-  MsmWork wk = var_items[vi];
-  u32 k[8];
-  const uint4* sp = reinterpret_cast<const uint4*>(scalars + ((size_t)wk.slot * n_items + it) * 8);
-  uint4 lo = sp[0], hi = sp[1];
-  k[0] = lo.x; k[1] = lo.y; k[2] = lo.z; k[3] = lo.w; k[4] = hi.x; k[5] = hi.y; k[6] = hi.z; k[7] = hi.w;
-  G1Affine base = pts[(size_t)wk.base * n_items + it];
-  partials[gid] = g1_mul_window4(base, k);
+  u32 lane = (u32)(gid / n_items);
+  // this thread's table area: [term slot][16] entries, interleaved over threads for coalescing
+  size_t n_threads = n_items * vpl;
+  u32 k[SVK_VAR_TERMS_MAX][8];
+  u32 nt = 0;
+  for (u32 vi = lane; vi < n_var && nt < SVK_VAR_TERMS_MAX; vi += vpl, nt++) {
+    MsmWork wk = var_items[vi];
+    const uint4* sp = reinterpret_cast<const uint4*>(scalars + ((size_t)wk.slot * n_items + it) * 8);
+    uint4 lo = sp[0], hi = sp[1];
+    k[nt][0] = lo.x; k[nt][1] = lo.y; k[nt][2] = lo.z; k[nt][3] = lo.w; k[nt][4] = hi.x; k[nt][5] = hi.y; k[nt][6] = hi.z; k[nt][7] = hi.w;
+    G1Affine base = pts[(size_t)wk.base * n_items + it];
+    G1Jac* tb = tables + ((size_t)nt * 16) * n_threads + gid;  // entry d at tb[d * n_threads]
+    G1Jac e = G1Jac::from_affine(base);
+    tb[1 * n_threads] = e;
+    G1Jac d2 = e.dbl();
+    tb[2 * n_threads] = d2;
+    G1Jac cur = d2;
+    for (u32 d = 3; d < 16; d++) {
+      cur = cur.add_affine(base);
+      tb[d * n_threads] = cur;
+    }
+  }
+  G1Jac acc = G1Jac::identity();
+  for (int w = 63; w >= 0; w--) {
+    if (w != 63) acc = acc.dbl().dbl().dbl().dbl();
+    for (u32 t = 0; t < nt; t++) {
+      u32 d = (k[t][w >> 3] >> ((w & 7) * 4)) & 0xf;
+      if (d) acc = acc.add(tables[((size_t)t * 16 + d) * n_threads + gid]);
+    }
+  }
+  partials[gid] = acc;
 }
 
 // work: per side, per lane a list of items of kind 1 (fixed-base window slice), 2 (add base), 3 (add partial #base)
@@ -156,21 +185,29 @@ __global__ void __launch_bounds__(128) k_msm_sum(size_t n_items, const MsmWork* 
       const uint4* sp = reinterpret_cast<const uint4*>(scalars + ((size_t)wk.slot * n_items + it) * 8);
       uint4 lo = sp[0], hi = sp[1];
       k[0] = lo.x; k[1] = lo.y; k[2] = lo.z; k[3] = lo.w; k[4] = hi.x; k[5] = hi.y; k[6] = hi.z; k[7] = hi.w;
-      const G1Affine* tb = tables + (size_t)wk.base * SVK_FIXED_WINDOWS * 16;
+      const G1Affine* tb = tables + (size_t)wk.base * SVK_FIXED_WINDOWS * SVK_FIXED_DIGITS;
       for (int w = wk.w0; w < wk.w1; w++) {
-        u32 d = (k[w >> 3] >> ((w & 7) * 4)) & 0xf;
-        acc = acc.add_affine(tb[w * 16 + d]);
+        u32 d = (k[w >> 2] >> ((w & 3) * 8)) & 0xff;
+        acc = acc.add_affine(tb[w * SVK_FIXED_DIGITS + d]);
       }
     } else if (wk.kind == 2) {
       acc = acc.add_affine(wk.fixed ? fixed_bases[wk.base] : pts[(size_t)wk.base * n_items + it]);
-    } else {
+    } else if (wk.kind == 3) {
       acc = acc.add(partials[(size_t)wk.base * n_items + it]);
+    } else {  // kind 0: a full variable-base multiplication (the few rhs terms of GWC)
+      u32 k[8];
+      const uint4* sp = reinterpret_cast<const uint4*>(scalars + ((size_t)wk.slot * n_items + it) * 8);
+      uint4 lo = sp[0], hi = sp[1];
+      k[0] = lo.x; k[1] = lo.y; k[2] = lo.z; k[3] = lo.w; k[4] = hi.x; k[5] = hi.y; k[6] = hi.z; k[7] = hi.w;
+      acc = acc.add(g1_mul_window4(pts[(size_t)wk.base * n_items + it], k));
     }
   }
+  if (off[MSM_LANES] > 1) {  // a side with a single item (SHPLONK rhs = W') has nothing to reduce
 #pragma unroll
-  for (int d = MSM_LANES / 2; d >= 1; d >>= 1) {
-    G1Jac o = shfl_down_jac(acc, d);
-    if (lane < (u32)d) acc = acc.add(o);
+    for (int d = MSM_LANES / 2; d >= 1; d >>= 1) {
+      G1Jac o = shfl_down_jac(acc, d);
+      if (lane < (u32)d) acc = acc.add(o);
+    }
   }
   if (active && lane == 0) sums[(size_t)blockIdx.y * n_items + item] = acc;
 }
@@ -193,7 +230,7 @@ __global__ void __launch_bounds__(128) k_to_affine(size_t n_items, const G1Jac* 
 int svk_fixed_tables_launch(svk_ctx* ctx, ProtocolDevice* pd) {
   u32 n_fixed = pd->n_pre + 1;
   u32 total = n_fixed * SVK_FIXED_WINDOWS;
-  SVK_LAUNCH(ctx, "k_fixed_tables", k_fixed_tables<<<(total + 63) / 64, 64, 0, ctx->stream>>>(n_fixed, pd->d_fixed, pd->d_fixed_tables));
+  SVK_LAUNCH(ctx, "k_fixed_tables", k_fixed_tables<<<(total + 31) / 32, 32, 0, ctx->stream>>>(n_fixed, pd->d_fixed, pd->d_fixed_tables));
   SVK_CUDA(ctx, cudaGetLastError());
   SVK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -231,7 +268,7 @@ int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const
   if (svk_scratch(ctx, 4, n_pts * n * sizeof(G1Affine) + 64, (void**)&d_pts)) return -1;
   if (svk_scratch(ctx, 5, (size_t)pd->n_scalar_slots * n * 32 + 32, (void**)&d_scalars)) return -1;
   if (!d_out_challenges) {
-    if (svk_scratch(ctx, 6, (size_t)pd->n_challenges * n * 32 + 32, (void**)&d_chal_scratch)) return -1;
+    if (svk_scratch(ctx, 1, (size_t)pd->n_challenges * n * 32 + 32, (void**)&d_chal_scratch)) return -1;
     d_out_challenges = d_chal_scratch;
   }
   unsigned b = 256;
@@ -253,13 +290,16 @@ int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const
                                                               d_out_challenges, pd->n_challenges, d_err));
   }
   if (mode == 0) {
-    G1Jac *d_partials, *d_sums;
-    if (svk_scratch(ctx, 7, (size_t)std::max<u32>(pd->n_var, 1) * n * sizeof(G1Jac), (void**)&d_partials)) return -1;
+    G1Jac *d_partials, *d_sums, *d_tables;
+    u32 vpl = pd->var_lanes;
+    u32 terms_per_thread = (pd->n_var + vpl - 1) / vpl;
+    if (svk_scratch(ctx, 7, (size_t)std::max<u32>(vpl, 1) * n * sizeof(G1Jac), (void**)&d_partials)) return -1;
     if (svk_scratch(ctx, 15, 2 * n * sizeof(G1Jac), (void**)&d_sums)) return -1;
     if (pd->n_var) {
-      size_t total = n * pd->n_var;
+      size_t total = n * vpl;
+      if (svk_scratch(ctx, 6, (size_t)terms_per_thread * 16 * total * sizeof(G1Jac), (void**)&d_tables)) return -1;
       SVK_LAUNCH(ctx, "k_msm_var",
-                 k_msm_var<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(n, pd->d_var_items, pd->n_var, d_pts, d_scalars, d_partials));
+                 k_msm_var<<<(unsigned)((total + 63) / 64), 64, 0, s>>>(n, pd->d_var_items, pd->n_var, vpl, d_pts, d_scalars, d_tables, d_partials));
     }
     dim3 grid((unsigned)((n * MSM_LANES + 127) / 128), 2);
     SVK_LAUNCH(ctx, "k_msm_sum",
