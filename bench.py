@@ -35,7 +35,8 @@ def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=128)
-    ap.add_argument("--inflight", type=int, default=32, help="independent batches in flight (one libsvk context + stream each)")
+    ap.add_argument("--inflight", type=int, default=8, help="launches in flight (one libsvk context + stream each)")
+    ap.add_argument("--batches-per-launch", type=int, default=8, help="4096-proof batches verified by one call (each folded + decided on its own)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4096, help="proofs per GPU per step")
     ap.add_argument("--group-size", type=int, default=8, help="KzgAs fold group size (0 = the reference's flat fold)")
@@ -166,12 +167,12 @@ class Slot:
     keep several independent 4096-proof batches in flight, which is how a throughput device hides the
     latency-bound tail of a batch (serial fold sponge, the single pairing)."""
 
-    def __init__(self, torch, V, ShardedBatchVerifier, g, local, dev, world, rank, group_size):
+    def __init__(self, torch, V, ShardedBatchVerifier, g, local, dev, world, rank, group_size, max_batches):
         self.ctx = V.Context(local)
         self.stream = torch.cuda.Stream(device=dev)
         self.ctx.set_stream(self.stream.cuda_stream)
         self.pv = V.PlonkVerifier(self.ctx, g["dk"], g["protocol"], V.SHPLONK)
-        self.sv = ShardedBatchVerifier(self.pv, world, rank, dev, self.stream, group_size=group_size)
+        self.sv = ShardedBatchVerifier(self.pv, world, rank, dev, self.stream, group_size=group_size, max_batches=max_batches)
 
 
 def run_ours(args):
@@ -190,10 +191,13 @@ def run_ours(args):
     from snark_verifier_axiom_b200 import verifier as V
     from snark_verifier_axiom_b200.distributed import ShardedBatchVerifier
 
-    g, reps, np = make_workload(args.batch)
-    n = args.batch
+    B = max(1, args.batches_per_launch)
+    g, reps, np = make_workload(args.batch * B)
+    nb1 = args.batch           # proofs per batch (= per step)
+    n = args.batch * B         # proofs per launch
     S = max(1, args.inflight)
-    slots = [Slot(torch, V, ShardedBatchVerifier, g, local, dev, world, rank, args.group_size) for _ in range(S)]
+    steps = -(-args.steps // B) * B  # whole launches
+    slots = [Slot(torch, V, ShardedBatchVerifier, g, local, dev, world, rank, args.group_size, B) for _ in range(S)]
     pv = slots[0].pv
     inst, n_inst, proofs, lens = pv.pack(reps)
     h_inst = torch.from_numpy(inst).pin_memory()
@@ -210,10 +214,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def launch(k):
+    def launch(k, nb=B):
         sl = slots[k % S]
         di, dp = d_inputs[k % n_copies]
-        sl.sv.verify_dev(di, n_inst, dp, n)
+        if nb == B:
+            sl.sv.verify_dev(di, n_inst, dp, n, n_batches=B)
+        else:
+            sl.sv.verify_dev(di.view(n, -1)[: nb * nb1], n_inst, dp[: nb * nb1], nb * nb1, n_batches=nb)
 
     # ---- warm-up (every slot)
     for k in range(max(args.warmup, 1) * S):
@@ -222,16 +229,20 @@ def run_ours(args):
     for sl in slots:
         assert sl.sv.last_ok(), "warm-up batch did not verify"
 
-    # ---- single-batch latency (one slot, nothing else in flight)
-    lat = []
-    for k in range(3):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(slots[0].stream)
-        slots[0].sv.verify_dev(*d_inputs[k % n_copies][:1], n_inst, d_inputs[k % n_copies][1], n)
-        e1.record(slots[0].stream)
-        slots[0].stream.synchronize()
-        lat.append(e0.elapsed_time(e1))
-    latency_ms = min(lat)
+    # ---- latency of ONE 4096-proof batch and of one launch of B batches (one slot, nothing else in flight)
+    def one_latency(nb):
+        lat = []
+        for k in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(slots[0].stream)
+            launch(0, nb)
+            e1.record(slots[0].stream)
+            slots[0].stream.synchronize()
+            lat.append(e0.elapsed_time(e1))
+        return min(lat)
+
+    latency_ms = one_latency(1)
+    launch_latency_ms = one_latency(B)
 
     # ---- timed: exactly K steps (batches), round-robin over the in-flight slots; device time by CUDA
     # events on the launching streams: from a common start event to the last slot's end event
@@ -244,7 +255,8 @@ def run_ours(args):
     e_start.record(master)
     for sl in slots:
         sl.stream.wait_event(e_start)
-    for k in range(args.steps):
+    n_launches = steps // B
+    for k in range(n_launches):
         launch(k)
     e_ends = []
     for sl in slots:
@@ -259,21 +271,22 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    ms_per_step = ms_total / args.steps
+    ms_per_step = ms_total / steps
     for sl in slots:
         assert sl.sv.last_ok(), "timed batch did not verify"
-    value = world * n / (ms_per_step * 1e-3)
+    value = world * nb1 / (ms_per_step * 1e-3)
 
     # ---- e2e: the public host-buffer call (pinned host buffers -> H2D of proofs + instances, verification,
     # D2H of statuses + verdict inside every call), same number of batches in flight (one host thread per slot)
-    e2e_steps = max(S, min(args.steps, 4 * S))
+    e2e_launches = max(S, min(n_launches, 4 * S))
+    e2e_steps = e2e_launches * B
     h_i, h_p, h_l = h_inst.numpy(), h_proofs.numpy(), torch.from_numpy(lens.astype(np.int32)).pin_memory().numpy().view(np.uint32)
 
     def e2e_worker(si):
         torch.cuda.set_device(local)
         res = None
-        for k in range(si, e2e_steps, S):
-            res = slots[si].sv.verify_host(h_i, n_inst, h_p, h_l, n)
+        for k in range(si, e2e_launches, S):
+            res = slots[si].sv.verify_host(h_i, n_inst, h_p, h_l, n, n_batches=B)
         return res
 
     pool = ThreadPoolExecutor(S) if world == 1 else None
@@ -284,8 +297,8 @@ def run_ours(args):
     if world > 1:
         for sl in slots:
             e2e_bufs.append(dict(d_inst=torch.empty_like(d_inputs[0][0]), d_proofs=torch.empty_like(d_inputs[0][1]),
-                                 h_status=torch.zeros(n, dtype=torch.int32).pin_memory(), h_rec=torch.zeros(256, dtype=torch.uint8).pin_memory(),
-                                 h_gather=torch.zeros(world * 256, dtype=torch.uint8).pin_memory(), h_final=torch.zeros(256, dtype=torch.uint8).pin_memory()))
+                                 h_status=torch.zeros(n, dtype=torch.int32).pin_memory(),
+                                 h_gather=torch.zeros(world * B * 256, dtype=torch.uint8).pin_memory(), h_final=torch.zeros(B * 256, dtype=torch.uint8).pin_memory()))
 
     def e2e_async(steps):
         for k in range(steps):
@@ -293,7 +306,7 @@ def run_ours(args):
             with torch.cuda.stream(sl.stream):
                 b["d_inst"].copy_(h_inst, non_blocking=True)
                 b["d_proofs"].copy_(h_proofs, non_blocking=True)
-            sl.sv.verify_dev(b["d_inst"], n_inst, b["d_proofs"], n)
+            sl.sv.verify_dev(b["d_inst"], n_inst, b["d_proofs"], n, n_batches=B)
             with torch.cuda.stream(sl.stream):
                 b["h_status"].copy_(sl.sv.d_status[:n], non_blocking=True)
                 b["h_gather"].copy_(sl.sv.d_gather, non_blocking=True)
@@ -301,9 +314,9 @@ def run_ours(args):
         torch.cuda.synchronize()
         out = []
         for sl, b in zip(slots, e2e_bufs):
-            g_ = b["h_gather"].numpy().reshape(world, 256)
-            f_ = b["h_final"].numpy()
-            ok_ = bool(g_[:, 165].all() and f_[164] and not f_[160:164].any())
+            g_ = b["h_gather"].numpy().reshape(world, B, 256)
+            f_ = b["h_final"].numpy().reshape(B, 256)
+            ok_ = bool(g_[:, :, 165].all() and f_[:, 164].all() and not f_[:, 160:164].any())
             out.append((ok_, b["h_status"].numpy()))
         return out
 
@@ -316,7 +329,7 @@ def run_ours(args):
     if pool:
         results = list(pool.map(e2e_worker, range(S)))
     else:
-        results = e2e_async(e2e_steps)
+        results = e2e_async(e2e_launches)
     barrier()
     dt = time.perf_counter() - t0
     for ok, status in results:
@@ -324,9 +337,9 @@ def run_ours(args):
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = world * n * e2e_steps / float(t.item())
-    h2d = int(h_i.nbytes + h_p.nbytes + h_l.nbytes)
-    d2h = int(n * 4 + 256)
+    e2e_val = world * nb1 * e2e_steps / float(t.item())
+    h2d = int(h_i.nbytes + h_p.nbytes + h_l.nbytes) // B   # per step (= per 4096-proof batch)
+    d2h = int(nb1 * 4 + 256)
 
     # ---- per-kernel device time (CUDA events around every launch, one batch in flight) -> roofline.
     # Runs on EVERY rank: verify_dev contains the all_gather when world > 1.
@@ -338,7 +351,7 @@ def run_ours(args):
     for k in range(prof_steps):
         with torch.cuda.stream(sl.stream):
             flush.fill_(1)
-        sl.sv.verify_dev(d_inputs[k % n_copies][0], n_inst, d_inputs[k % n_copies][1], n)
+        sl.sv.verify_dev(d_inputs[k % n_copies][0], n_inst, d_inputs[k % n_copies][1], n, n_batches=B)
     buf = ctypes.create_string_buffer(1 << 16)
     L.svk_profile_report(c, buf, len(buf))
     L.svk_profile_enable(c, 0)
@@ -351,30 +364,32 @@ def run_ours(args):
         work = {
             "k_tape": n * info["n_fr_mul"],
             "k_decompress": n * info["n_points"] * 372,
-            "k_msm_var": n * info["msm_modmul_per_proof"],  # k_msm_var + k_msm_sum + k_to_affine together; k_msm_var carries > 80 % of it
+            "k_msm_var": n * info["msm_var_modmul_per_proof"],
         }
-        kernels = {k: {"launches_per_step": v["count"] / prof_steps, "ms_per_step": v["ms"] / prof_steps} for k, v in prof.items()}
+        work_other = n * (info["msm_modmul_per_proof"] - info["msm_var_modmul_per_proof"])  # k_msm_sum + k_to_affine
+        kernels = {k: {"launches": v["count"] / prof_steps, "ms_per_launch_of_B_batches": v["ms"] / prof_steps} for k, v in prof.items()}
         name = max((k for k in prof if k in work), key=lambda k: prof[k]["ms"])
         ms_launch = prof[name]["ms"] / prof[name]["count"]
         ach = work[name] / (ms_launch * 1e-3)
-        total_work = sum(work.values())
+        total_work = (sum(work.values()) + work_other) / B  # per 4096-proof batch (fold and pairing not counted: < 8 %)
         roofline = {
             "bound": "imad", "kernel": name, "achieved": ach / 1e9, "peak": peak / 1e9,
             "unit": "Gmodmul/s (1 modmul = one 8x32-bit-limb Montgomery multiplication = 139 IMAD + 37 IADD3, cuobjdump)",
             "frac": ach / peak, "traffic": None,
             "peak_source": "measured in this run: svk_bench_modmul_peak (independent Montgomery-mul chains, 8 warps/SMSP on all SMs)",
-            "kernel_ms_per_launch": ms_launch, "kernels_single_batch": kernels,
+            "kernel_ms_per_launch": ms_launch, "batches_per_launch": B, "kernels_one_launch_in_flight": kernels,
             "whole_step_frac": (total_work * world / (ms_per_step * 1e-3)) / peak,
             "hbm_gbs_algorithmic": (h2d + d2h) / (ms_per_step * 1e-3) / 1e9,
         }
         base = None if args.no_cpu_baseline else cpu_baseline(g, args.cpu_sample, args.group_size)
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (254-bit Fq/Fr Montgomery, integer pipe)",
             "data": "synthetic: 64 distinct trapdoor-forged StandardPlonk k=8 SHPLONK proofs (tests/golden, oracle-generated) tiled to the batch",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": n, "global_batch": world * n, "proof_bytes": info["proof_len"], "fold_group_size": args.group_size,
+            "config": {"workload": WORKLOAD, "batch_per_gpu": nb1, "global_batch": world * nb1, "proof_bytes": info["proof_len"], "fold_group_size": args.group_size,
+                       "batches_per_launch": B, "launches_in_flight": S, "launch_latency_ms": launch_latency_ms,
                        "fold": "flat (reference aggregation.rs:235-245)" if args.group_size in (0, 1) else f"tree, groups of {args.group_size}",
-                       "batches_in_flight": S, "single_batch_latency_ms": latency_ms,
+                       "batches_in_flight": S * B, "single_batch_latency_ms": latency_ms,
                        "l2": f"inputs rotate over {n_copies} distinct device copies ({n_copies * (h2d >> 20)} MiB > L2)",
                        "parallelism": f"proof-sharded x{world}, NCCL all_gather of {world} folded accumulators" if world > 1 else "single GPU"},
             "clocks": clocks, "gpu_launches": int(launches),

@@ -80,7 +80,8 @@ int svk_kzg_decide_batch_dev(svk_ctx* ctx, int dk, size_t n, const void* d_accs,
  * reference would reject with Error::InvalidProtocol still compiles; its proofs get that status. */
 int svk_protocol_compile(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos, int dk);
 /* out[16] = { proof_len, n_instances, n_challenges, n_regs, n_ops, n_poseidon_perms, verify_valid,
- *             n_fr_mul, n_lhs_terms, n_rhs_terms, n_points, n_scalar_slots, msm_modmul_per_proof, 0, 0, 0 } */
+ *             n_fr_mul, n_lhs_terms, n_rhs_terms, n_points, n_scalar_slots, msm_modmul_per_proof (all three MSM
+ *             kernels), msm_var_modmul_per_proof (k_msm_var only), n_var_terms, var_lanes } */
 int svk_protocol_info(svk_ctx* ctx, int proto, uint32_t* out);
 
 /* ---- PlonkSuccinctVerifier::{read_proof, verify} (verifier/plonk.rs:32-93) over a batch ----------
@@ -137,6 +138,23 @@ int svk_msm_g1_dev(svk_ctx* ctx, size_t n, const void* d_scalars, const void* d_
 /* Batched `base * scalar` (loader/native.rs:67): out[i] = scalars[i] * points[i % n_points]. */
 int svk_g1_mul_batch(svk_ctx* ctx, size_t n, const svk_fe* scalars, const svk_g1* points, size_t n_points, svk_g1* out);
 int svk_g1_mul_batch_dev(svk_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, size_t n_points, void* d_out);
+
+/* Several batches per call: n_batches batches of batch_size proofs laid out back to back.  Every batch is folded
+ * and decided on its own (same results as n_batches separate svk_plonk_verify_batch calls); the kernels of one call
+ * serve all batches, so the serial tail of a batch (fold levels, the pairing) is shared.  Records, 256 B per batch:
+ * { svk_acc folded ; svk_fe r ; int32 fold_status ; uint8 decide_ok ; uint8 ok ; padding }. */
+int svk_plonk_verify_multi(svk_ctx* ctx, int proto, size_t n_batches, size_t batch_size, const svk_fe* instances, uint32_t n_instances,
+                           const uint8_t* proofs, size_t proof_stride, const uint32_t* proof_lens, size_t group_size, int locate_failures,
+                           int32_t* out_status, uint8_t* out_records);
+int svk_plonk_verify_multi_dev(svk_ctx* ctx, int proto, size_t n_batches, size_t batch_size, const void* d_instances, uint32_t n_instances,
+                               const void* d_proofs, size_t proof_stride, const void* d_proof_lens, size_t group_size, void* d_out_accs,
+                               void* d_out_status, void* d_out_records);
+
+/* Segmented fold / decide on 256-byte records (the layout above), device pointers: n_seg independent groups of n
+ * accumulators each ([seg][n] x svk_acc) -> one record per segment; decide fills `decide_ok` of every record.
+ * Used for the cross-GPU level of a sharded verification (distributed.py). */
+int svk_kzg_as_fold_multi_dev(svk_ctx* ctx, size_t n_seg, size_t n, const void* d_accs, size_t group_size, void* d_out_records);
+int svk_kzg_decide_records_dev(svk_ctx* ctx, int dk, size_t n_records, void* d_records);
 
 /* ---- micro-benchmark of the integer-multiply roofline (DESIGN.md "IMAD peak") ------------------
  * Runs `iters` dependent Montgomery multiplications per thread on every SM; returns modmul/s. */

@@ -43,6 +43,10 @@ def _load():
     lib.svk_msm_g1_dev.argtypes = [vp, sz, vp, vp, vp, vp]
     lib.svk_g1_mul_batch.argtypes = [vp, sz, vp, vp, sz, vp]
     lib.svk_g1_mul_batch_dev.argtypes = [vp, sz, vp, vp, sz, vp]
+    lib.svk_plonk_verify_multi.argtypes = [vp, i32, sz, sz, vp, ctypes.c_uint32, vp, sz, vp, sz, i32, vp, vp]
+    lib.svk_plonk_verify_multi_dev.argtypes = [vp, i32, sz, sz, vp, ctypes.c_uint32, vp, sz, vp, sz, vp, vp, vp]
+    lib.svk_kzg_as_fold_multi_dev.argtypes = [vp, sz, sz, vp, sz, vp]
+    lib.svk_kzg_decide_records_dev.argtypes = [vp, i32, sz, vp]
     lib.svk_bench_modmul_peak.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     return lib
 

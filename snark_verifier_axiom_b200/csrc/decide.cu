@@ -16,29 +16,34 @@ __device__ __forceinline__ G1Affine load_g1_canon(const uint8_t* p) {
 
 // status: bit0 = accept.  A point that is not a canonical on-curve encoding makes the reference's
 // `G1Affine` unconstructible; such accumulators are reported as reject.
-__global__ void __launch_bounds__(64) k_decide(size_t n, const uint8_t* accs, uint8_t* out_ok, const G2Line* t_g2,
-                                               const G2Line* t_neg_sg2, const PairingConsts* consts) {
+__global__ void __launch_bounds__(64) k_decide(size_t n, const uint8_t* accs, size_t acc_stride, uint8_t* out_ok, size_t ok_stride,
+                                               const G2Line* t_g2, const G2Line* t_neg_sg2, const PairingConsts* consts) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  G1Affine lhs = load_g1_canon(accs + i * 128);
-  G1Affine rhs = load_g1_canon(accs + i * 128 + 64);
+  G1Affine lhs = load_g1_canon(accs + i * acc_stride);
+  G1Affine rhs = load_g1_canon(accs + i * acc_stride + 64);
   bool ok = Fq::is_canonical(lhs.x.v) && Fq::is_canonical(lhs.y.v) && Fq::is_canonical(rhs.x.v) && Fq::is_canonical(rhs.y.v);
   if (!lhs.is_identity()) { lhs.x = lhs.x.to_mont(); lhs.y = lhs.y.to_mont(); }
   if (!rhs.is_identity()) { rhs.x = rhs.x.to_mont(); rhs.y = rhs.y.to_mont(); }
   ok = ok && g1_on_curve(lhs) && g1_on_curve(rhs);
   bool acc = false;
   if (ok) acc = kzg_decide(lhs, rhs, t_g2, t_neg_sg2, *consts);
-  out_ok[i] = acc ? 1 : 0;
+  out_ok[i * ok_stride] = acc ? 1 : 0;
 }
 
+int svk_decide_launch_strided(svk_ctx* ctx, int dk, size_t n, const void* d_accs, size_t acc_stride, void* d_ok, size_t ok_stride);
 int svk_decide_launch(svk_ctx* ctx, int dk, size_t n, const void* d_accs, void* d_ok) {
+  return svk_decide_launch_strided(ctx, dk, n, d_accs, 128, d_ok, 1);
+}
+
+int svk_decide_launch_strided(svk_ctx* ctx, int dk, size_t n, const void* d_accs, size_t acc_stride, void* d_ok, size_t ok_stride) {
   if (dk < 0 || dk >= (int)ctx->dks.size()) return svk_fail(ctx, "bad deciding-key id %d", dk);
   if (n == 0) return 0;
   const DkDevice& k = ctx->dks[dk];
   unsigned block = 64;
   unsigned grid = (unsigned)((n + block - 1) / block);
   SVK_LAUNCH(ctx, "k_decide",
-             k_decide<<<grid, block, 0, ctx->stream>>>(n, (const uint8_t*)d_accs, (uint8_t*)d_ok, k.d_lines_g2, k.d_lines_neg_sg2,
+             k_decide<<<grid, block, 0, ctx->stream>>>(n, (const uint8_t*)d_accs, acc_stride, (uint8_t*)d_ok, ok_stride, k.d_lines_g2, k.d_lines_neg_sg2,
                                                        ctx->d_pairing_consts));
   SVK_CUDA(ctx, cudaGetLastError());
   return 0;

@@ -23,12 +23,15 @@ __device__ __forceinline__ void load_canon32(u32* v, const uint8_t* p) {
 
 // status word: 0 ok, else SVK_TRANSCRIPT | sub << 8 (identity point: common_ec_point fails,
 // transcript/halo2.rs:214-224; non-canonical coordinate: not a G1Affine at all)
-__global__ void __launch_bounds__(32) k_fold_sponge(size_t n, size_t m, const uint8_t* accs, const PoseidonConsts* pk, u32* scalars,
-                                                    u32* out_r, int32_t* status) {
-  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+// Segments: `n_seg` independent batches of `n` accumulators each, laid out back to back; groups never cross a
+// segment boundary, so one launch folds the same tree level of every batch.
+__global__ void __launch_bounds__(32) k_fold_sponge(size_t n_seg, size_t n, size_t m, const uint8_t* accs, const PoseidonConsts* pk, u32* scalars,
+                                                    u32* out_r, size_t out_r_stride_words, int32_t* status, size_t status_stride_words) {
+  size_t G = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t n_groups = (n + m - 1) / m;
-  if (g >= n_groups) return;
-  size_t begin = g * m, end = begin + m < n ? begin + m : n;
+  if (G >= n_groups * n_seg) return;
+  size_t seg = G / n_groups, g = G % n_groups;
+  size_t begin = seg * n + g * m, end = (g * m + m < n ? g * m + m : n) + seg * n;
   PoseidonState st;
   poseidon_init(st, *pk);
   int32_t bad = 0;
@@ -51,7 +54,7 @@ __global__ void __launch_bounds__(32) k_fold_sponge(size_t n, size_t m, const ui
   Fr r = st.s[1];
   Fr rc = r.from_mont();
   if (out_r)
-    for (int k = 0; k < 8; k++) out_r[g * 8 + k] = rc.v[k];
+    for (int k = 0; k < 8; k++) out_r[seg * out_r_stride_words + k] = rc.v[k];
   // powers r^j, j = 0.. (loader.rs:71-78); r^0 = 1 is not stored (the MSM adds the base directly)
   Fr p = r;
   for (size_t i = begin + 1; i < end; i++) {
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(32) k_fold_sponge(size_t n, size_t m, const ui
     o[1] = make_uint4(pc.v[4], pc.v[5], pc.v[6], pc.v[7]);
     p = p * r;
   }
-  if (bad) atomicMax(status, bad);
+  if (bad) atomicMax(status + seg * status_stride_words, bad);
 }
 
 __device__ __noinline__ G1Jac fold_mul_window4(const G1Affine& p, const u32* k) {
@@ -80,12 +83,15 @@ __device__ __noinline__ G1Jac fold_mul_window4(const G1Affine& p, const u32* k) 
 }
 
 // grid = (n_groups, 2); blockDim = L (power of two); dynamic smem = L * sizeof(G1Jac)
-__global__ void k_group_msm(size_t n, size_t m, const uint8_t* accs, const u32* scalars, uint8_t* out_accs, int32_t* status) {
+__global__ void k_group_msm(size_t n, size_t m, const uint8_t* accs, const u32* scalars, uint8_t* out_accs, size_t out_stride,
+                            int32_t* status, size_t status_stride_words) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   G1Jac* sm = reinterpret_cast<G1Jac*>(smem_raw);
-  size_t g = blockIdx.x;
+  size_t G = blockIdx.x;
   int h = blockIdx.y;
-  size_t begin = g * m, end = begin + m < n ? begin + m : n;
+  size_t n_groups = (n + m - 1) / m;
+  size_t seg = G / n_groups, g = G % n_groups;
+  size_t begin = seg * n + g * m, end = (g * m + m < n ? g * m + m : n) + seg * n;
   G1Jac acc = G1Jac::identity();
   for (size_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
     G1Affine b;
@@ -94,7 +100,7 @@ __global__ void k_group_msm(size_t n, size_t m, const uint8_t* accs, const u32* 
     bool canon = Fq::is_canonical(b.x.v) && Fq::is_canonical(b.y.v);
     if (!b.is_identity()) { b.x = b.x.to_mont(); b.y = b.y.to_mont(); }
     if (!canon || !g1_on_curve(b)) {
-      atomicMax(status, SVK_TRANSCRIPT | (SVK_T_POINT_INVALID << 8));
+      atomicMax(status + seg * status_stride_words, SVK_TRANSCRIPT | (SVK_T_POINT_INVALID << 8));
       continue;
     }
     if (i == begin) {
@@ -114,7 +120,7 @@ __global__ void k_group_msm(size_t n, size_t m, const uint8_t* accs, const u32* 
   if (threadIdx.x == 0) {
     G1Affine a = sm[0].to_affine();
     Fq x = a.x.from_mont(), y = a.y.from_mont();
-    uint4* o = reinterpret_cast<uint4*>(out_accs + g * 128 + h * 64);
+    uint4* o = reinterpret_cast<uint4*>(out_accs + G * out_stride + h * 64);
     o[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
     o[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
     o[2] = make_uint4(y.v[0], y.v[1], y.v[2], y.v[3]);
@@ -122,34 +128,40 @@ __global__ void k_group_msm(size_t n, size_t m, const uint8_t* accs, const u32* 
   }
 }
 
-// Folds d_accs[0..n) down to one accumulator at d_out_acc (device).  d_out_r (32 B, may be null)
-// receives the challenge of the LAST fold call (the root); d_status one int32.
+// Folds `n_seg` independent batches of `n` accumulators each (d_accs: [seg][n] x 128 B) down to one accumulator per
+// batch, written to d_out + seg * out_stride: { svk_acc (128) ; r of the last fold call (32) ; int32 status }.
 // The fold owns scratch slots 8 (ping-pong accumulators) and 9 (scalars).
-int svk_fold_launch(svk_ctx* ctx, size_t n, const uint8_t* d_accs, size_t group_size, uint8_t* d_out_acc, u32* d_out_r,
-                    int32_t* d_status) {
-  if (n == 0) return svk_fail(ctx, "fold of zero accumulators (`assert!(!instances.is_empty())`, accumulation.rs:121)");
+int svk_fold_launch_seg(svk_ctx* ctx, size_t n_seg, size_t n, const uint8_t* d_accs, size_t group_size, uint8_t* d_out, size_t out_stride) {
+  if (n == 0 || n_seg == 0) return svk_fail(ctx, "fold of zero accumulators (`assert!(!instances.is_empty())`, accumulation.rs:121)");
+  if (out_stride < 164 || out_stride % 4) return svk_fail(ctx, "fold: bad output stride");
   cudaStream_t s = ctx->stream;
   size_t m = (group_size <= 1 || group_size >= n) ? n : group_size;
   size_t first_groups = (n + m - 1) / m;
   uint8_t* d_tmp;
   u32* d_scal;
-  if (svk_scratch(ctx, 8, (first_groups + (first_groups + m - 1) / m + 2) * 128, (void**)&d_tmp)) return -1;
-  if (svk_scratch(ctx, 9, n * 32 + 32, (void**)&d_scal)) return -1;
-  SVK_CUDA(ctx, cudaMemsetAsync(d_status, 0, 4, s));
+  size_t lvl0 = n_seg * first_groups, lvl1 = n_seg * ((first_groups + m - 1) / m);
+  if (svk_scratch(ctx, 8, (lvl0 + lvl1 + 2) * 128, (void**)&d_tmp)) return -1;
+  if (svk_scratch(ctx, 9, n_seg * n * 32 + 32, (void**)&d_scal)) return -1;
+  SVK_CUDA(ctx, cudaMemset2DAsync(d_out + 160, out_stride, 0, 4, n_seg, s));
+  int32_t* d_status = (int32_t*)(d_out + 160);
+  u32* d_r = (u32*)(d_out + 128);
   const uint8_t* cur = d_accs;
   size_t cnt = n;
-  uint8_t* bufs[2] = {d_tmp, d_tmp + (first_groups + 1) * 128};
+  uint8_t* bufs[2] = {d_tmp, d_tmp + (lvl0 + 1) * 128};
   int which = 0;
   for (;;) {
     size_t groups = (cnt + m - 1) / m;
     bool last = groups == 1;
-    uint8_t* dst = last ? d_out_acc : bufs[which];
+    uint8_t* dst = last ? d_out : bufs[which];
+    size_t total_groups = groups * n_seg;
     SVK_LAUNCH(ctx, "k_fold_sponge",
-               k_fold_sponge<<<(unsigned)((groups + 31) / 32), 32, 0, s>>>(cnt, m, cur, ctx->d_poseidon, d_scal, last ? d_out_r : nullptr, d_status));
+               k_fold_sponge<<<(unsigned)((total_groups + 31) / 32), 32, 0, s>>>(n_seg, cnt, m, cur, ctx->d_poseidon, d_scal, last ? d_r : nullptr,
+                                                                                out_stride / 4, d_status, out_stride / 4));
     unsigned L = 32;
     while (L < m && L < 256) L <<= 1;
-    dim3 grid((unsigned)groups, 2);
-    SVK_LAUNCH(ctx, "k_group_msm", k_group_msm<<<grid, L, L * sizeof(G1Jac), s>>>(cnt, m, cur, d_scal, dst, d_status));
+    dim3 grid((unsigned)total_groups, 2);
+    SVK_LAUNCH(ctx, "k_group_msm",
+               k_group_msm<<<grid, L, L * sizeof(G1Jac), s>>>(cnt, m, cur, d_scal, dst, last ? out_stride : 128, d_status, out_stride / 4));
     if (last) break;
     cur = dst;
     cnt = groups;
@@ -159,21 +171,38 @@ int svk_fold_launch(svk_ctx* ctx, size_t n, const uint8_t* d_accs, size_t group_
   return 0;
 }
 
-// ok = decide_ok && every status == 0 && fold_status == 0   (PlonkVerifier::verify over the batch)
-__global__ void k_batch_verdict(size_t n, const int32_t* status, const int32_t* fold_status, const uint8_t* decide_ok, uint8_t* out_ok) {
+// single batch, separate output pointers (svk_kzg_as_fold_dev): staged through a 256-byte record
+int svk_fold_launch(svk_ctx* ctx, size_t n, const uint8_t* d_accs, size_t group_size, uint8_t* d_out_acc, u32* d_out_r, int32_t* d_status) {
+  uint8_t* rec;
+  if (svk_scratch(ctx, 16, 256, (void**)&rec)) return -1;
+  if (svk_fold_launch_seg(ctx, 1, n, d_accs, group_size, rec, 256)) return -1;
+  cudaStream_t s = ctx->stream;
+  SVK_CUDA(ctx, cudaMemcpyAsync(d_out_acc, rec, 128, cudaMemcpyDeviceToDevice, s));
+  if (d_out_r) SVK_CUDA(ctx, cudaMemcpyAsync(d_out_r, rec + 128, 32, cudaMemcpyDeviceToDevice, s));
+  SVK_CUDA(ctx, cudaMemcpyAsync(d_status, rec + 160, 4, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+// Per batch: ok = decide_ok && every proof status == 0 && fold_status == 0   (PlonkVerifier::verify over the batch).
+// One block per batch; records: { acc 128 ; r 32 ; fold_status 4 ; decide_ok 1 ; ok 1 } with stride rec_stride.
+__global__ void k_batch_verdict(size_t batch, const int32_t* status, uint8_t* records, size_t rec_stride) {
   __shared__ int any_bad;
   if (threadIdx.x == 0) any_bad = 0;
   __syncthreads();
+  size_t seg = blockIdx.x;
   int bad = 0;
-  for (size_t i = threadIdx.x; i < n; i += blockDim.x) bad |= status[i] != 0;
+  for (size_t i = threadIdx.x; i < batch; i += blockDim.x) bad |= status[seg * batch + i] != 0;
   if (bad) atomicOr(&any_bad, 1);
   __syncthreads();
-  if (threadIdx.x == 0) out_ok[0] = (!any_bad && fold_status[0] == 0 && decide_ok[0]) ? 1 : 0;
+  if (threadIdx.x == 0) {
+    uint8_t* rec = records + seg * rec_stride;
+    int32_t fold_status = *reinterpret_cast<const int32_t*>(rec + 160);
+    rec[165] = (!any_bad && fold_status == 0 && rec[164]) ? 1 : 0;
+  }
 }
 
-int svk_batch_verdict_launch(svk_ctx* ctx, size_t n, const int32_t* d_status, const int32_t* d_fold_status, const uint8_t* d_decide_ok,
-                             uint8_t* d_out_ok) {
-  SVK_LAUNCH(ctx, "k_batch_verdict", k_batch_verdict<<<1, 256, 0, ctx->stream>>>(n, d_status, d_fold_status, d_decide_ok, d_out_ok));
+int svk_batch_verdict_launch(svk_ctx* ctx, size_t n_seg, size_t batch, const int32_t* d_status, uint8_t* d_records, size_t rec_stride) {
+  SVK_LAUNCH(ctx, "k_batch_verdict", k_batch_verdict<<<(unsigned)n_seg, 256, 0, ctx->stream>>>(batch, d_status, d_records, rec_stride));
   SVK_CUDA(ctx, cudaGetLastError());
   return 0;
 }

@@ -13,8 +13,9 @@ int svk_msm_launch(svk_ctx* ctx, size_t n, const uint8_t* d_scalars, const uint8
 int svk_g1_mul_batch_launch(svk_ctx* ctx, size_t n, const uint8_t* d_scalars, const uint8_t* d_points, size_t n_points, uint8_t* d_out);
 int svk_fixed_tables_launch(svk_ctx* ctx, ProtocolDevice* pd);
 int svk_fold_launch(svk_ctx* ctx, size_t n, const uint8_t* d_accs, size_t group_size, uint8_t* d_out_acc, u32* d_out_r, int32_t* d_status);
-int svk_batch_verdict_launch(svk_ctx* ctx, size_t n, const int32_t* d_status, const int32_t* d_fold_status, const uint8_t* d_decide_ok,
-                             uint8_t* d_out_ok);
+int svk_fold_launch_seg(svk_ctx* ctx, size_t n_seg, size_t n, const uint8_t* d_accs, size_t group_size, uint8_t* d_out, size_t out_stride);
+int svk_decide_launch_strided(svk_ctx* ctx, int dk, size_t n, const void* d_accs, size_t acc_stride, void* d_ok, size_t ok_stride);
+int svk_batch_verdict_launch(svk_ctx* ctx, size_t n_seg, size_t batch, const int32_t* d_status, uint8_t* d_records, size_t rec_stride);
 int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const uint8_t* d_instances, u32 n_instances_given,
                                const uint8_t* d_proofs, size_t proof_stride, const u32* d_proof_lens, uint8_t* d_out_acc,
                                u32* d_out_challenges, int32_t* d_out_status);
@@ -114,7 +115,7 @@ void svk_destroy(svk_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto& k : ctx->dks) { cudaFree(k.d_lines_g2); cudaFree(k.d_lines_neg_sg2); }
-  for (int i = 0; i < 16; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+  for (int i = 0; i < 24; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   cudaFree(ctx->d_pairing_consts);
   cudaFree(ctx->d_poseidon);
   for (auto* p : ctx->protocols) {
@@ -332,7 +333,7 @@ int svk_protocol_info(svk_ctx* ctx, int proto, uint32_t* out) {
   ProtocolDevice* pd = ctx->protocols[proto];
   out[0] = pd->proof_len; out[1] = pd->n_instances; out[2] = pd->n_challenges; out[3] = pd->n_regs; out[4] = pd->n_ops;
   out[5] = (u32)pd->n_perm; out[6] = pd->verify_valid ? 1 : 0; out[7] = (u32)pd->n_fr_mul; out[8] = pd->n_lhs; out[9] = pd->n_rhs;
-  out[10] = (u32)pd->points.size(); out[11] = pd->n_scalar_slots; out[12] = (u32)pd->msm_work_modmul;
+  out[10] = (u32)pd->points.size(); out[11] = pd->n_scalar_slots; out[12] = (u32)pd->msm_work_modmul; out[13] = (u32)(pd->n_var * (161 + 64 * 16) + pd->var_lanes * 252 * 7); out[14] = pd->n_var; out[15] = pd->var_lanes;
   return 0;
 }
 
@@ -396,62 +397,94 @@ int svk_kzg_as_fold(svk_ctx* ctx, size_t n, const svk_acc* accs, size_t group_si
   return 0;
 }
 
-// ---- PlonkVerifier::verify over a batch: succinct verify each, fold, ONE pairing -------------------
-// d_work: >= n*128 (accumulators) + 512 bytes of device scratch owned by the caller of the _dev variant
-int svk_plonk_verify_batch_dev(svk_ctx* ctx, int proto, size_t n, const void* d_instances, uint32_t n_instances, const void* d_proofs,
-                               size_t proof_stride, const void* d_proof_lens, size_t group_size, void* d_out_accs, void* d_out_status,
-                               void* d_out_folded /* 128 acc + 32 r + 4 fold status + 1 decide + 1 ok */) {
+int svk_kzg_as_fold_multi_dev(svk_ctx* ctx, size_t n_seg, size_t n, const void* d_accs, size_t group_size, void* d_out_records) {
+  SVK_CUDA(ctx, cudaSetDevice(ctx->device));
+  return svk_fold_launch_seg(ctx, n_seg, n, (const uint8_t*)d_accs, group_size, (uint8_t*)d_out_records, 256);
+}
+
+int svk_kzg_decide_records_dev(svk_ctx* ctx, int dk, size_t n_records, void* d_records) {
+  SVK_CUDA(ctx, cudaSetDevice(ctx->device));
+  return svk_decide_launch_strided(ctx, dk, n_records, d_records, 256, (uint8_t*)d_records + 164, 256);
+}
+
+// ---- PlonkVerifier::verify over batches: succinct verify each proof, fold every batch, ONE pairing per batch ----
+// n_batches batches of batch_size proofs, back to back.  d_out_records: n_batches x 256 B
+//   { svk_acc folded ; svk_fe r ; int32 fold_status ; uint8 decide_ok ; uint8 ok }
+int svk_plonk_verify_multi_dev(svk_ctx* ctx, int proto, size_t n_batches, size_t batch_size, const void* d_instances, uint32_t n_instances,
+                               const void* d_proofs, size_t proof_stride, const void* d_proof_lens, size_t group_size, void* d_out_accs,
+                               void* d_out_status, void* d_out_records) {
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
-  if (n == 0) return svk_fail(ctx, "empty batch");
+  if (n_batches == 0 || batch_size == 0) return svk_fail(ctx, "empty batch");
   ProtocolDevice* pd = ctx->protocols[proto];
-  uint8_t* f = (uint8_t*)d_out_folded;
+  size_t n = n_batches * batch_size;
+  uint8_t* rec = (uint8_t*)d_out_records;
   if (svk_succinct_verify_launch(ctx, pd, n, (const uint8_t*)d_instances, n_instances, (const uint8_t*)d_proofs, proof_stride,
                                  (const u32*)d_proof_lens, (uint8_t*)d_out_accs, nullptr, (int32_t*)d_out_status))
     return -1;
-  if (svk_fold_launch(ctx, n, (const uint8_t*)d_out_accs, group_size, f, (u32*)(f + 128), (int32_t*)(f + 160))) return -1;
-  if (svk_decide_launch(ctx, pd->dk, 1, f, f + 164)) return -1;
-  return svk_batch_verdict_launch(ctx, n, (const int32_t*)d_out_status, (const int32_t*)(f + 160), f + 164, f + 165);
+  if (svk_fold_launch_seg(ctx, n_batches, batch_size, (const uint8_t*)d_out_accs, group_size, rec, 256)) return -1;
+  if (svk_decide_launch_strided(ctx, pd->dk, n_batches, rec, 256, rec + 164, 256)) return -1;
+  return svk_batch_verdict_launch(ctx, n_batches, batch_size, (const int32_t*)d_out_status, rec, 256);
 }
 
-int svk_plonk_verify_batch(svk_ctx* ctx, int proto, size_t n, const svk_fe* instances, uint32_t n_instances, const uint8_t* proofs,
-                           size_t proof_stride, const uint32_t* proof_lens, size_t group_size, int locate_failures, int32_t* out_status,
-                           svk_acc* out_folded, uint8_t* out_ok) {
+int svk_plonk_verify_batch_dev(svk_ctx* ctx, int proto, size_t n, const void* d_instances, uint32_t n_instances, const void* d_proofs,
+                               size_t proof_stride, const void* d_proof_lens, size_t group_size, void* d_out_accs, void* d_out_status,
+                               void* d_out_folded) {
+  return svk_plonk_verify_multi_dev(ctx, proto, 1, n, d_instances, n_instances, d_proofs, proof_stride, d_proof_lens, group_size, d_out_accs,
+                                    d_out_status, d_out_folded);
+}
+
+int svk_plonk_verify_multi(svk_ctx* ctx, int proto, size_t n_batches, size_t batch_size, const svk_fe* instances, uint32_t n_instances,
+                           const uint8_t* proofs, size_t proof_stride, const uint32_t* proof_lens, size_t group_size, int locate_failures,
+                           int32_t* out_status, uint8_t* out_records) {
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
-  if (n == 0) return svk_fail(ctx, "empty batch");
+  if (n_batches == 0 || batch_size == 0) return svk_fail(ctx, "empty batch");
+  size_t n = n_batches * batch_size;
   cudaStream_t s = ctx->stream;
   size_t inst_bytes = n * (size_t)n_instances * 32, proof_bytes = n * proof_stride;
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
   size_t off_proofs = al(inst_bytes), off_lens = off_proofs + al(proof_bytes), off_accs = off_lens + al(n * 4), off_status = off_accs + n * 128,
-         off_fold = off_status + al(n * 4), off_dec = off_fold + 256, total = off_dec + al(n);
+         off_rec = off_status + al(n * 4), off_dec = off_rec + n_batches * 256, total = off_dec + al(n);
   uint8_t* d;
   if (svk_scratch(ctx, 0, total, (void**)&d)) return -1;
   if (inst_bytes) SVK_CUDA(ctx, cudaMemcpyAsync(d, instances, inst_bytes, cudaMemcpyHostToDevice, s));
   SVK_CUDA(ctx, cudaMemcpyAsync(d + off_proofs, proofs, proof_bytes, cudaMemcpyHostToDevice, s));
   if (proof_lens) SVK_CUDA(ctx, cudaMemcpyAsync(d + off_lens, proof_lens, n * 4, cudaMemcpyHostToDevice, s));
-  if (svk_plonk_verify_batch_dev(ctx, proto, n, d, n_instances, d + off_proofs, proof_stride, proof_lens ? d + off_lens : nullptr, group_size,
-                                 d + off_accs, d + off_status, d + off_fold))
+  if (svk_plonk_verify_multi_dev(ctx, proto, n_batches, batch_size, d, n_instances, d + off_proofs, proof_stride,
+                                 proof_lens ? d + off_lens : nullptr, group_size, d + off_accs, d + off_status, d + off_rec))
     return -1;
   // results go straight into the caller's buffers (pinned buffers keep these copies asynchronous)
   SVK_CUDA(ctx, cudaMemcpyAsync(out_status, d + off_status, n * 4, cudaMemcpyDeviceToHost, s));
-  uint8_t folded_local[128];
-  SVK_CUDA(ctx, cudaMemcpyAsync(out_folded ? (void*)out_folded : (void*)folded_local, d + off_fold, 128, cudaMemcpyDeviceToHost, s));
-  SVK_CUDA(ctx, cudaMemcpyAsync(out_ok, d + off_fold + 165, 1, cudaMemcpyDeviceToHost, s));
+  SVK_CUDA(ctx, cudaMemcpyAsync(out_records, d + off_rec, n_batches * 256, cudaMemcpyDeviceToHost, s));
   if (svk_wait(ctx)) return -1;
-  if (!*out_ok && locate_failures) {
-    // every proof read fine but the folded pairing failed: decide each accumulator to name the culprits
-    bool all_ok = true;
-    for (size_t i = 0; i < n; i++) all_ok = all_ok && out_status[i] == 0;
-    if (all_ok) {
-      std::vector<uint8_t> oks(n);
-      if (svk_decide_launch(ctx, ctx->protocols[proto]->dk, n, d + off_accs, d + off_dec)) return -1;
-      SVK_CUDA(ctx, cudaMemcpyAsync(oks.data(), d + off_dec, n, cudaMemcpyDeviceToHost, s));
+  if (locate_failures) {
+    // a batch whose proofs all read fine but whose folded pairing failed: decide each accumulator to name the culprits
+    for (size_t b = 0; b < n_batches; b++) {
+      if (out_records[b * 256 + 165]) continue;
+      bool all_ok = true;
+      for (size_t i = 0; i < batch_size; i++) all_ok = all_ok && out_status[b * batch_size + i] == 0;
+      if (!all_ok) continue;
+      std::vector<uint8_t> oks(batch_size);
+      if (svk_decide_launch(ctx, ctx->protocols[proto]->dk, batch_size, d + off_accs + b * batch_size * 128, d + off_dec)) return -1;
+      SVK_CUDA(ctx, cudaMemcpyAsync(oks.data(), d + off_dec, batch_size, cudaMemcpyDeviceToHost, s));
       if (svk_wait(ctx)) return -1;
-      for (size_t i = 0; i < n; i++)
-        if (!oks[i]) out_status[i] = SVK_ASSERTION_FAILURE;
+      for (size_t i = 0; i < batch_size; i++)
+        if (!oks[i]) out_status[b * batch_size + i] = SVK_ASSERTION_FAILURE;
     }
   }
+  return 0;
+}
+
+int svk_plonk_verify_batch(svk_ctx* ctx, int proto, size_t n, const svk_fe* instances, uint32_t n_instances, const uint8_t* proofs,
+                           size_t proof_stride, const uint32_t* proof_lens, size_t group_size, int locate_failures, int32_t* out_status,
+                           svk_acc* out_folded, uint8_t* out_ok) {
+  uint8_t rec[256];
+  if (svk_plonk_verify_multi(ctx, proto, 1, n, instances, n_instances, proofs, proof_stride, proof_lens, group_size, locate_failures,
+                             out_status, rec))
+    return -1;
+  if (out_folded) memcpy(out_folded, rec, 128);
+  *out_ok = rec[165];
   return 0;
 }
 

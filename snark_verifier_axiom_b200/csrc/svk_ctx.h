@@ -44,8 +44,8 @@ struct svk_ctx {
   PoseidonConsts h_poseidon;
   std::vector<DkDevice> dks;
   // scratch buffers (grown on demand, reused across calls)
-  void* scratch[16] = {nullptr};
-  size_t scratch_sz[16] = {0};
+  void* scratch[24] = {nullptr};
+  size_t scratch_sz[24] = {0};
   std::vector<struct ProtocolDevice*> protocols;
 };
 

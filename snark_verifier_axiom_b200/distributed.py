@@ -39,35 +39,38 @@ class LibsvkOps:
     def _p(t):
         return ctypes.c_void_p(t.data_ptr())
 
-    def local_verify(self, d_inst, n_inst, d_proofs, n, group_size, d_accs, d_status, d_record, d_lens=None):
-        rc = self.L.svk_plonk_verify_batch_dev(self.c, self.pv.pid, n, self._p(d_inst), n_inst, self._p(d_proofs), d_proofs.shape[1],
+    def local_verify(self, d_inst, n_inst, d_proofs, n_batches, batch, group_size, d_accs, d_status, d_records, d_lens=None):
+        """n_batches batches of `batch` proofs: succinct verify + fold + decide + verdict, one record per batch"""
+        rc = self.L.svk_plonk_verify_multi_dev(self.c, self.pv.pid, n_batches, batch, self._p(d_inst), n_inst, self._p(d_proofs), d_proofs.shape[1],
                                                self._p(d_lens) if d_lens is not None else None, group_size, self._p(d_accs), self._p(d_status),
-                                               self._p(d_record))
+                                               self._p(d_records))
         self.ctx._check(rc)
 
-    def fold(self, n, d_accs, d_record):
-        """flat KzgAs fold of n accumulators -> record[0:128] acc, [128:160] r, [160:164] status"""
-        rc = self.L.svk_kzg_as_fold_dev(self.c, n, self._p(d_accs), 0, self._p(d_record), ctypes.c_void_p(d_record.data_ptr() + 128),
-                                        ctypes.c_void_p(d_record.data_ptr() + OFF_FOLD_STATUS))
-        self.ctx._check(rc)
+    def fold(self, n_seg, n, d_accs, d_records):
+        """flat KzgAs fold of n_seg x n accumulators -> one record per segment"""
+        self.ctx._check(self.L.svk_kzg_as_fold_multi_dev(self.c, n_seg, n, self._p(d_accs), 0, self._p(d_records)))
 
-    def decide(self, d_record):
-        rc = self.L.svk_kzg_decide_batch_dev(self.c, self.pv.kzg_as.dk_id, 1, self._p(d_record), ctypes.c_void_p(d_record.data_ptr() + OFF_DECIDE_OK))
-        self.ctx._check(rc)
+    def decide(self, n_records, d_records):
+        self.ctx._check(self.L.svk_kzg_decide_records_dev(self.c, self.pv.kzg_as.dk_id, n_records, self._p(d_records)))
 
 
 class ShardedBatchVerifier:
-    def __init__(self, pv, world, rank, device, stream=None, group_size=8, ops=None):
+    """Verifies `n_batches` batches per call on this rank's shard; with world > 1 the per-rank batch accumulators are
+    all-gathered and batch b of every rank is folded into the global accumulator of batch b, then decided."""
+
+    def __init__(self, pv, world, rank, device, stream=None, group_size=8, ops=None, max_batches=1):
         self.world, self.rank, self.device, self.stream = world, rank, device, stream
         self.group_size = group_size
         self.ops = ops or LibsvkOps(pv)
         self.pv = pv
         self._n = 0
+        self.max_batches = max_batches
         kw = dict(dtype=torch.uint8, device=device)
-        self.d_record = torch.zeros(RECORD, **kw)
-        self.d_gather = torch.zeros(world * RECORD, **kw)
-        self.d_final = torch.zeros(RECORD, **kw)
+        self.d_records = torch.zeros(max_batches * RECORD, **kw)
+        self.d_gather = torch.zeros(world * max_batches * RECORD, **kw)
+        self.d_final = torch.zeros(max_batches * RECORD, **kw)
         self.d_accs = self.d_status = None
+        self.nb = 1
 
     def _ensure(self, n):
         if self._n < n:
@@ -82,56 +85,57 @@ class ShardedBatchVerifier:
 
         return contextlib.nullcontext()
 
-    def verify_dev(self, d_inst, n_inst, d_proofs, n, d_lens=None):
-        """Enqueue: local succinct verify + fold + decide of this rank's shard; if world > 1 all_gather the
-        per-rank records, fold the `world` accumulators and decide.  No host synchronisation."""
+    def verify_dev(self, d_inst, n_inst, d_proofs, n, d_lens=None, n_batches=1):
+        """Enqueue (no host synchronisation): `n_batches` batches of n // n_batches proofs each -- local succinct verify
+        + fold + decide per batch; if world > 1 all_gather the records, fold batch b over the ranks and decide."""
+        assert n % n_batches == 0 and n_batches <= self.max_batches
         self._ensure(n)
-        self.ops.local_verify(d_inst, n_inst, d_proofs, n, self.group_size, self.d_accs, self.d_status, self.d_record, d_lens)
+        self.nb = n_batches
+        nb = n_batches
+        self.ops.local_verify(d_inst, n_inst, d_proofs, nb, n // nb, self.group_size, self.d_accs, self.d_status, self.d_records, d_lens)
         if self.world > 1:
             with self._on_stream():
-                dist.all_gather_into_tensor(self.d_gather, self.d_record)
-                accs = self.d_gather.view(self.world, RECORD)[:, :128].contiguous()
-            self.ops.fold(self.world, accs, self.d_final)
-            self.ops.decide(self.d_final)
+                dist.all_gather_into_tensor(self.d_gather[: self.world * nb * RECORD], self.d_records[: nb * RECORD])
+                # [rank][batch][256] -> accumulators [batch][rank][128]
+                accs = self.d_gather[: self.world * nb * RECORD].view(self.world, nb, RECORD)[:, :, :128].permute(1, 0, 2).contiguous()
+            self.ops.fold(nb, self.world, accs, self.d_final)
+            self.ops.decide(nb, self.d_final)
             self._keep = accs
 
-    def last_ok(self) -> bool:
-        """Host read of the verdict (synchronises)."""
+    def last_ok(self):
+        """Host read of the verdicts (synchronises) -> bool (all batches of the last call accepted)."""
+        return all(self.last_verdicts())
+
+    def last_verdicts(self):
+        nb = self.nb
         if self.world == 1:
-            rec = self.d_record.cpu().numpy()
-            return bool(rec[OFF_OK])
-        g = self.d_gather.cpu().numpy().reshape(self.world, RECORD)
-        f = self.d_final.cpu().numpy()
-        fold_status = int(np.frombuffer(f[OFF_FOLD_STATUS : OFF_FOLD_STATUS + 4].tobytes(), np.int32)[0])
-        return bool(g[:, OFF_OK].all() and fold_status == 0 and f[OFF_DECIDE_OK])
+            rec = self.d_records[: nb * RECORD].cpu().numpy().reshape(nb, RECORD)
+            return [bool(x) for x in rec[:, OFF_OK]]
+        g = self.d_gather[: self.world * nb * RECORD].cpu().numpy().reshape(self.world, nb, RECORD)
+        f = self.d_final[: nb * RECORD].cpu().numpy().reshape(nb, RECORD)
+        out = []
+        for b in range(nb):
+            fold_status = int(np.frombuffer(f[b, OFF_FOLD_STATUS : OFF_FOLD_STATUS + 4].tobytes(), np.int32)[0])
+            out.append(bool(g[:, b, OFF_OK].all() and fold_status == 0 and f[b, OFF_DECIDE_OK]))
+        return out
 
-    def final_accumulator(self) -> bytes:
-        src = self.d_record if self.world == 1 else self.d_final
-        return src.cpu().numpy()[:128].tobytes()
+    def final_accumulator(self, b=0) -> bytes:
+        src = self.d_records if self.world == 1 else self.d_final
+        return src.cpu().numpy()[b * RECORD : b * RECORD + 128].tobytes()
 
-    def verify_host(self, h_inst, n_inst, h_proofs, h_lens, n):
-        """End-to-end call with HOST buffers: H2D of instances + proofs (+ lengths), the batch verification,
-        D2H of the per-proof statuses and the verdict.  -> (ok, status int32[n])"""
-        if self.world == 1 and isinstance(self.ops, LibsvkOps):
-            if getattr(self, "_h_n", 0) < n:  # pinned result buffers, reused: pageable targets make the copies synchronous
-                pin = self.device.type == "cuda"
-                self._h_st = torch.zeros(n, dtype=torch.int32, pin_memory=pin).numpy()
-                self._h_folded = torch.zeros(128, dtype=torch.uint8, pin_memory=pin).numpy()
-                self._h_ok = torch.zeros(8, dtype=torch.uint8, pin_memory=pin).numpy()
-                self._h_n = n
-            st, folded, ok = self._h_st[:n], self._h_folded, self._h_ok
-            o = self.ops
-            rc = o.L.svk_plonk_verify_batch(o.c, self.pv.pid, n, h_inst.ctypes.data_as(ctypes.c_void_p), n_inst,
-                                            h_proofs.ctypes.data_as(ctypes.c_void_p), h_proofs.shape[1],
-                                            h_lens.ctypes.data_as(ctypes.c_void_p), self.group_size, 0, st.ctypes.data_as(ctypes.c_void_p),
-                                            folded.ctypes.data_as(ctypes.c_void_p), ok.ctypes.data_as(ctypes.c_void_p))
-            o.ctx._check(rc)
-            return bool(ok[0]), st
-        with self._on_stream():
-            d_inst = torch.from_numpy(h_inst).to(self.device, non_blocking=True)
-            d_proofs = torch.from_numpy(h_proofs).to(self.device, non_blocking=True)
-            d_lens = torch.from_numpy(h_lens.astype(np.int32)).to(self.device, non_blocking=True)
-        self.verify_dev(d_inst, n_inst, d_proofs, n, d_lens)
-        with self._on_stream():
-            st = self.d_status[:n].cpu().numpy()
-        return self.last_ok(), st
+    def verify_host(self, h_inst, n_inst, h_proofs, h_lens, n, n_batches=1):
+        """End-to-end call with HOST buffers (single GPU): H2D of instances + proofs (+ lengths), the verification of
+        `n_batches` batches, D2H of the per-proof statuses and the per-batch records.  -> (ok, status int32[n])"""
+        assert self.world == 1 and isinstance(self.ops, LibsvkOps)
+        if getattr(self, "_h_n", 0) < n or getattr(self, "_h_nb", 0) < n_batches:
+            pin = self.device.type == "cuda"  # pinned result buffers, reused: pageable targets make the copies synchronous
+            self._h_st = torch.zeros(n, dtype=torch.int32, pin_memory=pin).numpy()
+            self._h_rec = torch.zeros(n_batches * RECORD, dtype=torch.uint8, pin_memory=pin).numpy()
+            self._h_n, self._h_nb = n, n_batches
+        st, rec = self._h_st[:n], self._h_rec[: n_batches * RECORD]
+        o = self.ops
+        rc = o.L.svk_plonk_verify_multi(o.c, self.pv.pid, n_batches, n // n_batches, h_inst.ctypes.data_as(ctypes.c_void_p), n_inst,
+                                        h_proofs.ctypes.data_as(ctypes.c_void_p), h_proofs.shape[1], h_lens.ctypes.data_as(ctypes.c_void_p),
+                                        self.group_size, 0, st.ctypes.data_as(ctypes.c_void_p), rec.ctypes.data_as(ctypes.c_void_p))
+        o.ctx._check(rc)
+        return bool(rec.reshape(n_batches, RECORD)[:, OFF_OK].all()), st

@@ -146,7 +146,8 @@ class Context:
         out = (ctypes.c_uint32 * 16)()
         self._check(self._L.svk_protocol_info(self._c, pid, out))
         keys = ["proof_len", "n_instances", "n_challenges", "n_regs", "n_ops", "n_poseidon_perms", "verify_valid", "n_fr_mul",
-                "n_lhs_terms", "n_rhs_terms", "n_points", "n_scalar_slots", "msm_modmul_per_proof"]
+                "n_lhs_terms", "n_rhs_terms", "n_points", "n_scalar_slots", "msm_modmul_per_proof", "msm_var_modmul_per_proof",
+                "n_var_terms", "var_lanes"]
         return dict(zip(keys, [int(x) for x in out]))
 
     def modmul_peak(self, iters: int = 4000):
@@ -265,6 +266,26 @@ class PlonkVerifier:
         self.ctx._check(L.svk_plonk_verify_batch(c, self.pid, n, _ptr(inst), n_inst, _ptr(proofs), proofs.shape[1], _ptr(lens), group_size,
                                                  1 if locate_failures else 0, _ptr(st), _ptr(folded), _ptr(ok)))
         return BatchResult(bool(ok[0]), st, KzgAccumulator.from_bytes(folded.tobytes()) if ok[0] else None)
+
+    def verify_batches(self, batches: Sequence[Sequence[Snark]], group_size: int = 0, locate_failures: bool = True) -> List[BatchResult]:
+        """Several equally sized batches in ONE call (`svk_plonk_verify_multi`): each batch is folded and decided on
+        its own; the kernels of the call serve all batches."""
+        nb = len(batches)
+        bs = len(batches[0])
+        assert all(len(b) == bs for b in batches)
+        flat = [s for b in batches for s in b]
+        inst, n_inst, proofs, lens = self.pack(flat)
+        st = np.zeros(nb * bs, np.int32)
+        rec = np.zeros(nb * 256, np.uint8)
+        L, c = self.ctx._L, self.ctx._c
+        self.ctx._check(L.svk_plonk_verify_multi(c, self.pid, nb, bs, _ptr(inst), n_inst, _ptr(proofs), proofs.shape[1], _ptr(lens), group_size,
+                                                 1 if locate_failures else 0, _ptr(st), _ptr(rec)))
+        out = []
+        for b in range(nb):
+            r = rec[b * 256 : (b + 1) * 256]
+            ok = bool(r[165])
+            out.append(BatchResult(ok, st[b * bs : (b + 1) * bs], KzgAccumulator.from_bytes(r[:128].tobytes()) if ok else None))
+        return out
 
     def verify_one(self, snark: Snark) -> None:
         """The reference's single-proof `PlonkVerifier::verify(..)` -> Ok(()) or raises Error."""

@@ -25,7 +25,8 @@ class OracleOps:
         self.S = forge.Setup(0)
         self.trace = cref.Trace(self.S, "bdfg21")
 
-    def local_verify(self, d_inst, n_inst, d_proofs, n, group_size, d_accs, d_status, d_record, d_lens=None):
+    def local_verify(self, d_inst, n_inst, d_proofs, n_batches, n, group_size, d_accs, d_status, d_record, d_lens=None):
+        assert n_batches == 1
         buf = d_proofs.numpy()
         lens = np.full(n, buf.shape[1], dtype=np.int32)
         inp = np.ascontiguousarray(d_inst.numpy()).view(np.uint64).reshape(n, -1)
@@ -40,12 +41,13 @@ class OracleOps:
         rec[165] = 1 if (ok and (st == 0).all() and fst == 0) else 0
         d_record[:] = torch.from_numpy(rec)
 
-    def fold(self, n, d_accs, d_record):
+    def fold(self, n_seg, n, d_accs, d_record):
+        assert n_seg == 1
         acc, r, fst = self.cref.fold(d_accs.numpy().reshape(n, 128), 0)
         d_record[:128] = torch.from_numpy(acc)
         d_record[160:164] = torch.from_numpy(np.array([fst], dtype=np.int32).view(np.uint8))
 
-    def decide(self, d_record):
+    def decide(self, n_records, d_record):
         d_record[164] = 1 if self.cref.decide(d_record.numpy()[:128], self.S.dk) else 0
 
 

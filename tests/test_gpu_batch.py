@@ -77,3 +77,25 @@ def test_fold_rejects_identity(env):
     with pytest.raises(V.Error) as e:
         AS.create_proof([a, V.KzgAccumulator(None, g_mul(3))])
     assert e.value.kind == "Transcript"
+
+
+def test_verify_batches_equals_separate_calls(env):
+    """svk_plonk_verify_multi: 3 batches in one call == 3 separate PlonkVerifier::verify batches (folded accumulator,
+    verdict, statuses), including one batch with a corrupted proof."""
+    V, S, ctx, AS, pv = env
+    insts, proofs = forge.forge_batch(S, "bdfg21", 15, seed0=800)
+    snarks = [V.Snark(i, p) for i, p in zip(insts, proofs)]
+    bad = bytearray(proofs[7])
+    bad[9 * 32 + 11] ^= 8
+    snarks[7] = V.Snark(insts[7], bytes(bad))
+    batches = [snarks[0:5], snarks[5:10], snarks[10:15]]
+    for m in (0, 2):
+        multi = pv[0].verify_batches(batches, group_size=m)
+        for b, res in zip(batches, multi):
+            single = pv[0].verify(b, group_size=m)
+            assert res.ok == single.ok
+            assert [int(x) for x in res.status] == [int(x) for x in single.status]
+            if res.ok:
+                assert (res.folded.lhs, res.folded.rhs) == (single.folded.lhs, single.folded.rhs)
+        assert [r.ok for r in multi] == [True, False, True]
+        assert [int(x) for x in multi[1].status] == [0, 0, 3, 0, 0]
