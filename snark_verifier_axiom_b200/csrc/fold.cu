@@ -9,7 +9,7 @@
 // one accumulator remains -- the same tree the oracle's `api.fold` performs.
 //
 //   k_fold_sponge : one group per thread: Poseidon sponge -> r, then the scalars r^j (canonical)
-//   k_group_msm   : one block per (group, lhs|rhs): windowed scalar multiplications strided over the
+//   k_group_var / k_group_sum : the group MSMs (see below)
 //                   block's threads, shared-memory tree reduction of the partial sums, to_affine
 #include "g1.cuh"
 #include "poseidon.cuh"
@@ -82,50 +82,88 @@ __device__ __noinline__ G1Jac fold_mul_window4(const G1Affine& p, const u32* k) 
   return acc;
 }
 
-// grid = (n_groups, 2); blockDim = L (power of two); dynamic smem = L * sizeof(G1Jac)
-__global__ void k_group_msm(size_t n, size_t m, const uint8_t* accs, const u32* scalars, uint8_t* out_accs, size_t out_stride,
-                            int32_t* status, size_t status_stride_words) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  G1Jac* sm = reinterpret_cast<G1Jac*>(smem_raw);
-  size_t G = blockIdx.x;
-  int h = blockIdx.y;
+// Group MSM, split like the per-proof MSM (verify.cu):
+//   k_group_var  `vpl` threads per (group, side); a thread owns terms j = 1 + lane, 1 + lane + vpl, ... of its group
+//                and runs them as ONE interleaved (Straus) multiplication: 252 shared doublings + per term a
+//                15-entry Jacobian table and 64 table additions.  vpl = 1 where groups are plentiful (minimal work:
+//                1778 + 7 x 1185 M for a group of 8 instead of 7 x 2977), vpl = m - 1 on the upper, narrow levels
+//                (minimal latency).  The first version ran one block of 32 threads per (group, side) with 7 active
+//                lanes and was the largest consumer of issue slots of the whole step (profiles/r1_notes.md).
+//   k_group_sum  one (group, side) per thread: base_0 (scalar r^0 = 1) + partial sums, Fermat to_affine.
+#define FOLD_TERMS_MAX 16
+__device__ __forceinline__ bool load_acc_point(G1Affine& b, const uint8_t* p) {
+  load_canon32(b.x.v, p);
+  load_canon32(b.y.v, p + 32);
+  bool canon = Fq::is_canonical(b.x.v) && Fq::is_canonical(b.y.v);
+  if (!b.is_identity()) { b.x = b.x.to_mont(); b.y = b.y.to_mont(); }
+  return canon && g1_on_curve(b);
+}
+
+__global__ void __launch_bounds__(64) k_group_var(size_t n_seg, size_t n, size_t m, u32 vpl, const uint8_t* accs, const u32* scalars,
+                                                  G1Jac* tables, G1Jac* partials, int32_t* status, size_t status_stride_words) {
   size_t n_groups = (n + m - 1) / m;
+  size_t n_threads = n_seg * n_groups * 2 * vpl;
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_threads) return;
+  u32 lane = (u32)(gid % vpl);
+  size_t gs = gid / vpl;  // (G, side)
+  int h = (int)(gs & 1);
+  size_t G = gs >> 1;
   size_t seg = G / n_groups, g = G % n_groups;
   size_t begin = seg * n + g * m, end = (g * m + m < n ? g * m + m : n) + seg * n;
-  G1Jac acc = G1Jac::identity();
-  for (size_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
-    G1Affine b;
-    load_canon32(b.x.v, accs + i * 128 + h * 64);
-    load_canon32(b.y.v, accs + i * 128 + h * 64 + 32);
-    bool canon = Fq::is_canonical(b.x.v) && Fq::is_canonical(b.y.v);
-    if (!b.is_identity()) { b.x = b.x.to_mont(); b.y = b.y.to_mont(); }
-    if (!canon || !g1_on_curve(b)) {
+  u32 k[FOLD_TERMS_MAX][8];
+  u32 nt = 0;
+  for (size_t i = begin + 1 + lane; i < end && nt < FOLD_TERMS_MAX; i += vpl, nt++) {
+    load_canon32(k[nt], reinterpret_cast<const uint8_t*>(scalars + i * 8));
+    G1Affine base;
+    if (!load_acc_point(base, accs + i * 128 + h * 64)) {
       atomicMax(status + seg * status_stride_words, SVK_TRANSCRIPT | (SVK_T_POINT_INVALID << 8));
-      continue;
+      base = G1Affine::identity();
     }
-    if (i == begin) {
-      acc = acc.add_affine(b);
-    } else {
-      u32 k[8];
-      load_canon32(k, reinterpret_cast<const uint8_t*>(scalars + i * 8));
-      acc = acc.add(fold_mul_window4(b, k));
+    G1Jac* tb = tables + ((size_t)nt * 16) * n_threads + gid;  // entry d at tb[d * n_threads]
+    G1Jac e = G1Jac::from_affine(base);
+    tb[1 * n_threads] = e;
+    G1Jac cur = e.dbl();
+    tb[2 * n_threads] = cur;
+    for (u32 d = 3; d < 16; d++) {
+      cur = cur.add_affine(base);
+      tb[d * n_threads] = cur;
     }
   }
-  sm[threadIdx.x] = acc;
-  __syncthreads();
-  for (unsigned s = blockDim.x / 2; s >= 1; s >>= 1) {
-    if (threadIdx.x < s) sm[threadIdx.x] = sm[threadIdx.x].add(sm[threadIdx.x + s]);
-    __syncthreads();
+  G1Jac acc = G1Jac::identity();
+  for (int w = 63; w >= 0; w--) {
+    if (w != 63) acc = acc.dbl().dbl().dbl().dbl();
+    for (u32 t = 0; t < nt; t++) {
+      u32 d = (k[t][w >> 3] >> ((w & 7) * 4)) & 0xf;
+      if (d) acc = acc.add(tables[((size_t)t * 16 + d) * n_threads + gid]);
+    }
   }
-  if (threadIdx.x == 0) {
-    G1Affine a = sm[0].to_affine();
-    Fq x = a.x.from_mont(), y = a.y.from_mont();
-    uint4* o = reinterpret_cast<uint4*>(out_accs + G * out_stride + h * 64);
-    o[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
-    o[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
-    o[2] = make_uint4(y.v[0], y.v[1], y.v[2], y.v[3]);
-    o[3] = make_uint4(y.v[4], y.v[5], y.v[6], y.v[7]);
+  partials[gid] = acc;
+}
+
+__global__ void __launch_bounds__(128) k_group_sum(size_t n_seg, size_t n, size_t m, u32 vpl, const uint8_t* accs, const G1Jac* partials,
+                                                   uint8_t* out_accs, size_t out_stride, int32_t* status, size_t status_stride_words) {
+  size_t n_groups = (n + m - 1) / m;
+  size_t gs = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gs >= n_seg * n_groups * 2) return;
+  int h = (int)(gs & 1);
+  size_t G = gs >> 1;
+  size_t seg = G / n_groups, g = G % n_groups;
+  size_t begin = seg * n + g * m;
+  G1Affine b0;
+  if (!load_acc_point(b0, accs + begin * 128 + h * 64)) {
+    atomicMax(status + seg * status_stride_words, SVK_TRANSCRIPT | (SVK_T_POINT_INVALID << 8));
+    b0 = G1Affine::identity();
   }
+  G1Jac acc = G1Jac::from_affine(b0);
+  for (u32 l = 0; l < vpl; l++) acc = acc.add(partials[gs * vpl + l]);
+  G1Affine a = acc.to_affine();
+  Fq x = a.x.from_mont(), y = a.y.from_mont();
+  uint4* o = reinterpret_cast<uint4*>(out_accs + G * out_stride + h * 64);
+  o[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  o[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+  o[2] = make_uint4(y.v[0], y.v[1], y.v[2], y.v[3]);
+  o[3] = make_uint4(y.v[4], y.v[5], y.v[6], y.v[7]);
 }
 
 // Folds `n_seg` independent batches of `n` accumulators each (d_accs: [seg][n] x 128 B) down to one accumulator per
@@ -157,11 +195,22 @@ int svk_fold_launch_seg(svk_ctx* ctx, size_t n_seg, size_t n, const uint8_t* d_a
     SVK_LAUNCH(ctx, "k_fold_sponge",
                k_fold_sponge<<<(unsigned)((total_groups + 31) / 32), 32, 0, s>>>(n_seg, cnt, m, cur, ctx->d_poseidon, d_scal, last ? d_r : nullptr,
                                                                                 out_stride / 4, d_status, out_stride / 4));
-    unsigned L = 32;
-    while (L < m && L < 256) L <<= 1;
-    dim3 grid((unsigned)total_groups, 2);
-    SVK_LAUNCH(ctx, "k_group_msm",
-               k_group_msm<<<grid, L, L * sizeof(G1Jac), s>>>(cnt, m, cur, d_scal, dst, last ? out_stride : 128, d_status, out_stride / 4));
+    // lanes per (group, side): 1 while there are enough groups to fill the machine, else one lane per term
+    size_t gm = cnt < m ? cnt : m;
+    u32 vpl = 1;
+    if (total_groups * 2 < 2048 && gm > 1) vpl = (u32)(gm - 1);
+    size_t terms_per_thread = gm > 1 ? (gm - 1 + vpl - 1) / vpl : 0;
+    if (terms_per_thread > FOLD_TERMS_MAX) vpl = (u32)((gm - 1 + FOLD_TERMS_MAX - 1) / FOLD_TERMS_MAX), terms_per_thread = (gm - 1 + vpl - 1) / vpl;
+    size_t var_threads = total_groups * 2 * vpl;
+    G1Jac *d_tables, *d_partials;
+    if (svk_scratch(ctx, 17, (terms_per_thread * 16 * var_threads + 1) * sizeof(G1Jac), (void**)&d_tables)) return -1;
+    if (svk_scratch(ctx, 18, (var_threads + 1) * sizeof(G1Jac), (void**)&d_partials)) return -1;
+    SVK_LAUNCH(ctx, "k_group_var",
+               k_group_var<<<(unsigned)((var_threads + 63) / 64), 64, 0, s>>>(n_seg, cnt, m, vpl, cur, d_scal, d_tables, d_partials, d_status,
+                                                                              out_stride / 4));
+    SVK_LAUNCH(ctx, "k_group_sum",
+               k_group_sum<<<(unsigned)((total_groups * 2 + 127) / 128), 128, 0, s>>>(n_seg, cnt, m, vpl, cur, d_partials, dst,
+                                                                                      last ? out_stride : 128, d_status, out_stride / 4));
     if (last) break;
     cur = dst;
     cnt = groups;
