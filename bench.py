@@ -35,7 +35,7 @@ def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=128)
-    ap.add_argument("--inflight", type=int, default=8, help="launches in flight (one libsvk context + stream each)")
+    ap.add_argument("--inflight", type=int, default=16, help="launches in flight (one libsvk context + stream each)")
     ap.add_argument("--batches-per-launch", type=int, default=8, help="4096-proof batches verified by one call (each folded + decided on its own)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4096, help="proofs per GPU per step")
