@@ -28,7 +28,7 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 METRIC = "bn254_kzg_proofs_verified_per_sec"
 UNIT = "proofs/s"
-WORKLOAD = "standard_plonk_k8_shplonk_poseidon: succinct verify each + KzgAs fold + one pairing"
+WORKLOAD = "standard_plonk_k8_{scheme}_poseidon: succinct verify each + KzgAs fold + one pairing"
 
 
 def parse():
@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4096, help="proofs per GPU per step")
     ap.add_argument("--group-size", type=int, default=8, help="KzgAs fold group size (0 = the reference's flat fold)")
+    ap.add_argument("--scheme", default="bdfg21", choices=["bdfg21", "gwc19"], help="multi-open scheme of the proofs (BASELINE config 2: SHPLONK; config 4: GWC)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="proofs in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -97,7 +98,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ workload
-def make_workload(batch):
+def make_workload(batch, scheme="bdfg21"):
     """`batch` proofs from the committed fixture (64 distinct trapdoor-forged proofs per scheme, generated
     by tests/golden/make_golden.py), tiled.  Verification time does not depend on the proof bytes."""
     import numpy as np
@@ -105,30 +106,30 @@ def make_workload(batch):
     from snark_verifier_axiom_b200.standard_plonk import load_golden
 
     g = load_golden()
-    snarks = g["schemes"]["bdfg21"]["snarks"]
+    snarks = g["schemes"][scheme]["snarks"]
     reps = [snarks[i % len(snarks)] for i in range(batch)]
     return g, reps, np
 
 
-def cpu_baseline(g, sample, group_size):
+def cpu_baseline(g, sample, group_size, scheme="bdfg21"):
     """The reference's algorithm on the host: oracle/c (`kind: port`, C restatement: naive per-pair scalar
     multiplication, per-element Fermat inversion, serial sponge, one pairing) when built, else the Python
     oracle.  Bounded sample of the same workload; returns the cpu_baseline object."""
     try:
         from oracle.c import cref
 
-        return cref.bench_baseline(g, sample, group_size)
+        return cref.bench_baseline(g, sample, group_size, scheme)
     except Exception as e:  # C oracle not built: Python oracle, tiny sample
         note = f"python oracle (C oracle unavailable: {type(e).__name__})"
     from oracle import api, forge
 
     S = forge.Setup(0)
     n = min(sample or 4, 4)
-    snarks = g["schemes"]["bdfg21"]["snarks"][:n]
+    snarks = g["schemes"][scheme]["snarks"][:n]
     t0 = time.perf_counter()
     pairs = []
     for s in snarks:
-        a = api.succinct_verify(S.dk.svk, S.protocol, s.instances, s.proof, "bdfg21")[0]
+        a = api.succinct_verify(S.dk.svk, S.protocol, s.instances, s.proof, scheme)[0]
         pairs.append((a.lhs.pt, a.rhs.pt))
     acc, _ = api.fold(pairs, group_size)
     ok = api.decide(S.dk, acc)
@@ -142,11 +143,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    g, reps, np = make_workload(64)
+    g, reps, np = make_workload(64, args.scheme)
     vals = []
     base = None
     for _ in range(args.warmup + args.steps):
-        base = cpu_baseline(g, args.cpu_sample, args.group_size)
+        base = cpu_baseline(g, args.cpu_sample, args.group_size, args.scheme)
         vals.append(base["value"])
     vals = vals[args.warmup:] or vals
     v = sum(vals) / len(vals)
@@ -155,7 +156,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * args.batch / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (254-bit Fq/Fr)",
         "data": "synthetic: trapdoor-forged StandardPlonk k=8 SHPLONK proofs (tests/golden), CPU sample",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "fold_group_size": args.group_size},
+        "config": {"workload": WORKLOAD.format(scheme="shplonk" if args.scheme == "bdfg21" else "gwc"), "batch_per_gpu": args.batch, "fold_group_size": args.group_size},
         "cpu_baseline": base, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out))
@@ -167,11 +168,11 @@ class Slot:
     keep several independent 4096-proof batches in flight, which is how a throughput device hides the
     latency-bound tail of a batch (serial fold sponge, the single pairing)."""
 
-    def __init__(self, torch, V, ShardedBatchVerifier, g, local, dev, world, rank, group_size, max_batches):
+    def __init__(self, torch, V, ShardedBatchVerifier, g, local, dev, world, rank, group_size, max_batches, mos):
         self.ctx = V.Context(local)
         self.stream = torch.cuda.Stream(device=dev)
         self.ctx.set_stream(self.stream.cuda_stream)
-        self.pv = V.PlonkVerifier(self.ctx, g["dk"], g["protocol"], V.SHPLONK)
+        self.pv = V.PlonkVerifier(self.ctx, g["dk"], g["protocol"], mos)
         self.sv = ShardedBatchVerifier(self.pv, world, rank, dev, self.stream, group_size=group_size, max_batches=max_batches)
 
 
@@ -192,12 +193,13 @@ def run_ours(args):
     from snark_verifier_axiom_b200.distributed import ShardedBatchVerifier
 
     B = max(1, args.batches_per_launch)
-    g, reps, np = make_workload(args.batch * B)
+    g, reps, np = make_workload(args.batch * B, args.scheme)
+    mos = V.SHPLONK if args.scheme == "bdfg21" else V.GWC
     nb1 = args.batch           # proofs per batch (= per step)
     n = args.batch * B         # proofs per launch
     S = max(1, args.inflight)
     steps = -(-args.steps // B) * B  # whole launches
-    slots = [Slot(torch, V, ShardedBatchVerifier, g, local, dev, world, rank, args.group_size, B) for _ in range(S)]
+    slots = [Slot(torch, V, ShardedBatchVerifier, g, local, dev, world, rank, args.group_size, B, mos) for _ in range(S)]
     pv = slots[0].pv
     inst, n_inst, proofs, lens = pv.pack(reps)
     h_inst = torch.from_numpy(inst).pin_memory()
@@ -381,12 +383,12 @@ def run_ours(args):
             "whole_step_frac": (total_work * world / (ms_per_step * 1e-3)) / peak,
             "hbm_gbs_algorithmic": (h2d + d2h) / (ms_per_step * 1e-3) / 1e9,
         }
-        base = None if args.no_cpu_baseline else cpu_baseline(g, args.cpu_sample, args.group_size)
+        base = None if args.no_cpu_baseline else cpu_baseline(g, args.cpu_sample, args.group_size, args.scheme)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (254-bit Fq/Fr Montgomery, integer pipe)",
-            "data": "synthetic: 64 distinct trapdoor-forged StandardPlonk k=8 SHPLONK proofs (tests/golden, oracle-generated) tiled to the batch",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": nb1, "global_batch": world * nb1, "proof_bytes": info["proof_len"], "fold_group_size": args.group_size,
+            "data": "synthetic: 64 distinct trapdoor-forged StandardPlonk k=8 proofs (tests/golden, oracle-generated) tiled to the batch",
+            "config": {"workload": WORKLOAD.format(scheme="shplonk" if args.scheme == "bdfg21" else "gwc"), "batch_per_gpu": nb1, "global_batch": world * nb1, "proof_bytes": info["proof_len"], "fold_group_size": args.group_size,
                        "batches_per_launch": B, "launches_in_flight": S, "launch_latency_ms": launch_latency_ms,
                        "fold": "flat (reference aggregation.rs:235-245)" if args.group_size in (0, 1) else f"tree, groups of {args.group_size}",
                        "batches_in_flight": S * B, "single_batch_latency_ms": latency_ms,

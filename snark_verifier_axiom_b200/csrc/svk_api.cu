@@ -42,20 +42,29 @@ static int upload(svk_ctx* ctx, T** d, const std::vector<T>& v) {
 // (one full windowed scalar multiplication each, ~2977 M); in k_msm_sum every one of the 16 lanes of a proof
 // gets an EQUAL number of fixed-base table windows (11 M each; vk commitments and g), and the partial sums /
 // scalar == 1 bases are dealt round-robin.  Returns the algorithmic Fq mults per proof for this side.
-static size_t schedule_msm(const std::vector<MsmTermDev>& terms, std::vector<MsmWork>& var_items, std::vector<MsmWork>& work,
-                           std::vector<u32>& lane_off, bool partial_side, u32 var_lanes) {
+// `var_lane_base`: index of this side's first k_msm_var lane; `var_lanes`: how many lanes this side may use.
+static size_t schedule_msm(const std::vector<MsmTermDev>& terms, std::vector<std::vector<MsmWork>>& var_lanes_items, u32 var_lane_base,
+                           u32 var_lanes, std::vector<MsmWork>& work, std::vector<u32>& lane_off) {
   const int L = SVK_MSM_LANES;
   std::vector<std::vector<MsmWork>> lanes(L);
   size_t total = 0;
   int rr = 0;
+  u32 n_var = 0;
   std::vector<MsmTermDev> fixed_terms;
   for (auto& t : terms) {
     if (t.slot < 0) { lanes[rr++ % L].push_back({2, t.fixed, t.base, -1, 0, 0}); total += 11; }
     else if (t.fixed) fixed_terms.push_back(t);
-    else { var_items.push_back({0, 0, t.base, t.slot, 0, 0}); total += 161 + 64 * 16; }
+    else {
+      var_lanes_items[var_lane_base + (n_var % var_lanes)].push_back({0, 0, t.base, t.slot, 0, 0});
+      n_var++;
+      total += 161 + 64 * 16;
+    }
   }
-  if (partial_side)  // the k_msm_var partial sums of this proof (one per var lane) are added on this side
-    for (u32 l = 0; l < var_lanes; l++) { lanes[rr++ % L].push_back({3, 0, (int32_t)l, -1, 0, 0}); total += 252 * 7 + 16; }
+  u32 used = std::min(n_var, var_lanes);
+  for (u32 l = 0; l < used; l++) {  // this side's k_msm_var partial sums
+    lanes[rr++ % L].push_back({3, 0, (int32_t)(var_lane_base + l), -1, 0, 0});
+    total += 252 * 7 + 16;
+  }
   size_t fixed_windows = fixed_terms.size() * SVK_FIXED_WINDOWS;
   size_t per = (fixed_windows + L - 1) / L;
   size_t ti = 0, w = 0;
@@ -119,7 +128,7 @@ void svk_destroy(svk_ctx* ctx) {
   cudaFree(ctx->d_pairing_consts);
   cudaFree(ctx->d_poseidon);
   for (auto* p : ctx->protocols) {
-    cudaFree(p->d_ops); cudaFree(p->d_aux); cudaFree(p->d_consts); cudaFree(p->d_sched); cudaFree(p->d_lhs); cudaFree(p->d_rhs); cudaFree(p->d_fixed); { std::lock_guard<std::mutex> lk(g_table_mu); auto it = g_tables.find(p->table_key); if (it != g_tables.end() && --it->second.refs == 0) { cudaFree(it->second.d); g_tables.erase(it); } } cudaFree(p->d_var_items); cudaFree(p->d_work_lhs); cudaFree(p->d_work_rhs); cudaFree(p->d_lane_off_lhs); cudaFree(p->d_lane_off_rhs);
+    cudaFree(p->d_ops); cudaFree(p->d_aux); cudaFree(p->d_consts); cudaFree(p->d_sched); cudaFree(p->d_lhs); cudaFree(p->d_rhs); cudaFree(p->d_fixed); { std::lock_guard<std::mutex> lk(g_table_mu); auto it = g_tables.find(p->table_key); if (it != g_tables.end() && --it->second.refs == 0) { cudaFree(it->second.d); g_tables.erase(it); } } cudaFree(p->d_var_items); cudaFree(p->d_var_lane_off); cudaFree(p->d_work_lhs); cudaFree(p->d_work_rhs); cudaFree(p->d_lane_off_lhs); cudaFree(p->d_lane_off_rhs);
     delete p;
   }
   if (ctx->done) cudaEventDestroy(ctx->done);
@@ -283,26 +292,25 @@ int svk_protocol_compile(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos,
   pd->n_rhs = (u32)rhs.size();
   std::vector<MsmWork> wl, wr, var_items;
   std::vector<u32> ol, orr;
-  // Variable-base terms of BOTH sides must be summed on their own side: k_msm_var handles one side's terms per
-  // launch only if the other side has none (true for SHPLONK: rhs = W'; GWC's rhs has 3 scaled W_i).  To keep one
-  // launch, a side that owns variable-base terms gets its own var-item range; here both ranges share the kernel by
-  // running the lhs terms through k_msm_var and the (few) rhs terms as fixed-free full multiplications in k_msm_sum.
+  // k_msm_var lanes: `var_lanes` threads per proof for the lhs terms, and one more for the rhs side when it has
+  // scaled variable bases of its own (GWC: rhs = sum u^i W_i; SHPLONK's rhs is W' itself).
   pd->var_lanes = 2;  // measured on B200 (profiles/r1_notes.md): 1 and 2 give the same throughput, 2 halves the kernel's latency
   if (const char* e = getenv("SVK_VAR_LANES")) pd->var_lanes = (u32)std::max(1, std::min(8, atoi(e)));
-  std::vector<MsmWork> var_rhs;
-  pd->msm_work_modmul = schedule_msm(lhs, var_items, wl, ol, true, pd->var_lanes) + schedule_msm(rhs, var_rhs, wr, orr, false, 0);
-  // rhs variable-base terms (GWC): executed inside k_msm_sum as kind-0 items, dealt over the lanes
-  if (!var_rhs.empty()) {
-    std::vector<std::vector<MsmWork>> lanes(SVK_MSM_LANES);
-    for (int l = 0; l < SVK_MSM_LANES; l++) lanes[l].assign(wr.begin() + orr[l], wr.begin() + orr[l + 1]);
-    for (size_t i = 0; i < var_rhs.size(); i++) lanes[i % SVK_MSM_LANES].push_back(var_rhs[i]);
-    wr.clear();
-    for (int l = 0; l < SVK_MSM_LANES; l++) { orr[l] = (u32)wr.size(); wr.insert(wr.end(), lanes[l].begin(), lanes[l].end()); }
-    orr[SVK_MSM_LANES] = (u32)wr.size();
-    pd->msm_work_modmul += var_rhs.size() * (2977 - 161 - 1024);
+  bool rhs_var = false;
+  for (auto& t : rhs) rhs_var = rhs_var || (t.slot >= 0 && !t.fixed);
+  std::vector<std::vector<MsmWork>> vlanes(pd->var_lanes + (rhs_var ? 1 : 0));
+  pd->msm_work_modmul = schedule_msm(lhs, vlanes, 0, pd->var_lanes, wl, ol) + schedule_msm(rhs, vlanes, pd->var_lanes, 1, wr, orr);
+  std::vector<u32> vloff;
+  for (auto& l : vlanes) {
+    vloff.push_back((u32)var_items.size());
+    var_items.insert(var_items.end(), l.begin(), l.end());
+    pd->var_terms_per_thread = std::max<u32>(pd->var_terms_per_thread, (u32)l.size());
   }
+  vloff.push_back((u32)var_items.size());
   pd->n_var = (u32)var_items.size();
-  if ((pd->n_var + pd->var_lanes - 1) / pd->var_lanes > 16) { delete pd; return svk_fail(ctx, "too many variable-base terms per thread (raise SVK_VAR_LANES)"); }
+  pd->var_lanes_total = (u32)vloff.size() - 1;
+  if (pd->var_terms_per_thread > 16) { delete pd; return svk_fail(ctx, "too many variable-base terms per thread (raise SVK_VAR_LANES)"); }
+  if (upload(ctx, &pd->d_var_lane_off, vloff)) { delete pd; return -1; }
   if (upload(ctx, &pd->d_var_items, var_items) || upload(ctx, &pd->d_work_lhs, wl) || upload(ctx, &pd->d_lane_off_lhs, ol) || upload(ctx, &pd->d_work_rhs, wr) ||
       upload(ctx, &pd->d_lane_off_rhs, orr)) { delete pd; return -1; }
   pd->table_key = std::to_string(ctx->device) + ":" + std::string((const char*)fixed.data(), fixed.size() * sizeof(G1Affine));
@@ -333,7 +341,7 @@ int svk_protocol_info(svk_ctx* ctx, int proto, uint32_t* out) {
   ProtocolDevice* pd = ctx->protocols[proto];
   out[0] = pd->proof_len; out[1] = pd->n_instances; out[2] = pd->n_challenges; out[3] = pd->n_regs; out[4] = pd->n_ops;
   out[5] = (u32)pd->n_perm; out[6] = pd->verify_valid ? 1 : 0; out[7] = (u32)pd->n_fr_mul; out[8] = pd->n_lhs; out[9] = pd->n_rhs;
-  out[10] = (u32)pd->points.size(); out[11] = pd->n_scalar_slots; out[12] = (u32)pd->msm_work_modmul; out[13] = (u32)(pd->n_var * (161 + 64 * 16) + pd->var_lanes * 252 * 7); out[14] = pd->n_var; out[15] = pd->var_lanes;
+  out[10] = (u32)pd->points.size(); out[11] = pd->n_scalar_slots; out[12] = (u32)pd->msm_work_modmul; out[13] = (u32)(pd->n_var * (161 + 64 * 16) + pd->var_lanes_total * 252 * 7); out[14] = pd->n_var; out[15] = pd->var_lanes_total;
   return 0;
 }
 

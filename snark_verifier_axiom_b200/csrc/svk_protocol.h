@@ -52,7 +52,10 @@ struct ProtocolDevice {
   MsmWork* d_var_items = nullptr;      // variable-base terms of both sides; partial index = position here
   u32 n_var = 0;
   std::string table_key;               // key of the shared fixed-base table (svk_api.cu: g_tables)
-  u32 var_lanes = 1;                   // threads per proof in k_msm_var (terms dealt round-robin)
+  u32 var_lanes = 1;                   // k_msm_var threads per proof serving the lhs side
+  u32 var_lanes_total = 1;             // ... plus the lanes of the rhs side (GWC: rhs = sum u^i W_i)
+  u32 var_terms_per_thread = 0;
+  u32* d_var_lane_off = nullptr;       // items of var lane l = var_items[off[l] .. off[l+1])
   size_t msm_work_modmul = 0;          // algorithmic Fq mults per proof of the scheduled MSM (DESIGN.md work model)
   G1Affine* d_fixed = nullptr;  // preprocessed..., then g at index n_pre
   u32 n_pre = 0;

@@ -124,11 +124,12 @@ __global__ void __launch_bounds__(32) k_fixed_tables(u32 n_fixed, const G1Affine
 //   k_to_affine  one (proof, side) per thread: Fermat inversion, canonical accumulator bytes
 // Straus / interleaved windows: one thread owns up to SVK_VAR_TERMS_MAX variable-base terms of ONE proof and
 // shares the 252 doublings between them (per term: a 15-entry Jacobian table + 64 table additions).  With
-// `vpl` threads ("var lanes") per proof the terms are dealt round-robin: vpl = 1 minimises total work
+// `vpl` threads ("var lanes") per proof, each with its own host-scheduled item list (lanes never mix the lhs and
+// rhs sides): fewer lanes minimise total work
 // (1778 + 11 x 1185 M per StandardPlonk proof instead of 11 x 2977), larger vpl shortens the latency.
 // partials[(lane * n_items) + proof]  (Jacobian)
 #define SVK_VAR_TERMS_MAX 16
-__global__ void __launch_bounds__(64) k_msm_var(size_t n_items, const MsmWork* var_items, u32 n_var, u32 vpl, const G1Affine* pts,
+__global__ void __launch_bounds__(64) k_msm_var(size_t n_items, const MsmWork* var_items, const u32* var_lane_off, u32 vpl, const G1Affine* pts,
                                                 const u32* scalars, G1Jac* tables, G1Jac* partials) {
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= n_items * vpl) return;
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(64) k_msm_var(size_t n_items, const MsmWork* v
   size_t n_threads = n_items * vpl;
   u32 k[SVK_VAR_TERMS_MAX][8];
   u32 nt = 0;
-  for (u32 vi = lane; vi < n_var && nt < SVK_VAR_TERMS_MAX; vi += vpl, nt++) {
+  for (u32 vi = var_lane_off[lane]; vi < var_lane_off[lane + 1] && nt < SVK_VAR_TERMS_MAX; vi++, nt++) {
     MsmWork wk = var_items[vi];
     const uint4* sp = reinterpret_cast<const uint4*>(scalars + ((size_t)wk.slot * n_items + it) * 8);
     uint4 lo = sp[0], hi = sp[1];
@@ -291,15 +292,15 @@ int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const
   }
   if (mode == 0) {
     G1Jac *d_partials, *d_sums, *d_tables;
-    u32 vpl = pd->var_lanes;
-    u32 terms_per_thread = (pd->n_var + vpl - 1) / vpl;
+    u32 vpl = pd->var_lanes_total;
+    u32 terms_per_thread = pd->var_terms_per_thread;
     if (svk_scratch(ctx, 7, (size_t)std::max<u32>(vpl, 1) * n * sizeof(G1Jac), (void**)&d_partials)) return -1;
     if (svk_scratch(ctx, 15, 2 * n * sizeof(G1Jac), (void**)&d_sums)) return -1;
     if (pd->n_var) {
       size_t total = n * vpl;
       if (svk_scratch(ctx, 6, (size_t)terms_per_thread * 16 * total * sizeof(G1Jac), (void**)&d_tables)) return -1;
       SVK_LAUNCH(ctx, "k_msm_var",
-                 k_msm_var<<<(unsigned)((total + 63) / 64), 64, 0, s>>>(n, pd->d_var_items, pd->n_var, vpl, d_pts, d_scalars, d_tables, d_partials));
+                 k_msm_var<<<(unsigned)((total + 63) / 64), 64, 0, s>>>(n, pd->d_var_items, pd->d_var_lane_off, vpl, d_pts, d_scalars, d_tables, d_partials));
     }
     dim3 grid((unsigned)((n * MSM_LANES + 127) / 128), 2);
     SVK_LAUNCH(ctx, "k_msm_sum",

@@ -97,6 +97,31 @@ def main():
                           "kernels_ms": {k: round(v, 3) for k, v in prof.items()}}))
     del pts, dl
 
+    # ---- config 1: one SHPLONK proof, full PlonkVerifier::verify (succinct verify + fold of one + pairing), latency
+    g = load_golden()
+    pv1 = V.PlonkVerifier(ctx, g["dk"], g["protocol"], V.SHPLONK)
+    sn = g["schemes"]["bdfg21"]["snarks"][0]
+    import time as _t
+    pv1.verify_one(sn)
+    t0 = _t.perf_counter()
+    for _ in range(5):
+        pv1.verify_one(sn)
+    gpu_ms = 1e3 * (_t.perf_counter() - t0) / 5
+    try:
+        from oracle import forge
+        from oracle.c import cref
+        S_ = forge.Setup(0)
+        tr_ = cref.Trace(S_, "bdfg21")
+        t0 = _t.perf_counter()
+        for _ in range(5):
+            accs_, st_ = cref.replay(tr_, [sn.proof], [sn.instances], 1)
+            assert cref.decide(accs_[0], S_.dk)
+        cpu_ms = 1e3 * (_t.perf_counter() - t0) / 5
+    except Exception as e:  # oracle not available
+        cpu_ms = None
+    print(json.dumps({"config": "single_proof_verify_latency", "gpu_ms_host_call": gpu_ms, "cpu_port_ms_1_thread": cpu_ms,
+                      "note": "one proof cannot fill a GPU: the B200 path is a throughput device (batch configs)"}))
+
     # ---- config 5
     g = load_golden()
     kid = ctx.load_deciding_key(g["dk"])
