@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="proofs in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tiled", action="store_true", help="tile the 64 fixture proofs instead of forging distinct ones")
     return ap.parse_args()
 
 
@@ -201,7 +202,17 @@ def run_ours(args):
     steps = -(-args.steps // B) * B  # whole launches
     slots = [Slot(torch, V, ShardedBatchVerifier, g, local, dev, world, rank, args.group_size, B, mos) for _ in range(S)]
     pv = slots[0].pv
-    inst, n_inst, proofs, lens = pv.pack(reps)
+    data = "synthetic: 64 distinct trapdoor-forged StandardPlonk k=8 proofs (tests/golden, oracle-generated) tiled to the batch"
+    if args.scheme == "bdfg21" and not args.tiled:
+        # n DISTINCT valid proofs per launch, forged with the test SRS trapdoor on the GPU (snark_verifier_axiom_b200/synth.py)
+        from snark_verifier_axiom_b200 import synth
+
+        inst, proofs = synth.forge_shplonk_batch(pv, g["trapdoor_s"], g["vk_dlogs"], n, seed=1 + rank)
+        inst = np.ascontiguousarray(inst)
+        n_inst, lens = 1, np.full(n, proofs.shape[1], dtype=np.uint32)
+        data = f"synthetic: {n} distinct valid StandardPlonk k=8 SHPLONK proofs per launch, forged at start-up with the test-SRS trapdoor (synth.py; oracle-validated in tests/test_gpu_synth.py)"
+    else:
+        inst, n_inst, proofs, lens = pv.pack(reps)
     h_inst = torch.from_numpy(inst).pin_memory()
     h_proofs = torch.from_numpy(proofs).pin_memory()
     # distinct device copies of the inputs, rotated per step, together larger than the 126 MB L2
@@ -387,7 +398,7 @@ def run_ours(args):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (254-bit Fq/Fr Montgomery, integer pipe)",
-            "data": "synthetic: 64 distinct trapdoor-forged StandardPlonk k=8 proofs (tests/golden, oracle-generated) tiled to the batch",
+            "data": data,
             "config": {"workload": WORKLOAD.format(scheme="shplonk" if args.scheme == "bdfg21" else "gwc"), "batch_per_gpu": nb1, "global_batch": world * nb1, "proof_bytes": info["proof_len"], "fold_group_size": args.group_size,
                        "batches_per_launch": B, "launches_in_flight": S, "launch_latency_ms": launch_latency_ms,
                        "fold": "flat (reference aggregation.rs:235-245)" if args.group_size in (0, 1) else f"tree, groups of {args.group_size}",

@@ -100,6 +100,16 @@ int svk_plonk_succinct_verify_batch_dev(svk_ctx* ctx, int proto, size_t n, const
                                         const void* d_proofs, size_t proof_stride, const void* d_proof_lens, void* d_out_acc,
                                         void* d_out_challenges, void* d_out_status);
 
+/* The unevaluated `Msm` (util/msm.rs:20-24) behind out_acc: the terms of `lhs` (side 0) / `rhs` (side 1) as
+ * (fixed, base, slot) triples -- fixed = 1: base indexes protocol.preprocessed (base == len: the generator `svk.g`),
+ * fixed = 0: base is the ordinal of a G1 point read from the proof; slot = index into the per-proof scalar vector,
+ * -1 when the scalar is the constant 1 -- and the scalar vectors themselves ([n][n_scalar_slots], canonical).
+ * Debug / tooling surface (the synthetic-workload generator solves for the last opening point with it). */
+int svk_protocol_msm_terms(svk_ctx* ctx, int proto, int side, int32_t* out, size_t max_terms);
+int svk_plonk_msm_scalars_batch(svk_ctx* ctx, int proto, size_t n, const svk_fe* instances, uint32_t n_instances, const uint8_t* proofs,
+                                size_t proof_stride, const uint32_t* proof_lens, svk_fe* out_scalars, svk_fe* out_challenges,
+                                int32_t* out_status);
+
 /* ---- KzgAs accumulation (pcs/kzg/accumulation.rs:17-63, 97-137, 139-196) ------------------------
  * `KzgAs::create_proof` / `read_proof`+`verify` with `KzgAsProvingKey::default()` (zk = false, the
  * SDK's use at snark-verifier-sdk/src/halo2/aggregation.rs:235-245): a fresh Poseidon transcript

@@ -47,6 +47,8 @@ def _load():
     lib.svk_plonk_verify_multi_dev.argtypes = [vp, i32, sz, sz, vp, ctypes.c_uint32, vp, sz, vp, sz, vp, vp, vp]
     lib.svk_kzg_as_fold_multi_dev.argtypes = [vp, sz, sz, vp, sz, vp]
     lib.svk_kzg_decide_records_dev.argtypes = [vp, i32, sz, vp]
+    lib.svk_protocol_msm_terms.argtypes = [vp, i32, i32, vp, sz]
+    lib.svk_plonk_msm_scalars_batch.argtypes = [vp, i32, sz, vp, ctypes.c_uint32, vp, sz, vp, vp, vp, vp]
     lib.svk_bench_modmul_peak.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     return lib
 

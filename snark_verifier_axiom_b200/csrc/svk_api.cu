@@ -290,6 +290,8 @@ int svk_protocol_compile(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos,
   std::vector<MsmTermDev> lhs = conv(cp.lhs), rhs = conv(cp.rhs);
   pd->n_lhs = (u32)lhs.size();
   pd->n_rhs = (u32)rhs.size();
+  pd->h_lhs = lhs;
+  pd->h_rhs = rhs;
   std::vector<MsmWork> wl, wr, var_items;
   std::vector<u32> ol, orr;
   // k_msm_var lanes: `var_lanes` threads per proof for the lhs terms, and one more for the rhs side when it has
@@ -342,6 +344,33 @@ int svk_protocol_info(svk_ctx* ctx, int proto, uint32_t* out) {
   out[0] = pd->proof_len; out[1] = pd->n_instances; out[2] = pd->n_challenges; out[3] = pd->n_regs; out[4] = pd->n_ops;
   out[5] = (u32)pd->n_perm; out[6] = pd->verify_valid ? 1 : 0; out[7] = (u32)pd->n_fr_mul; out[8] = pd->n_lhs; out[9] = pd->n_rhs;
   out[10] = (u32)pd->points.size(); out[11] = pd->n_scalar_slots; out[12] = (u32)pd->msm_work_modmul; out[13] = (u32)(pd->n_var * (161 + 64 * 16) + pd->var_lanes_total * 252 * 7); out[14] = pd->n_var; out[15] = pd->var_lanes_total;
+  return 0;
+}
+
+// ---- the unevaluated `Msm` of the final accumulator (util/msm.rs:20-24): terms and per-proof scalars -------------
+int svk_protocol_msm_terms(svk_ctx* ctx, int proto, int side, int32_t* out, size_t max_terms) {
+  if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
+  const std::vector<MsmTermDev>& t = side ? ctx->protocols[proto]->h_rhs : ctx->protocols[proto]->h_lhs;
+  if (t.size() > max_terms) return svk_fail(ctx, "terms buffer too small");
+  for (size_t i = 0; i < t.size(); i++) { out[3 * i] = t[i].fixed; out[3 * i + 1] = t[i].base; out[3 * i + 2] = t[i].slot; }
+  return (int)t.size();
+}
+
+int svk_plonk_msm_scalars_batch(svk_ctx* ctx, int proto, size_t n, const svk_fe* instances, uint32_t n_instances, const uint8_t* proofs,
+                                size_t proof_stride, const uint32_t* proof_lens, svk_fe* out_scalars, svk_fe* out_challenges,
+                                int32_t* out_status) {
+  if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
+  ProtocolDevice* pd = ctx->protocols[proto];
+  std::vector<svk_acc> accs(n);
+  if (svk_plonk_succinct_verify_batch(ctx, proto, n, instances, n_instances, proofs, proof_stride, proof_lens, accs.data(), out_challenges,
+                                      out_status))
+    return -1;
+  // scratch slot 5 still holds the scalars of that call: [slot][item] x 32 B  ->  [item][slot]
+  size_t ns = pd->n_scalar_slots;
+  std::vector<uint8_t> tmp(ns * n * 32);
+  SVK_CUDA(ctx, cudaMemcpy(tmp.data(), ctx->scratch[5], tmp.size(), cudaMemcpyDeviceToHost));
+  for (size_t s = 0; s < ns; s++)
+    for (size_t i = 0; i < n; i++) memcpy(out_scalars[i * ns + s].b, &tmp[(s * n + i) * 32], 32);
   return 0;
 }
 

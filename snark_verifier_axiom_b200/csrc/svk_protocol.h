@@ -45,6 +45,7 @@ struct ProtocolDevice {
   std::vector<PointSched> points;
   PointSched* d_sched = nullptr;
   MsmTermDev *d_lhs = nullptr, *d_rhs = nullptr;
+  std::vector<MsmTermDev> h_lhs, h_rhs;  // host copies (svk_protocol_msm_terms)
   u32 n_lhs = 0, n_rhs = 0;
   MsmWork *d_work_lhs = nullptr, *d_work_rhs = nullptr;  // lane schedules: items of lane l = work[lane_off[l] .. lane_off[l+1])
   u32 *d_lane_off_lhs = nullptr, *d_lane_off_rhs = nullptr;

@@ -35,6 +35,9 @@ def main():
         "s_g2": [[hx(S.s_g2[0][0]), hx(S.s_g2[0][1])], [hx(S.s_g2[1][0]), hx(S.s_g2[1][1])]],
         "preprocessed": [pt(p) for p in S.preprocessed],
         "transcript_initial_state": hx(S.transcript_initial_state),
+        # trapdoor of this TEST SRS and discrete logs of the vk commitments (what makes forging possible)
+        "trapdoor_s": hx(S.s),
+        "vk_dlogs": [hx(d) for d in S.vk_dlogs],
         "schemes": {},
     }
     for scheme in ("bdfg21", "gwc19"):
