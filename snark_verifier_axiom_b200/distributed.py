@@ -139,3 +139,38 @@ class ShardedBatchVerifier:
                                         self.group_size, 0, st.ctypes.data_as(ctypes.c_void_p), rec.ctypes.data_as(ctypes.c_void_p))
         o.ctx._check(rc)
         return bool(rec.reshape(n_batches, RECORD)[:, OFF_OK].all()), st
+
+
+# ---------------------------------------------------------------------------------------------- sharded G1 MSM (config 3)
+class LibsvkMsmOps:
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def msm(self, n, d_scalars, d_points, d_out, d_status):
+        c = self.ctx
+        c._check(c._L.svk_msm_g1_dev(c._c, n, ctypes.c_void_p(d_scalars.data_ptr()), ctypes.c_void_p(d_points.data_ptr()),
+                                     ctypes.c_void_p(d_out.data_ptr()), ctypes.c_void_p(d_status.data_ptr())))
+
+
+def msm_sharded(ops, world, device, d_scalars, d_points, n_local, stream=None):
+    """`util::msm::multi_scalar_multiplication` over points sharded across ranks (contiguous n/world shards, SURVEY 8e):
+    every rank reduces its shard with the Pippenger kernel, the `world` partial results (64 B each) are all-gathered,
+    and each rank adds them -- EC addition is not an NCCL reduce op, so the "reduce" is an all-gather followed by an MSM
+    with unit scalars over `world` points.  Returns a uint8[64] device tensor (canonical affine point)."""
+    kw = dict(dtype=torch.uint8, device=device)
+    part = torch.zeros(64, **kw)
+    st = torch.zeros(2, dtype=torch.int32, device=device)
+    ops.msm(n_local, d_scalars, d_points, part, st)
+    if world == 1:
+        return part
+    import contextlib
+
+    cm = torch.cuda.stream(stream) if (stream is not None and device.type == "cuda") else contextlib.nullcontext()
+    with cm:
+        gathered = torch.zeros(world * 64, **kw)
+        dist.all_gather_into_tensor(gathered, part)
+        ones = torch.zeros(world, 32, **kw)
+        ones[:, 0] = 1
+    out = torch.zeros(64, **kw)
+    ops.msm(world, ones.view(-1), gathered, out, st[1:])
+    return out

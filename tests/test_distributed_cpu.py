@@ -113,3 +113,59 @@ def test_sharded_verify_gloo_world2():
     exp = b"".join(int(v).to_bytes(32, "little") for v in (l[0], l[1], r[0], r[1]))
     assert res[0][4] == exp
     assert api.decide(S.dk, (l, r))
+
+
+class OracleMsmOps:
+    def msm(self, n, d_scalars, d_points, d_out, d_status):
+        from oracle import bn254
+
+        s = d_scalars.numpy().reshape(n, 32)
+        p = d_points.numpy().reshape(n, 64)
+        acc = None
+        for i in range(n):
+            k = int.from_bytes(s[i].tobytes(), "little")
+            x, y = int.from_bytes(p[i, :32].tobytes(), "little"), int.from_bytes(p[i, 32:].tobytes(), "little")
+            pt = None if x == 0 and y == 0 else (x, y)
+            acc = bn254.g1_add(acc, bn254.g1_mul(pt, k))
+        b = bytes(64) if acc is None else acc[0].to_bytes(32, "little") + acc[1].to_bytes(32, "little")
+        d_out[:] = torch.from_numpy(np.frombuffer(b, dtype=np.uint8).copy())
+
+
+def _msm_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import random
+
+    from oracle import bn254
+    from snark_verifier_axiom_b200.distributed import msm_sharded, shard_range
+
+    rng = random.Random(11)
+    n = 9
+    pts = [bn254.g1_mul(bn254.G1_GEN, rng.randrange(1, bn254.R)) for _ in range(n)]
+    sc = [rng.randrange(bn254.R) for _ in range(n)]
+    lo, hi = shard_range(n, world, rank)
+    ds = torch.from_numpy(np.frombuffer(b"".join(s.to_bytes(32, "little") for s in sc[lo:hi]), dtype=np.uint8).copy())
+    dp = torch.from_numpy(np.frombuffer(b"".join(p[0].to_bytes(32, "little") + p[1].to_bytes(32, "little") for p in pts[lo:hi]), dtype=np.uint8).copy())
+    out = msm_sharded(OracleMsmOps(), world, torch.device("cpu"), ds, dp, hi - lo)
+    exp = bn254.g1_msm_naive(list(zip(sc, pts)))
+    q.put((rank, out.numpy().tobytes() == exp[0].to_bytes(32, "little") + exp[1].to_bytes(32, "little")))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_msm_sharded_gloo_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_msm_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
