@@ -44,7 +44,8 @@ static int upload(svk_ctx* ctx, T** d, const std::vector<T>& v) {
 // scalar == 1 bases are dealt round-robin.  Returns the algorithmic Fq mults per proof for this side.
 // `var_lane_base`: index of this side's first k_msm_var lane; `var_lanes`: how many lanes this side may use.
 static size_t schedule_msm(const std::vector<MsmTermDev>& terms, std::vector<std::vector<MsmWork>>& var_lanes_items, u32 var_lane_base,
-                           u32 var_lanes, std::vector<MsmWork>& work, std::vector<u32>& lane_off) {
+                           u32 var_lanes, std::vector<MsmWork>& work, std::vector<u32>& lane_off, std::vector<FixedSlot>& fixed_sched,
+                           u32& fixed_per) {
   const int L = SVK_MSM_LANES;
   std::vector<std::vector<MsmWork>> lanes(L);
   size_t total = 0;
@@ -65,18 +66,16 @@ static size_t schedule_msm(const std::vector<MsmTermDev>& terms, std::vector<std
     lanes[rr++ % L].push_back({3, 0, (int32_t)(var_lane_base + l), -1, 0, 0});
     total += 252 * 7 + 16;
   }
+  // fixed-base table additions: a flat list of (term, window) pairs dealt evenly, `per` per lane, padded with no-ops
   size_t fixed_windows = fixed_terms.size() * SVK_FIXED_WINDOWS;
   size_t per = (fixed_windows + L - 1) / L;
-  size_t ti = 0, w = 0;
-  for (int l = 0; l < L && fixed_windows; l++) {
-    size_t room = std::min(per, fixed_windows);
-    while (room) {
-      size_t take = std::min<size_t>(room, SVK_FIXED_WINDOWS - w);
-      lanes[l].push_back({1, 1, fixed_terms[ti].base, fixed_terms[ti].slot, (int32_t)w, (int32_t)(w + take)});
-      total += take * 11;
-      room -= take; fixed_windows -= take; w += take;
-      if (w == SVK_FIXED_WINDOWS) { w = 0; ti++; }
-    }
+  fixed_per = (u32)per;
+  fixed_sched.assign(per * L, FixedSlot{-1, 0, 0});
+  for (size_t i = 0; i < fixed_windows; i++) {
+    const MsmTermDev& ft = fixed_terms[i / SVK_FIXED_WINDOWS];
+    size_t lane = i / per, j = i % per;
+    fixed_sched[lane * per + j] = FixedSlot{ft.base, (int32_t)(i % SVK_FIXED_WINDOWS), ft.slot};
+    total += 11;
   }
   work.clear(); lane_off.assign(L + 1, 0);
   for (int l = 0; l < L; l++) { lane_off[l] = (u32)work.size(); work.insert(work.end(), lanes[l].begin(), lanes[l].end()); }
@@ -128,7 +127,7 @@ void svk_destroy(svk_ctx* ctx) {
   cudaFree(ctx->d_pairing_consts);
   cudaFree(ctx->d_poseidon);
   for (auto* p : ctx->protocols) {
-    cudaFree(p->d_ops); cudaFree(p->d_aux); cudaFree(p->d_consts); cudaFree(p->d_sched); cudaFree(p->d_lhs); cudaFree(p->d_rhs); cudaFree(p->d_fixed); { std::lock_guard<std::mutex> lk(g_table_mu); auto it = g_tables.find(p->table_key); if (it != g_tables.end() && --it->second.refs == 0) { cudaFree(it->second.d); g_tables.erase(it); } } cudaFree(p->d_var_items); cudaFree(p->d_var_lane_off); cudaFree(p->d_work_lhs); cudaFree(p->d_work_rhs); cudaFree(p->d_lane_off_lhs); cudaFree(p->d_lane_off_rhs);
+    cudaFree(p->d_ops); cudaFree(p->d_aux); cudaFree(p->d_consts); cudaFree(p->d_sched); cudaFree(p->d_lhs); cudaFree(p->d_rhs); cudaFree(p->d_fixed); { std::lock_guard<std::mutex> lk(g_table_mu); auto it = g_tables.find(p->table_key); if (it != g_tables.end() && --it->second.refs == 0) { cudaFree(it->second.d); g_tables.erase(it); } } cudaFree(p->d_var_items); cudaFree(p->d_var_lane_off); cudaFree(p->d_fixed_lhs); cudaFree(p->d_fixed_rhs); cudaFree(p->d_work_lhs); cudaFree(p->d_work_rhs); cudaFree(p->d_lane_off_lhs); cudaFree(p->d_lane_off_rhs);
     delete p;
   }
   if (ctx->done) cudaEventDestroy(ctx->done);
@@ -301,7 +300,10 @@ int svk_protocol_compile(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos,
   bool rhs_var = false;
   for (auto& t : rhs) rhs_var = rhs_var || (t.slot >= 0 && !t.fixed);
   std::vector<std::vector<MsmWork>> vlanes(pd->var_lanes + (rhs_var ? 1 : 0));
-  pd->msm_work_modmul = schedule_msm(lhs, vlanes, 0, pd->var_lanes, wl, ol) + schedule_msm(rhs, vlanes, pd->var_lanes, 1, wr, orr);
+  std::vector<FixedSlot> fl, fr;
+  pd->msm_work_modmul = schedule_msm(lhs, vlanes, 0, pd->var_lanes, wl, ol, fl, pd->fixed_per_lhs) +
+                        schedule_msm(rhs, vlanes, pd->var_lanes, 1, wr, orr, fr, pd->fixed_per_rhs);
+  if (upload(ctx, &pd->d_fixed_lhs, fl) || upload(ctx, &pd->d_fixed_rhs, fr)) { delete pd; return -1; }
   std::vector<u32> vloff;
   for (auto& l : vlanes) {
     vloff.push_back((u32)var_items.size());

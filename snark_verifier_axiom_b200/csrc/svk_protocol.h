@@ -26,6 +26,13 @@ struct MsmWork {
   int32_t slot;
   int32_t w0, w1;
 };
+// One fixed-base table addition of k_msm_sum: every lane of a proof's lane group runs the same number of these
+// (a uniform loop: per-lane item lists of different shapes diverged, ncu: 14 of 32 lanes active in that loop).
+struct FixedSlot {
+  int32_t base;  // index into fixed_bases / tables, -1 = padding (no-op)
+  int32_t w;     // 8-bit window index
+  int32_t slot;  // scalar slot
+};
 #define SVK_MSM_LANES 16
 #define SVK_FIXED_WINDOWS 32   // 8-bit windows of a 256-bit scalar
 #define SVK_FIXED_DIGITS 256   // table entries per window
@@ -49,6 +56,8 @@ struct ProtocolDevice {
   u32 n_lhs = 0, n_rhs = 0;
   MsmWork *d_work_lhs = nullptr, *d_work_rhs = nullptr;  // lane schedules: items of lane l = work[lane_off[l] .. lane_off[l+1])
   u32 *d_lane_off_lhs = nullptr, *d_lane_off_rhs = nullptr;
+  FixedSlot *d_fixed_lhs = nullptr, *d_fixed_rhs = nullptr;  // [lane][per] table additions
+  u32 fixed_per_lhs = 0, fixed_per_rhs = 0;
   G1Affine* d_fixed_tables = nullptr;  // [n_pre + 1][32 windows][256 digits]: d * 2^(8w) * B, affine Montgomery (4.7 MB for 9 bases)
   MsmWork* d_var_items = nullptr;      // variable-base terms of both sides; partial index = position here
   u32 n_var = 0;

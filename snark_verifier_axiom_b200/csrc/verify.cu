@@ -156,12 +156,28 @@ __global__ void __launch_bounds__(64) k_msm_var(size_t n_items, const MsmWork* v
       tb[d * n_threads] = cur;
     }
   }
+  // Table entries are fetched one step ahead of their use (the address depends on the scalar only): the tables of a
+  // launch are hundreds of MB, every read misses L2 (ncu: 2.6 GB of DRAM reads, long-scoreboard stall 0.65 per issue
+  // before prefetching), and a table addition (16 M) is long enough to cover a DRAM round trip.
   G1Jac acc = G1Jac::identity();
+  G1Jac nxt = G1Jac::identity();
+  u32 dn = nt ? ((k[0][7] >> 28) & 0xf) : 0;
+  if (dn) nxt = tables[((size_t)0 * 16 + dn) * n_threads + gid];
   for (int w = 63; w >= 0; w--) {
     if (w != 63) acc = acc.dbl().dbl().dbl().dbl();
     for (u32 t = 0; t < nt; t++) {
-      u32 d = (k[t][w >> 3] >> ((w & 7) * 4)) & 0xf;
-      if (d) acc = acc.add(tables[((size_t)t * 16 + d) * n_threads + gid]);
+      G1Jac cur = nxt;
+      u32 d = dn;
+      // next (term, window)
+      u32 t2 = t + 1;
+      int w2 = w;
+      if (t2 == nt) { t2 = 0; w2 = w - 1; }
+      dn = 0;
+      if (w2 >= 0) {
+        dn = (k[t2][w2 >> 3] >> ((w2 & 7) * 4)) & 0xf;
+        if (dn) nxt = tables[((size_t)t2 * 16 + dn) * n_threads + gid];
+      }
+      if (d) acc = acc.add(cur);
     }
   }
   partials[gid] = acc;
@@ -169,7 +185,8 @@ __global__ void __launch_bounds__(64) k_msm_var(size_t n_items, const MsmWork* v
 
 // work: per side, per lane a list of items of kind 1 (fixed-base window slice), 2 (add base), 3 (add partial #base)
 __global__ void __launch_bounds__(128) k_msm_sum(size_t n_items, const MsmWork* work_lhs, const u32* off_lhs, const MsmWork* work_rhs,
-                                                 const u32* off_rhs, const G1Affine* fixed_bases, const G1Affine* tables,
+                                                 const u32* off_rhs, const FixedSlot* fixed_lhs, u32 per_lhs, const FixedSlot* fixed_rhs,
+                                                 u32 per_rhs, const G1Affine* fixed_bases, const G1Affine* tables,
                                                  const G1Affine* pts, const u32* scalars, const G1Jac* partials, G1Jac* sums) {
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t item = gid / MSM_LANES;
@@ -179,6 +196,16 @@ __global__ void __launch_bounds__(128) k_msm_sum(size_t n_items, const MsmWork* 
   const MsmWork* work = blockIdx.y ? work_rhs : work_lhs;
   const u32* off = blockIdx.y ? off_rhs : off_lhs;
   G1Jac acc = G1Jac::identity();
+  // fixed-base table additions: the same trip count on every lane
+  const FixedSlot* fsched = (blockIdx.y ? fixed_rhs : fixed_lhs);
+  u32 per = blockIdx.y ? per_rhs : per_lhs;
+  for (u32 j = 0; j < per; j++) {
+    FixedSlot fs = fsched[lane * per + j];
+    if (fs.base < 0) continue;
+    u32 word = scalars[((size_t)fs.slot * n_items + it) * 8 + (fs.w >> 2)];
+    u32 d = (word >> ((fs.w & 3) * 8)) & 0xff;
+    acc = acc.add_affine(tables[((size_t)fs.base * SVK_FIXED_WINDOWS + fs.w) * SVK_FIXED_DIGITS + d]);
+  }
   for (u32 wi = off[lane]; wi < off[lane + 1]; wi++) {
     MsmWork wk = work[wi];
     if (wk.kind == 1) {
@@ -203,7 +230,7 @@ __global__ void __launch_bounds__(128) k_msm_sum(size_t n_items, const MsmWork* 
       acc = acc.add(g1_mul_window4(pts[(size_t)wk.base * n_items + it], k));
     }
   }
-  if (off[MSM_LANES] > 1) {  // a side with a single item (SHPLONK rhs = W') has nothing to reduce
+  if (off[MSM_LANES] > 1 || per) {  // a side with a single item (SHPLONK rhs = W') has nothing to reduce
 #pragma unroll
     for (int d = MSM_LANES / 2; d >= 1; d >>= 1) {
       G1Jac o = shfl_down_jac(acc, d);
@@ -304,7 +331,8 @@ int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const
     }
     dim3 grid((unsigned)((n * MSM_LANES + 127) / 128), 2);
     SVK_LAUNCH(ctx, "k_msm_sum",
-               k_msm_sum<<<grid, 128, 0, s>>>(n, pd->d_work_lhs, pd->d_lane_off_lhs, pd->d_work_rhs, pd->d_lane_off_rhs, pd->d_fixed,
+               k_msm_sum<<<grid, 128, 0, s>>>(n, pd->d_work_lhs, pd->d_lane_off_lhs, pd->d_work_rhs, pd->d_lane_off_rhs, pd->d_fixed_lhs,
+                                              pd->fixed_per_lhs, pd->d_fixed_rhs, pd->fixed_per_rhs, pd->d_fixed,
                                               pd->d_fixed_tables, d_pts, d_scalars, d_partials, d_sums));
     SVK_LAUNCH(ctx, "k_to_affine", k_to_affine<<<(unsigned)((2 * n + 127) / 128), 128, 0, s>>>(n, d_sums, d_err, d_out_acc));
   } else {
