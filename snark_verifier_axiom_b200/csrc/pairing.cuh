@@ -103,7 +103,7 @@ HDN Fq12 miller_loop_2(const G1Affine& p1, const G2Line* t1, const G1Affine& p2,
 HDN Fq12 fq12_pow_x(const Fq12& f) {
   Fq12 r = f;
   for (int i = 61; i >= 0; i--) {  // bit 62 is the MSB
-    r = r.sqr();
+    r = r.cyclotomic_sqr();
     int bit = (i >= 32) ? ((SVK_BN_X_HI >> (i - 32)) & 1) : ((SVK_BN_X_LO >> i) & 1);
     if (bit) r = r * f;
   }
@@ -118,25 +118,25 @@ HDN Fq12 final_exponentiation(const Fq12& f0, const PairingConsts& k) {
   Fq12 fx = fq12_pow_x(f);
   Fq12 fx2 = fq12_pow_x(fx);
   Fq12 fx3 = fq12_pow_x(fx2);
-  // small powers
-  Fq12 a2 = fx2.sqr();                // fx2^2
-  Fq12 a6 = a2.sqr() * a2;            // fx2^6
-  Fq12 a12 = a6.sqr();                // fx2^12
-  Fq12 a18 = a12 * a6;                // fx2^18
-  Fq12 a30 = a18 * a12;               // fx2^30
-  Fq12 b2 = fx.sqr();
-  Fq12 b6 = b2.sqr() * b2;            // fx^6
-  Fq12 b12 = b6.sqr();                // fx^12
-  Fq12 b18 = b12 * b6;                // fx^18
-  Fq12 c2 = fx3.sqr();
-  Fq12 c4 = c2.sqr();
-  Fq12 c8 = c4.sqr();
+  // small powers (everything here lives in the cyclotomic subgroup: Granger-Scott squarings)
+  Fq12 a2 = fx2.cyclotomic_sqr();                // fx2^2
+  Fq12 a6 = a2.cyclotomic_sqr() * a2;            // fx2^6
+  Fq12 a12 = a6.cyclotomic_sqr();                // fx2^12
+  Fq12 a18 = a12 * a6;                           // fx2^18
+  Fq12 a30 = a18 * a12;                          // fx2^30
+  Fq12 b2 = fx.cyclotomic_sqr();
+  Fq12 b6 = b2.cyclotomic_sqr() * b2;            // fx^6
+  Fq12 b12 = b6.cyclotomic_sqr();                // fx^12
+  Fq12 b18 = b12 * b6;                           // fx^18
+  Fq12 c2 = fx3.cyclotomic_sqr();
+  Fq12 c4 = c2.cyclotomic_sqr();
+  Fq12 c8 = c4.cyclotomic_sqr();
   Fq12 c9 = c8 * fx3;
-  Fq12 c18 = c9.sqr();
-  Fq12 c36 = c18.sqr();               // fx3^36
+  Fq12 c18 = c9.cyclotomic_sqr();
+  Fq12 c36 = c18.cyclotomic_sqr();               // fx3^36
   Fq12 e2 = a6 * f;                                   // f^(6x^2+1)
   Fq12 e1 = (c36 * a18 * b12).conj() * f;             // f^(-36x^3-18x^2-12x+1)
-  Fq12 e0 = (c36 * a30 * b18 * f.sqr()).conj();       // f^(-36x^3-30x^2-18x-2)
+  Fq12 e0 = (c36 * a30 * b18 * f.cyclotomic_sqr()).conj();  // f^(-36x^3-30x^2-18x-2)
   return fq12_frob3(f, k) * fq12_frob2(e2, k) * fq12_frob1(e1, k) * e0;
 }
 

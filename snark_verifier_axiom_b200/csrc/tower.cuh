@@ -100,6 +100,31 @@ struct Fq12 {
     return {t, ab + ab};
   }
   HD Fq12 conj() const { return {c0, c1.neg()}; }
+  // Granger-Scott squaring for elements of the cyclotomic subgroup (after the easy part of the final
+  // exponentiation): three Fq4 squarings = 9 Fq2 mul-equivalents = 18 Fq mul instead of 36.
+  // Fq4 = Fq2[y]/(y^2 - xi) pairs: (c0.c0, c1.c1), (c1.c0, c0.c2), (c0.c1, c1.c2).
+  HDN Fq12 cyclotomic_sqr() const {
+    const Fq2 &z0 = c0.c0, &z4 = c0.c1, &z3 = c0.c2, &z2 = c1.c0, &z1 = c1.c1, &z5 = c1.c2;
+    Fq2 tmp = z0 * z1;
+    Fq2 t0 = (z0 + z1) * (z1.mul_xi() + z0) - tmp - tmp.mul_xi();
+    Fq2 t1 = tmp.dbl();
+    tmp = z2 * z3;
+    Fq2 t2 = (z2 + z3) * (z3.mul_xi() + z2) - tmp - tmp.mul_xi();
+    Fq2 t3 = tmp.dbl();
+    tmp = z4 * z5;
+    Fq2 t4 = (z4 + z5) * (z5.mul_xi() + z4) - tmp - tmp.mul_xi();
+    Fq2 t5 = tmp.dbl();
+    Fq12 r;
+    // z0' = 3 t0 - 2 z0 ; z1' = 3 t1 + 2 z1 ; z2' = 3 xi t5 + 2 z2 ; z3' = 3 t4 - 2 z3 ; z4' = 3 t2 - 2 z4 ; z5' = 3 t3 + 2 z5
+    r.c0.c0 = (t0 - z0).dbl() + t0;
+    r.c1.c1 = (t1 + z1).dbl() + t1;
+    Fq2 x5 = t5.mul_xi();
+    r.c1.c0 = (x5 + z2).dbl() + x5;
+    r.c0.c2 = (t4 - z3).dbl() + t4;
+    r.c0.c1 = (t2 - z4).dbl() + t2;
+    r.c1.c2 = (t3 + z5).dbl() + t3;
+    return r;
+  }
   HDN Fq12 inv() const {
     Fq6 d = (c0.sqr() - c1.sqr().mul_v()).inv();
     return {c0 * d, (c1 * d).neg()};

@@ -169,3 +169,17 @@ int host_compile_run(const uint8_t* blob, size_t blob_len, int mos, const uint8_
   }
 }
 }
+
+extern "C" {
+// returns 1 if cyclotomic_sqr == sqr on an element of the cyclotomic subgroup built from random input limbs
+int host_cyclotomic_check(const u32* limbs96) {
+  static PairingConsts k = svk_host::make_pairing_consts();
+  Fq12 f;
+  Fq* p = reinterpret_cast<Fq*>(&f);
+  for (int i = 0; i < 12; i++) { memcpy(p[i].v, limbs96 + 8 * i, 32); p[i].v[7] &= 0x0fffffffu; p[i] = p[i].to_mont(); }
+  Fq12 t = f.conj() * f.inv();
+  Fq12 g = fq12_frob2(t, k) * t;  // in the cyclotomic subgroup
+  Fq12 a = g.sqr(), b = g.cyclotomic_sqr();
+  return (a == b) ? 1 : 0;
+}
+}
