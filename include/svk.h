@@ -40,6 +40,11 @@ enum {
 /* sub-codes stored in bits 8.. of a status word when the low byte is SVK_TRANSCRIPT */
 enum { SVK_T_EOF = 1, SVK_T_SCALAR_RANGE = 2, SVK_T_POINT_INVALID = 3, SVK_T_POINT_IDENTITY = 4 };
 
+/* Fiat-Shamir transcript of the proofs.  POSEIDON: `PoseidonTranscript` (system/halo2/transcript/halo2.rs:163-304; 32 B LE scalars,
+ * 32 B compressed points).  EVM: Keccak-256 `EvmTranscript` (system/halo2/transcript/evm.rs:152-243; 32 B BIG-endian scalars,
+ * 64 B uncompressed big-endian points) -- the format of `gen_evm_proof_*` / examples/evm-verifier.rs proofs. */
+enum { SVK_TRANSCRIPT_POSEIDON = 0, SVK_TRANSCRIPT_EVM = 1 };
+
 enum { SVK_MOS_BDFG21 = 0 /* SHPLONK, pcs/kzg/multiopen/bdfg21.rs */, SVK_MOS_GWC19 = 1 /* pcs/kzg/multiopen/gwc19.rs */ };
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -78,7 +83,8 @@ int svk_kzg_decide_batch_dev(svk_ctx* ctx, int dk, size_t n, const void* d_accs,
  * reference (protocol.rs:106-130, verifier/plonk.rs:58-92) is done once here.  `dk` supplies
  * `svk.g` (pcs/kzg.rs:21-37).  Returns a protocol id >= 0.  A protocol whose expressions the
  * reference would reject with Error::InvalidProtocol still compiles; its proofs get that status. */
-int svk_protocol_compile(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos, int dk);
+int svk_protocol_compile(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos, int dk); /* Poseidon transcript */
+int svk_protocol_compile_ex(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos, int transcript_kind, int dk);
 /* out[16] = { proof_len, n_instances, n_challenges, n_regs, n_ops, n_poseidon_perms, verify_valid,
  *             n_fr_mul, n_lhs_terms, n_rhs_terms, n_points, n_scalar_slots, msm_modmul_per_proof (all three MSM
  *             kernels), msm_var_modmul_per_proof (k_msm_var only), n_var_terms, var_lanes } */

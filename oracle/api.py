@@ -11,7 +11,7 @@ from . import bn254
 from .kzg import KzgAccumulator, KzgAsBdfg21, KzgAsGwc19
 from .loader import NativeLoader
 from .plonk import PlonkSuccinctVerifier, PlonkVerifier
-from .transcript import PoseidonTranscript, VerifyError
+from .transcript import PoseidonTranscript, VerifyError, make_transcript
 
 SCHEMES = {"bdfg21": KzgAsBdfg21, "gwc19": KzgAsGwc19}
 
@@ -19,7 +19,7 @@ SCHEMES = {"bdfg21": KzgAsBdfg21, "gwc19": KzgAsGwc19}
 STATUS = {"OK": 0, "InvalidInstances": 1, "InvalidProtocol": 2, "AssertionFailure": 3, "Transcript": 4}
 
 
-def succinct_verify(svk, protocol, instances, proof_bytes, scheme, loader=None, want_proof=False):
+def succinct_verify(svk, protocol, instances, proof_bytes, scheme, loader=None, want_proof=False, transcript="poseidon"):
     """-> (accumulators, PlonkProof).  Raises VerifyError like the reference returns Err."""
     loader = loader or NativeLoader()
     AS = SCHEMES[scheme]
@@ -28,18 +28,18 @@ def succinct_verify(svk, protocol, instances, proof_bytes, scheme, loader=None, 
     for col in instances:
         inst.append([loader.load_input(x, flat + j) for j, x in enumerate(col)])
         flat += len(col)
-    tr = PoseidonTranscript(loader, proof_bytes)
+    tr = make_transcript(transcript, loader, proof_bytes)
     proof = PlonkSuccinctVerifier.read_proof(svk, protocol, inst, tr, AS)
     accs = PlonkSuccinctVerifier.verify(svk, protocol, inst, proof, AS)
     return (accs, proof) if want_proof else accs
 
 
-def verify(dk, protocol, instances, proof_bytes, scheme):
+def verify(dk, protocol, instances, proof_bytes, scheme, transcript="poseidon"):
     """`PlonkVerifier::verify(...)`: returns None or raises VerifyError."""
     loader = NativeLoader()
     AS = SCHEMES[scheme]
     inst = [[loader.load_const(x) for x in col] for col in instances]
-    tr = PoseidonTranscript(loader, proof_bytes)
+    tr = make_transcript(transcript, loader, proof_bytes)
     proof = PlonkVerifier.read_proof(dk, protocol, inst, tr, AS)
     return PlonkVerifier.verify(dk, protocol, inst, proof, AS)
 

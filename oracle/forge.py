@@ -21,7 +21,7 @@ from .halo2_system import standard_plonk_protocol
 from .kzg import KzgAsBdfg21, KzgAsGwc19, KzgDecidingKey, gwc19_query_sets
 from .loader import EcPoint, NativeLoader
 from .plonk import CommonPolynomialEvaluation, PlonkProof
-from .transcript import PoseidonTranscript
+from .transcript import PoseidonTranscript, make_transcript
 
 # ---------------------------------------------------------------- fixed-base table for G (8-bit windows)
 _TABLE = None
@@ -103,9 +103,10 @@ def _msm_dlog(msm):
     return d
 
 
-def forge_proof(setup, scheme, seed):
+def forge_proof(setup, scheme, seed, transcript="poseidon"):
     """Returns (instances [[int]], proof bytes) accepted by PlonkVerifier<KzgAs<Bn256, scheme>>.
-    scheme in {"bdfg21", "gwc19"}."""
+    scheme in {"bdfg21", "gwc19"}; transcript "poseidon" (compressed LE points, LE scalars) or "evm"
+    (Keccak EvmTranscript: uncompressed BE points, BE scalars)."""
     rng = random.Random(("proof", seed).__repr__())
     protocol = setup.protocol
     AS = KzgAsBdfg21 if scheme == "bdfg21" else KzgAsGwc19
@@ -129,19 +130,27 @@ def forge_proof(setup, scheme, seed):
     else:
         opens = [bn254.G1_GEN] * n_open  # placeholders
 
+    def enc_pt(p):
+        if transcript == "poseidon":
+            return bn254.g1_to_bytes(p)
+        return int(p[0]).to_bytes(32, "big") + int(p[1]).to_bytes(32, "big")
+
+    def enc_fe(e):
+        return bn254.fe_to_bytes(e) if transcript == "poseidon" else int(e).to_bytes(32, "big")
+
     def assemble(open_pts):
         out = bytearray()
         for p in wit + quo:
-            out += bn254.g1_to_bytes(p)
+            out += enc_pt(p)
         for e in evals:
-            out += bn254.fe_to_bytes(e)
+            out += enc_fe(e)
         for p in open_pts:
-            out += bn254.g1_to_bytes(p)
+            out += enc_pt(p)
         return bytes(out)
 
     loader = DlogLoader(known)
     inst_loaded = [[loader.load_const(x) for x in col] for col in instances]
-    tr = PoseidonTranscript(loader, assemble(opens))
+    tr = make_transcript(transcript, loader, assemble(opens))
     proof = PlonkProof.read(setup.dk.svk, protocol, inst_loaded, tr, AS)
     for pt in proof.witnesses + proof.quotients:
         pt.dlog = known[pt.pt]
@@ -172,6 +181,6 @@ def forge_proof(setup, scheme, seed):
     return instances, assemble(opens)
 
 
-def forge_batch(setup, scheme, n, seed0=1):
-    out = [forge_proof(setup, scheme, seed0 + i) for i in range(n)]
+def forge_batch(setup, scheme, n, seed0=1, transcript="poseidon"):
+    out = [forge_proof(setup, scheme, seed0 + i, transcript) for i in range(n)]
     return [o[0] for o in out], [o[1] for o in out]

@@ -260,6 +260,8 @@ class TapeBuilder {
   std::vector<SsaOp> ops;
   std::vector<Fr> consts;
   int n_values = 0;
+  int transcript_kind = 0;  // 0 Poseidon (halo2.rs), 1 Keccak EvmTranscript (evm.rs)
+  size_t kbuf_len = 0;      // EvmTranscript: current length of `buf` in bytes (known statically)
   std::vector<Sym> tbuf;  // transcript buffer (Poseidon::buf)
   std::vector<PointRead> points;
   u32 cursor = 0;         // proof byte cursor
@@ -358,8 +360,28 @@ class TapeBuilder {
   }
 
   // ---- transcript (transcript/halo2.rs:198-261 over poseidon.rs:449-467)
-  void common_scalar(const Sym& s) { tbuf.push_back(s); }
+  void common_scalar(const Sym& s) {
+    if (transcript_kind == 1) {  // evm.rs:198-202
+      SsaOp o; o.op = T_KABSORB_REG; o.a = materialize(s);
+      ops.push_back(o);
+      kbuf_len += 32;
+      return;
+    }
+    tbuf.push_back(s);
+  }
+  void kabsorb_proof(u32 byte_offset) {
+    SsaOp o; o.op = T_KABSORB_PROOF; o.imm = byte_offset / 32;
+    ops.push_back(o);
+    kbuf_len += 32;
+  }
   Sym squeeze_challenge() {
+    if (transcript_kind == 1) {  // evm.rs:172-182
+      SsaOp q; q.op = T_KSQUEEZE; q.dst = new_value(); q.imm = kbuf_len == 32 ? 1 : 0;
+      ops.push_back(q);
+      kbuf_len = 32;
+      n_perm++;
+      return val(q.dst);
+    }
     std::vector<Sym> buf;
     buf.swap(tbuf);
     bool exact = buf.size() % SVK_POSEIDON_RATE == 0;
@@ -378,6 +400,13 @@ class TapeBuilder {
     return val(q.dst);
   }
   Sym read_scalar() {
+    if (transcript_kind == 1) {  // evm.rs:210-221: 32 B big-endian; the bytes read are the bytes absorbed
+      SsaOp o; o.op = T_READ_SCALAR_BE; o.dst = new_value(); o.imm = cursor / 32;
+      ops.push_back(o);
+      kabsorb_proof(cursor);
+      cursor += 32;
+      return val(o.dst);
+    }
     SsaOp o; o.op = T_READ_SCALAR; o.dst = new_value(); o.imm = cursor / 32;
     ops.push_back(o);
     cursor += 32;
@@ -386,6 +415,16 @@ class TapeBuilder {
     return s;
   }
   int read_ec_point() {  // returns the proof-point ordinal
+    if (transcript_kind == 1) {  // evm.rs:223-242: x || y, 64 B big-endian, validated by k_load_points_be
+      PointRead pr;
+      pr.byte_offset = cursor;
+      pr.val_x = pr.val_y = -1;
+      points.push_back(pr);
+      kabsorb_proof(cursor);
+      kabsorb_proof(cursor + 32);
+      cursor += 64;
+      return (int)points.size() - 1;
+    }
     PointRead pr;
     pr.byte_offset = cursor;
     pr.val_x = new_value();
@@ -475,6 +514,7 @@ struct SFraction {
 // ------------------------------------------------------------------ compiled output
 struct CompiledProtocol {
   int mos = 0;
+  int transcript_kind = 0;
   bool verify_valid = true;     // false => Error::InvalidProtocol for every proof that reads fine
   std::string invalid_reason;
   std::vector<TapeOp> ops;      // physical registers
@@ -507,7 +547,7 @@ class Compiler {
   TapeBuilder tb;
   std::vector<Sym> challenges_out;  // every squeezed challenge in order (for the ABI's out_challenges)
 
-  Compiler(const ProtocolDesc& p, int mos_) : P(p), mos(mos_) {}
+  Compiler(const ProtocolDesc& p, int mos_, int transcript_kind = 0) : P(p), mos(mos_) { tb.transcript_kind = transcript_kind; }
 
   Sym squeeze() {
     Sym s = tb.squeeze_challenge();
@@ -982,7 +1022,9 @@ class Compiler {
       auto& o = ops[i];
       switch (o.op) {
         case T_ADD: case T_SUB: case T_MUL: use(o.a, (int)i); use(o.b, (int)i); break;
-        case T_NEG: case T_ADDC: case T_SUBC: case T_CSUB: case T_MULC: case T_OUT_SCALAR: case T_OUT_CHALLENGE: use(o.a, (int)i); break;
+        case T_NEG: case T_ADDC: case T_SUBC: case T_CSUB: case T_MULC: case T_OUT_SCALAR: case T_OUT_CHALLENGE: case T_KABSORB_REG:
+          use(o.a, (int)i);
+          break;
         case T_PERM: if (o.imm >= 1) use(o.a, (int)i); if (o.imm >= 2) use(o.b, (int)i); break;
         case T_BINV: for (auto& pr : o.binv) use(pr.first, (int)i); break;
         default: break;
@@ -996,7 +1038,8 @@ class Compiler {
       return n_phys++;
     };
     // values written by the decompress kernel before the tape starts
-    for (auto& pr : tb.points) { phys[pr.val_x] = alloc(); phys[pr.val_y] = alloc(); }
+    for (auto& pr : tb.points)
+      if (pr.val_x >= 0) { phys[pr.val_x] = alloc(); phys[pr.val_y] = alloc(); }
     auto release_dead = [&](int v, int at) {
       if (v >= 0 && last_use[v] == at && phys[v] >= 0) { free_list.push_back(phys[v]); last_use[v] = -2; }
     };
@@ -1033,8 +1076,11 @@ class Compiler {
           out.n_fr_mul += 3 * o.binv.size() + 380;
           break;
         }
-        case T_READ_SCALAR: case T_INSTANCE:
+        case T_READ_SCALAR: case T_INSTANCE: case T_READ_SCALAR_BE:
           phys[o.dst] = alloc(); t.dst = P16(o.dst); t.a = (uint16_t)(o.imm & 0xffff); t.b = (uint16_t)(o.imm >> 16); break;
+        case T_KABSORB_REG: t.a = P16(o.a); release_dead(o.a, at); break;
+        case T_KABSORB_PROOF: t.a = (uint16_t)(o.imm & 0xffff); t.b = (uint16_t)(o.imm >> 16); break;
+        case T_KSQUEEZE: phys[o.dst] = alloc(); t.dst = P16(o.dst); t.a = (uint16_t)o.imm; break;
         case T_PERM:
           t.dst = (uint16_t)o.imm;
           if (o.imm >= 1) t.a = P16(o.a);
@@ -1059,15 +1105,19 @@ class Compiler {
     out.n_regs = (u32)n_phys;
     out.consts = tb.consts;
     out.points = tb.points;
-    for (auto& pr : out.points) { pr.val_x = phys[pr.val_x]; pr.val_y = phys[pr.val_y]; }
+    for (auto& pr : out.points)
+      if (pr.val_x >= 0) { pr.val_x = phys[pr.val_x]; pr.val_y = phys[pr.val_y]; }
   }
 };
 
-inline CompiledProtocol compile_protocol(const uint8_t* blob, size_t len, int mos) {
+inline CompiledProtocol compile_protocol(const uint8_t* blob, size_t len, int mos, int transcript_kind = 0) {
   if (mos != SVK_MOS_BDFG21 && mos != SVK_MOS_GWC19) throw CompileError(-1, "unknown multi-open scheme");
+  if (transcript_kind != 0 && transcript_kind != 1) throw CompileError(-1, "unknown transcript kind");
   ProtocolDesc p = parse_protocol(blob, len);
-  Compiler c(p, mos);
-  return c.run();
+  Compiler c(p, mos, transcript_kind);
+  CompiledProtocol out = c.run();
+  out.transcript_kind = transcript_kind;
+  return out;
 }
 
 }  // namespace svk_host

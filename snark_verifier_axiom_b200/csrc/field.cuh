@@ -210,6 +210,14 @@ struct Fe {
     for (int i = 0; i < 8; i++) r2.v[i] = P::r2(i);
     return (*this) * r2;
   }
+  // to_mont of ANY 256-bit value (value mod p, not necessarily canonical on input): R^2 goes first because the
+  // multiplier's carry bound needs its FIRST operand < p; the running sum then stays < R^2-operand + p < 2p.
+  HD Fe to_mont_wide() const {
+    Fe r2;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r2.v[i] = P::r2(i);
+    return r2 * (*this);
+  }
   HD Fe from_mont() const {
     Fe o = zero();
     o.v[0] = 1;

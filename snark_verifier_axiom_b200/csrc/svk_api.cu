@@ -234,17 +234,23 @@ int svk_kzg_decide_batch(svk_ctx* ctx, int dk, size_t n, const svk_acc* accs, ui
 }
 
 // ---- PlonkProtocol ingestion --------------------------------------------------------------------
+int svk_protocol_compile_ex(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos, int transcript_kind, int dk);
 int svk_protocol_compile(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos, int dk) {
+  return svk_protocol_compile_ex(ctx, blob, len, mos, SVK_TRANSCRIPT_POSEIDON, dk);
+}
+
+int svk_protocol_compile_ex(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos, int transcript_kind, int dk) {
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   if (dk < 0 || dk >= (int)ctx->dks.size()) return svk_fail(ctx, "bad deciding-key id %d", dk);
   svk_host::CompiledProtocol cp;
   try {
-    cp = svk_host::compile_protocol(blob, len, mos);
+    cp = svk_host::compile_protocol(blob, len, mos, transcript_kind);
   } catch (svk_host::CompileError& e) {
     return svk_fail(ctx, "protocol compile: %s", e.what());
   }
   ProtocolDevice* pd = new ProtocolDevice();
   pd->mos = mos;
+  pd->transcript_kind = transcript_kind;
   pd->dk = dk;
   pd->verify_valid = cp.verify_valid;
   pd->invalid_reason = cp.invalid_reason;
@@ -259,7 +265,7 @@ int svk_protocol_compile(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos,
   pd->n_fr_mul = cp.n_fr_mul;
   pd->num_instance = cp.num_instance;
   pd->n_pre = (u32)cp.preprocessed.size();
-  for (auto& p : cp.points) pd->points.push_back({p.byte_offset, (u32)p.val_x, (u32)p.val_y});
+  for (auto& p : cp.points) pd->points.push_back({p.byte_offset, (u32)(p.val_x < 0 ? 0 : p.val_x), (u32)(p.val_y < 0 ? 0 : p.val_y)});
   std::vector<G1Affine> fixed;
   for (auto& g : cp.preprocessed) {
     G1Affine a = G1Affine::identity();

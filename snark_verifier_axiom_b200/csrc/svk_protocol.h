@@ -39,6 +39,7 @@ struct FixedSlot {
 
 struct ProtocolDevice {
   int mos = 0;
+  int transcript_kind = 0;  // 0 Poseidon, 1 Keccak EvmTranscript
   bool verify_valid = true;
   std::string invalid_reason;
   TapeOp* d_ops = nullptr;

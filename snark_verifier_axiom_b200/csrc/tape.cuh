@@ -12,6 +12,7 @@
 //   Bdfg21::verify / Gwc19::verify        snark-verifier/src/pcs/kzg/multiopen/{bdfg21.rs:47-79,gwc19.rs:43-80}
 // up to (not including) the final group arithmetic, which is the per-proof MSM kernel (proof_msm.cu).
 #pragma once
+#include "keccak.cuh"
 #include "poseidon.cuh"
 
 enum TapeOpCode : uint16_t {
@@ -32,6 +33,11 @@ enum TapeOpCode : uint16_t {
   T_RESET,          // sponge state = default
   T_OUT_SCALAR,     // msm_scalar[dst] = canonical(reg[a])
   T_OUT_CHALLENGE,  // challenge[dst] = canonical(reg[a])
+  // ---- Keccak `EvmTranscript` (transcript/evm.rs:152-243); only emitted for transcript kind 1
+  T_READ_SCALAR_BE, // reg[dst] = proof scalar, 32 B BIG-endian, at byte offset 32*(a | b<<16)
+  T_KABSORB_REG,    // buf.extend(canonical(reg[a]) as 32 B big-endian)
+  T_KABSORB_PROOF,  // buf.extend(proof[32*(a | b<<16) .. +32])   (a scalar or half of an uncompressed point, as read)
+  T_KSQUEEZE,       // hash = keccak256(buf || [1 if a]); buf = hash; reg[dst] = hash (big-endian) mod r
   T_N_OPS
 };
 
@@ -79,10 +85,23 @@ struct TapeIo {
 
 #define SVK_BINV_MAX 48
 
+// Transcript state of one proof.  KECCAK selects the member that exists at compile time, so the Poseidon kernel
+// does not carry the 25-lane Keccak state.
+template <bool KECCAK>
+struct TranscriptState;
+template <>
+struct TranscriptState<false> {
+  PoseidonState ps;
+};
+template <>
+struct TranscriptState<true> {
+  KeccakSponge ks;
+};
+
 // Executes ops [begin, end) for one item.  Sponge state persists in `st` across calls.
-template <class Regs>
+template <bool KECCAK, class Regs>
 HD void tape_exec(const TapeOp* ops, u32 begin, u32 end, const uint16_t* aux, const Fr* consts, const PoseidonConsts& pk,
-                  const Regs& regs, const TapeIo& io, PoseidonState& st, u32& err) {
+                  const Regs& regs, const TapeIo& io, TranscriptState<KECCAK>& st, u32& err) {
   for (u32 pc = begin; pc < end; pc++) {
     TapeOp op = ops[pc];
     switch (op.op) {
@@ -147,15 +166,68 @@ HD void tape_exec(const TapeOp* ops, u32 begin, u32 end, const uint16_t* aux, co
         regs.store(op.dst, x.to_mont());
         break;
       }
-      case T_PERM: {
-        Fr in0 = Fr::zero(), in1 = Fr::zero();
-        if (op.dst >= 1) in0 = regs.load(op.a);
-        if (op.dst >= 2) in1 = regs.load(op.b);
-        poseidon_permute(st, pk, op.dst, in0, in1);
+      case T_PERM:
+        if constexpr (!KECCAK) {
+          Fr in0 = Fr::zero(), in1 = Fr::zero();
+          if (op.dst >= 1) in0 = regs.load(op.a);
+          if (op.dst >= 2) in1 = regs.load(op.b);
+          poseidon_permute(st.ps, pk, op.dst, in0, in1);
+        }
         break;
-      }
-      case T_SQUEEZE: regs.store(op.dst, st.s[1]); break;
-      case T_RESET: poseidon_init(st, pk); break;
+      case T_SQUEEZE:
+        if constexpr (!KECCAK) regs.store(op.dst, st.ps.s[1]);
+        break;
+      case T_RESET:
+        if constexpr (!KECCAK) poseidon_init(st.ps, pk);
+        else keccak_reset(st.ks);
+        break;
+      case T_READ_SCALAR_BE:
+        if constexpr (KECCAK) {
+          u32 off = 32u * ((u32)op.a | ((u32)op.b << 16));
+          Fr x = Fr::zero();
+          if (off + 32 > io.proof_len) {
+            tape_note_error(err, off, SVK_T_EOF);
+          } else {
+            const uint8_t* p = io.proof + off;
+            for (int i = 0; i < 8; i++) {
+              const uint8_t* q = p + 4 * (7 - i);
+              x.v[i] = ((u32)q[0] << 24) | ((u32)q[1] << 16) | ((u32)q[2] << 8) | (u32)q[3];
+            }
+            if (!Fr::is_canonical(x.v)) {
+              tape_note_error(err, off, SVK_T_SCALAR_RANGE);
+              x = Fr::zero();
+            }
+          }
+          regs.store(op.dst, x.to_mont());
+        }
+        break;
+      case T_KABSORB_REG:
+        if constexpr (KECCAK) {
+          Fr x = regs.load(op.a).from_mont();
+          keccak_absorb_limbs_be(st.ks, x.v);
+        }
+        break;
+      case T_KABSORB_PROOF:
+        if constexpr (KECCAK) {
+          u32 off = 32u * ((u32)op.a | ((u32)op.b << 16));
+          if (off + 32 <= io.proof_len) keccak_absorb(st.ks, io.proof + off, 32);
+        }
+        break;
+      case T_KSQUEEZE:
+        if constexpr (KECCAK) {
+          if (op.a) keccak_absorb_byte(st.ks, 1);
+          uint8_t h[32];
+          keccak_finish(st.ks, h);
+          keccak_absorb(st.ks, h, 32);  // buf = hash
+          Fr x;
+          for (int i = 0; i < 8; i++) {
+            const uint8_t* q = h + 4 * (7 - i);
+            x.v[i] = ((u32)q[0] << 24) | ((u32)q[1] << 16) | ((u32)q[2] << 8) | (u32)q[3];
+          }
+          // u256_to_fe: value mod r.  (R^2 * x + m r) / 2^256 < 2r for any 256-bit x, reduced once by the multiplier
+          regs.store(op.dst, x.to_mont_wide());
+        }
+        break;
       case T_OUT_SCALAR: {
         Fr x = regs.load(op.a).from_mont();
         RegFile o{io.out_scalars, regs.n_items, regs.item};

@@ -43,7 +43,42 @@ __global__ void __launch_bounds__(128) k_decompress(size_t n_items, u32 n_points
   pts[(size_t)pi * n_items + item] = pt;
 }
 
+// Uncompressed points of the Keccak `EvmTranscript` (transcript/evm.rs:223-242): x || y, 32 B big-endian each,
+// both < p, on the curve; (0, 0) decodes to the identity, which `common_ec_point` rejects (evm.rs:184-196).
+__global__ void __launch_bounds__(128) k_load_points_be(size_t n_items, u32 n_points, const PointSched* sched, const uint8_t* proofs,
+                                                        size_t proof_stride, const u32* proof_lens, G1Affine* pts, u32* err) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_items * n_points) return;
+  size_t item = idx % n_items;
+  u32 pi = (u32)(idx / n_items);
+  PointSched s = sched[pi];
+  u32 len = proof_lens ? proof_lens[item] : (u32)proof_stride;
+  G1Affine pt = G1Affine::identity();
+  if (s.byte_offset + 64 > len) {
+    atomicMin(&err[item], (s.byte_offset << 8) | SVK_T_EOF);
+  } else {
+    const uint8_t* p = proofs + item * proof_stride + s.byte_offset;
+    Fq x, y;
+    for (int i = 0; i < 8; i++) {
+      const uint8_t* q = p + 4 * (7 - i);
+      x.v[i] = ((u32)q[0] << 24) | ((u32)q[1] << 16) | ((u32)q[2] << 8) | (u32)q[3];
+      q += 32;
+      y.v[i] = ((u32)q[0] << 24) | ((u32)q[1] << 16) | ((u32)q[2] << 8) | (u32)q[3];
+    }
+    bool canon = Fq::is_canonical(x.v) && Fq::is_canonical(y.v);
+    if (canon && x.is_zero() && y.is_zero()) {
+      atomicMin(&err[item], (s.byte_offset << 8) | SVK_T_POINT_IDENTITY);
+    } else {
+      G1Affine c{x.to_mont(), y.to_mont()};
+      if (!canon || !g1_on_curve(c)) atomicMin(&err[item], (s.byte_offset << 8) | SVK_T_POINT_INVALID);
+      else pt = c;
+    }
+  }
+  pts[(size_t)pi * n_items + item] = pt;
+}
+
 // ------------------------------------------------------------------------------------------------
+template <bool KECCAK>
 __global__ void __launch_bounds__(32) k_tape(size_t n_items, const TapeOp* ops, u32 n_ops, const uint16_t* aux, const Fr* consts,
                                              const PoseidonConsts* pk, u32* regs, const uint8_t* proofs, size_t proof_stride,
                                              const u32* proof_lens, const uint8_t* instances, u32 n_instances, u32* out_scalars,
@@ -59,10 +94,11 @@ __global__ void __launch_bounds__(32) k_tape(size_t n_items, const TapeOp* ops, 
   io.out_scalars = out_scalars;
   io.out_challenges = out_challenges;
   io.n_challenge_slots = n_challenges;
-  PoseidonState st;
-  poseidon_init(st, *pk);
+  TranscriptState<KECCAK> st;
+  if constexpr (KECCAK) keccak_reset(st.ks);
+  else poseidon_init(st.ps, *pk);
   u32 e = SVK_NO_ERR;
-  tape_exec(ops, 0, n_ops, aux, consts, *pk, rf, io, st, e);
+  tape_exec<KECCAK>(ops, 0, n_ops, aux, consts, *pk, rf, io, st, e);
   if (e != SVK_NO_ERR) atomicMin(&err[item], e);
 }
 
@@ -307,15 +343,26 @@ int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const
   if (mode != 1) {
     if (n_pts) {
       size_t total = n * n_pts;
-      SVK_LAUNCH(ctx, "k_decompress",
-                 k_decompress<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(n, (u32)n_pts, pd->d_sched, d_proofs, proof_stride, d_proof_lens,
-                                                                             d_regs, d_pts, d_err));
+      if (pd->transcript_kind == 1)
+        SVK_LAUNCH(ctx, "k_load_points_be",
+                   k_load_points_be<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(n, (u32)n_pts, pd->d_sched, d_proofs, proof_stride,
+                                                                                   d_proof_lens, d_pts, d_err));
+      else
+        SVK_LAUNCH(ctx, "k_decompress",
+                   k_decompress<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(n, (u32)n_pts, pd->d_sched, d_proofs, proof_stride, d_proof_lens,
+                                                                               d_regs, d_pts, d_err));
     }
     u32 n_ops = pd->verify_valid ? pd->n_ops : pd->read_ops_end;
-    SVK_LAUNCH(ctx, "k_tape",
-               k_tape<<<(unsigned)((n + 31) / 32), 32, 0, s>>>(n, pd->d_ops, n_ops, pd->d_aux, pd->d_consts, ctx->d_poseidon, d_regs, d_proofs,
-                                                              proof_stride, d_proof_lens, d_instances, pd->n_instances, d_scalars,
-                                                              d_out_challenges, pd->n_challenges, d_err));
+    if (pd->transcript_kind == 1)
+      SVK_LAUNCH(ctx, "k_tape_keccak",
+                 k_tape<true><<<(unsigned)((n + 31) / 32), 32, 0, s>>>(n, pd->d_ops, n_ops, pd->d_aux, pd->d_consts, ctx->d_poseidon, d_regs,
+                                                                      d_proofs, proof_stride, d_proof_lens, d_instances, pd->n_instances,
+                                                                      d_scalars, d_out_challenges, pd->n_challenges, d_err));
+    else
+      SVK_LAUNCH(ctx, "k_tape",
+                 k_tape<false><<<(unsigned)((n + 31) / 32), 32, 0, s>>>(n, pd->d_ops, n_ops, pd->d_aux, pd->d_consts, ctx->d_poseidon, d_regs,
+                                                                       d_proofs, proof_stride, d_proof_lens, d_instances, pd->n_instances,
+                                                                       d_scalars, d_out_challenges, pd->n_challenges, d_err));
   }
   if (mode == 0) {
     G1Jac *d_partials, *d_sums, *d_tables;

@@ -22,6 +22,8 @@ from .protocol import PlonkProtocol
 
 SHPLONK = BDFG21 = 0
 GWC = GWC19 = 1
+POSEIDON_TRANSCRIPT = 0  # sdk `PoseidonTranscript` (snark-verifier-sdk/src/halo2.rs:58-67)
+EVM_TRANSCRIPT = 1       # Keccak `EvmTranscript` (snark-verifier/src/system/halo2/transcript/evm.rs)
 
 STATUS_NAMES = {0: "Ok", 1: "InvalidInstances", 2: "InvalidProtocol", 3: "AssertionFailure", 4: "Transcript"}
 
@@ -138,9 +140,9 @@ class Context:
     def load_deciding_key(self, dk: KzgDecidingKey) -> int:
         return self._check(self._L.svk_dk_load(self._c, dk.to_bytes()))
 
-    def compile_protocol(self, protocol: PlonkProtocol, mos: int, dk_id: int) -> int:
+    def compile_protocol(self, protocol: PlonkProtocol, mos: int, dk_id: int, transcript: int = 0) -> int:
         blob = protocol.to_bytes()
-        return self._check(self._L.svk_protocol_compile(self._c, blob, len(blob), mos, dk_id))
+        return self._check(self._L.svk_protocol_compile_ex(self._c, blob, len(blob), mos, transcript, dk_id))
 
     def protocol_info(self, pid: int) -> dict:
         out = (ctypes.c_uint32 * 16)()
@@ -211,11 +213,13 @@ class BatchResult:
 class PlonkVerifier:
     """`PlonkVerifier<KzgAs<Bn256, MOS>>` / `PlonkSuccinctVerifier<..>` for ONE protocol, over batches."""
 
-    def __init__(self, ctx: Context, dk: KzgDecidingKey, protocol: PlonkProtocol, mos: int = SHPLONK, kzg_as: Optional[KzgAs] = None):
+    def __init__(self, ctx: Context, dk: KzgDecidingKey, protocol: PlonkProtocol, mos: int = SHPLONK, kzg_as: Optional[KzgAs] = None,
+                 transcript: int = POSEIDON_TRANSCRIPT):
         self.ctx = ctx
         self.kzg_as = kzg_as or KzgAs(ctx, dk)
         self.mos = mos
-        self.pid = ctx.compile_protocol(protocol, mos, self.kzg_as.dk_id)
+        self.transcript = transcript
+        self.pid = ctx.compile_protocol(protocol, mos, self.kzg_as.dk_id, transcript)
         self.info = ctx.protocol_info(self.pid)
         self.protocol = protocol
 

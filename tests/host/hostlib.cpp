@@ -14,7 +14,7 @@ void host_fe_op(int field, int op, const u32* a, const u32* b, u32* out) {
     switch (op) {
       case 0: r = x * y; break; case 1: r = x + y; break; case 2: r = x - y; break; case 3: r = x.neg(); break;
       case 4: r = x.inv(); break; case 5: r = x.sqrt_candidate(); break; case 6: r = x.to_mont(); break;
-      case 7: r = x.from_mont(); break; case 8: r = x.sqr(); break; default: r = x.dbl(); break;
+      case 7: r = x.from_mont(); break; case 8: r = x.sqr(); break; case 10: r = x.to_mont_wide(); break; default: r = x.dbl(); break;
     }
     memcpy(out, r.v, 32);
   } else {
@@ -23,7 +23,7 @@ void host_fe_op(int field, int op, const u32* a, const u32* b, u32* out) {
     switch (op) {
       case 0: r = x * y; break; case 1: r = x + y; break; case 2: r = x - y; break; case 3: r = x.neg(); break;
       case 4: r = x.inv(); break; case 5: r = x.sqrt_candidate(); break; case 6: r = x.to_mont(); break;
-      case 7: r = x.from_mont(); break; case 8: r = x.sqr(); break; default: r = x.dbl(); break;
+      case 7: r = x.from_mont(); break; case 8: r = x.sqr(); break; case 10: r = x.to_mont_wide(); break; default: r = x.dbl(); break;
     }
     memcpy(out, r.v, 32);
   }
@@ -121,17 +121,27 @@ extern "C" {
 // Compile + run the tape for ONE proof on the host (same code the kernels run).
 // terms_out: per term 3 ints (which: 0 lhs / 1 rhs, base id, slot); returns #terms or <0.
 // info_out: [n_regs, n_ops, n_perm, n_challenges, n_scalar_slots, proof_len, err_word, verify_valid, n_fr_mul, n_points]
+int host_compile_run_ex(const uint8_t* blob, size_t blob_len, int mos, int transcript_kind, const uint8_t* proof, u32 proof_len,
+                        const uint8_t* instances, u32 n_instances, u32* challenges_out, u32* scalars_out,
+                        int* terms_out, int max_terms, long long* info_out, char* errbuf, int errbuf_len);
 int host_compile_run(const uint8_t* blob, size_t blob_len, int mos, const uint8_t* proof, u32 proof_len,
                      const uint8_t* instances, u32 n_instances, u32* challenges_out, u32* scalars_out,
                      int* terms_out, int max_terms, long long* info_out, char* errbuf, int errbuf_len) {
+  return host_compile_run_ex(blob, blob_len, mos, 0, proof, proof_len, instances, n_instances, challenges_out, scalars_out, terms_out,
+                             max_terms, info_out, errbuf, errbuf_len);
+}
+int host_compile_run_ex(const uint8_t* blob, size_t blob_len, int mos, int transcript_kind, const uint8_t* proof, u32 proof_len,
+                        const uint8_t* instances, u32 n_instances, u32* challenges_out, u32* scalars_out,
+                        int* terms_out, int max_terms, long long* info_out, char* errbuf, int errbuf_len) {
   static PoseidonConsts pk;
   static bool init = false;
   if (!init) { svk_host::make_poseidon_consts(pk); init = true; }
   try {
-    svk_host::CompiledProtocol cp = svk_host::compile_protocol(blob, blob_len, mos);
+    svk_host::CompiledProtocol cp = svk_host::compile_protocol(blob, blob_len, mos, transcript_kind);
     std::vector<u32> regs((size_t)cp.n_regs * 8 + 8, 0);
     u32 err = SVK_NO_ERR;
     for (auto& pr : cp.points) {
+      if (transcript_kind == 1) continue;  // uncompressed points: validated by k_load_points_be on the device, absorbed from the proof bytes
       G1Affine pt; u32 xc[8], yc[8];
       Fr fx = Fr::zero(), fy = Fr::zero();
       if (pr.byte_offset + 32 > proof_len) tape_note_error(err, pr.byte_offset, SVK_T_EOF);
@@ -149,10 +159,16 @@ int host_compile_run(const uint8_t* blob, size_t blob_len, int mos, const uint8_
     }
     RegFile rf{regs.data(), 1, 0};
     TapeIo io{proof, proof_len, instances, n_instances, scalars_out, challenges_out, cp.n_challenges};
-    PoseidonState st;
-    poseidon_init(st, pk);
     u32 end = cp.verify_valid ? (u32)cp.ops.size() : cp.read_ops_end;
-    tape_exec(cp.ops.data(), 0, end, cp.aux.data(), cp.consts.data(), pk, rf, io, st, err);
+    if (transcript_kind == 1) {
+      TranscriptState<true> st;
+      keccak_reset(st.ks);
+      tape_exec<true>(cp.ops.data(), 0, end, cp.aux.data(), cp.consts.data(), pk, rf, io, st, err);
+    } else {
+      TranscriptState<false> st;
+      poseidon_init(st.ps, pk);
+      tape_exec<false>(cp.ops.data(), 0, end, cp.aux.data(), cp.consts.data(), pk, rf, io, st, err);
+    }
     int nt = 0;
     for (int which = 0; which < 2; which++)
       for (auto& t : (which ? cp.rhs : cp.lhs)) {
@@ -181,5 +197,12 @@ int host_cyclotomic_check(const u32* limbs96) {
   Fq12 g = fq12_frob2(t, k) * t;  // in the cyclotomic subgroup
   Fq12 a = g.sqr(), b = g.cyclotomic_sqr();
   return (a == b) ? 1 : 0;
+}
+}
+
+#include "../../snark_verifier_axiom_b200/csrc/keccak.cuh"
+extern "C" {
+void host_keccak256(const uint8_t* data, u32 n, uint8_t* out) {
+  KeccakSponge k; keccak_reset(k); keccak_absorb(k, data, n); keccak_finish(k, out);
 }
 }

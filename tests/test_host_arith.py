@@ -66,6 +66,10 @@ def test_field_ops(lib):
         for a in vals[:12]:
             assert op(f, 4, a * Rm % m) == (pow(a, -1, m) * Rm % m if a else 0)
         assert lib.host_is_canonical(f, limbs([m - 1])) == 1 and lib.host_is_canonical(f, limbs([m])) == 0
+        # to_mont_wide: any 256-bit input (the Keccak challenge, evm.rs:172-182 `u256_to_fe`), worst cases included
+        wide = [(1 << 256) - 1, (1 << 256) - 2, 0xFFFFFFFF << 224, m, 2 * m, 5 * m + 3, (1 << 255) + 12345]
+        for a in wide + [rng.randrange(1 << 256) for _ in range(200)]:
+            assert op(f, 10, a) == a * Rm % m
     for a in [rng.randrange(P) for _ in range(8)]:
         Rm = (1 << 256) % P
         assert op(0, 5, a * Rm % P) == pow(a, (P + 1) // 4, P) * Rm % P
@@ -164,3 +168,30 @@ def test_compiler_and_tape(lib, scheme, mos):
     assert info[6] == ((9 * 32) << 8 | 2)
     lib.host_compile_run(blob, len(blob), mos, pf, 100, instb, 1, ch, sc, terms, 100, info, err, 256)
     assert info[6] & 0xFF == 1
+
+
+@pytest.mark.parametrize("scheme,mos", [("bdfg21", 0), ("gwc19", 1)])
+def test_compiler_and_tape_evm_transcript(lib, scheme, mos):
+    """Keccak `EvmTranscript` tape (transcript/evm.rs:152-243): challenges equal the oracle's; Keccak itself vs the
+    Python restatement on multi-block inputs."""
+    from oracle.keccak import keccak256
+
+    rng = random.Random(9)
+    for n in [0, 1, 31, 32, 33, 135, 136, 137, 500]:
+        d = bytes(rng.getrandbits(8) for _ in range(n))
+        out = ctypes.create_string_buffer(32)
+        lib.host_keccak256(d, n, out)
+        assert out.raw == keccak256(d)
+    assert keccak256(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"  # public Keccak-256 KAT
+    S = forge.Setup(0)
+    blob = to_product_protocol(S.protocol).to_bytes()
+    inst, pf = forge.forge_proof(S, scheme, 9, transcript="evm")
+    accs, proof = api.succinct_verify(S.dk.svk, S.protocol, inst, pf, scheme, want_proof=True, transcript="evm")
+    ch, sc = (ctypes.c_uint32 * (8 * 32))(), (ctypes.c_uint32 * (8 * 64))()
+    terms, info, err = (ctypes.c_int * 300)(), (ctypes.c_longlong * 10)(), ctypes.create_string_buffer(256)
+    instb = b"".join(int(x).to_bytes(32, "little") for col in inst for x in col)
+    nt = lib.host_compile_run_ex(blob, len(blob), mos, 1, pf, len(pf), instb, 1, ch, sc, terms, 100, info, err, 256)
+    assert nt > 0, err.value
+    exp = [c.v for c in proof.challenges] + [proof.z.v]
+    exp += [proof.pcs.mu.v, proof.pcs.gamma.v, proof.pcs.z_prime.v] if scheme == "bdfg21" else [proof.pcs.v.v, proof.pcs.u.v]
+    assert rd(ch, info[3]) == exp and info[5] == len(pf) and info[6] == 0xFFFFFFFF

@@ -14,6 +14,19 @@ def test_constants():
     assert B.g2_mul(B.G2_GEN, B.R) is None and B.g1_mul(B.G1_GEN, B.R - 1) == B.g1_neg(B.G1_GEN)
 
 
+def test_public_known_answers():
+    """Values that are public knowledge about alt_bn128 / BN254 (EIP-196/197 precompile documentation): they pin the
+    curve equation, the generator and the group law of the restatement independently of this repository."""
+    two_g = (1368015179489954701390400359078579693043519447331113978918064868415326638035,
+             9918110051302171585080402603319702774565515993150576347155970296011118125764)
+    assert B.g1_mul(B.G1_GEN, 2) == two_g and B.g1_add(B.G1_GEN, B.G1_GEN) == two_g
+    assert B.P == 21888242871839275222246405745257275088696311157297823662689037894645226208583
+    assert B.R == 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    # EIP-197 G2 generator (x = x_c0 + x_c1 u as listed there: imaginary part first in the ABI)
+    assert B.G2_GEN[0][1] == 11559732032986387107991004021392285783925812861821192530917403151452391805634
+    assert B.G2_GEN[0][0] == 10857046999023057135944570762232829481370756359578518086990519993285655852781
+
+
 def test_g1_encoding_roundtrip():
     rng = random.Random(1)
     for _ in range(20):
