@@ -16,7 +16,10 @@ __device__ __forceinline__ G1Affine load_g1_canon(const uint8_t* p) {
 
 // status: bit0 = accept.  A point that is not a canonical on-curve encoding makes the reference's
 // `G1Affine` unconstructible; such accumulators are reported as reject.
-__global__ void __launch_bounds__(64) k_decide(size_t n, const uint8_t* accs, size_t acc_stride, uint8_t* out_ok, size_t ok_stride,
+#ifndef SVK_DECIDE_MINBLOCKS
+#define SVK_DECIDE_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(64, SVK_DECIDE_MINBLOCKS) k_decide(size_t n, const uint8_t* accs, size_t acc_stride, uint8_t* out_ok, size_t ok_stride,
                                                const G2Line* t_g2, const G2Line* t_neg_sg2, const PairingConsts* consts) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

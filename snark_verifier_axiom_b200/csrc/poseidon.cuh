@@ -4,7 +4,9 @@
 // `PoseidonConsts` is the device image of `OptimizedPoseidonSpec` (poseidon.rs:59-95), built on the
 // host by poseidon_host.h (Grain LFSR + sparse-MDS factorisation) for the SDK parameters
 // R_F = 8, R_P = 57 (snark-verifier-sdk/src/halo2.rs:52-56).  All values in Montgomery form.
-// Cost: 8 full rounds x (3 x 3 + 9) + 57 partial rounds x (3 + 5) = 600 Fr multiplications.
+// Cost: 8 full rounds x (3 x 3 + 9) + 57 partial rounds x (3 + 5) = 600 Fr multiplications in the textbook count; every
+// MDS row is ONE fused 3-term dot product (field.cuh `dot3`: 3 limb products, 1 reduction, no additions), which is
+// value-identical and brings the permutation to ~510 multiplication-equivalents of integer-pipe work.
 #pragma once
 #include "field.cuh"
 
@@ -35,9 +37,9 @@ HD Fr fr_pow5(const Fr& x) {
 }
 
 HD void poseidon_mds(PoseidonState& st, const Fr (*m)[3]) {
-  Fr r0 = m[0][0] * st.s[0] + m[0][1] * st.s[1] + m[0][2] * st.s[2];
-  Fr r1 = m[1][0] * st.s[0] + m[1][1] * st.s[1] + m[1][2] * st.s[2];
-  Fr r2 = m[2][0] * st.s[0] + m[2][1] * st.s[1] + m[2][2] * st.s[2];
+  Fr r0 = Fr::dot3(m[0][0], st.s[0], m[0][1], st.s[1], m[0][2], st.s[2]);
+  Fr r1 = Fr::dot3(m[1][0], st.s[0], m[1][1], st.s[1], m[1][2], st.s[2]);
+  Fr r2 = Fr::dot3(m[2][0], st.s[0], m[2][1], st.s[1], m[2][2], st.s[2]);
   st.s[0] = r0;
   st.s[1] = r1;
   st.s[2] = r2;
@@ -68,7 +70,7 @@ HDN void poseidon_permute(PoseidonState& st, const PoseidonConsts& k, int n_in, 
   // partial rounds with sparse MDS (poseidon.rs:398-410)
   for (int r = 0; r < SVK_POSEIDON_RP; r++) {
     st.s[0] = fr_pow5(st.s[0]) + k.partial[r];
-    Fr n0 = k.sparse_row[r][0] * st.s[0] + k.sparse_row[r][1] * st.s[1] + k.sparse_row[r][2] * st.s[2];
+    Fr n0 = Fr::dot3(k.sparse_row[r][0], st.s[0], k.sparse_row[r][1], st.s[1], k.sparse_row[r][2], st.s[2]);
     Fr n1 = k.sparse_col_hat[r][0] * st.s[0] + st.s[1];
     Fr n2 = k.sparse_col_hat[r][1] * st.s[0] + st.s[2];
     st.s[0] = n0;

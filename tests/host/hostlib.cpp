@@ -28,6 +28,20 @@ void host_fe_op(int field, int op, const u32* a, const u32* b, u32* out) {
     memcpy(out, r.v, 32);
   }
 }
+// out = sum_k a[k] * b[k] * R^-1 mod p through the fused dot product (n = 2 or 3); `neg_mask` bit k replaces a[k] by p - a[k]
+void host_fe_dot(int field, int n, int neg_mask, const u32* a, const u32* b, u32* out) {
+  if (field == 0) {
+    Fq x[3], y[3];
+    for (int k = 0; k < n; k++) { memcpy(x[k].v, a + 8 * k, 32); memcpy(y[k].v, b + 8 * k, 32); if (neg_mask >> k & 1) x[k] = x[k].neg_lazy(); }
+    Fq r = n == 2 ? Fq::dot2(x[0], y[0], x[1], y[1]) : Fq::dot3(x[0], y[0], x[1], y[1], x[2], y[2]);
+    memcpy(out, r.v, 32);
+  } else {
+    Fr x[3], y[3];
+    for (int k = 0; k < n; k++) { memcpy(x[k].v, a + 8 * k, 32); memcpy(y[k].v, b + 8 * k, 32); if (neg_mask >> k & 1) x[k] = x[k].neg_lazy(); }
+    Fr r = n == 2 ? Fr::dot2(x[0], y[0], x[1], y[1]) : Fr::dot3(x[0], y[0], x[1], y[1], x[2], y[2]);
+    memcpy(out, r.v, 32);
+  }
+}
 int host_is_canonical(int field, const u32* a) { return field == 0 ? Fq::is_canonical(a) : Fr::is_canonical(a); }
 }
 

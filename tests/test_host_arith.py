@@ -70,6 +70,20 @@ def test_field_ops(lib):
         wide = [(1 << 256) - 1, (1 << 256) - 2, 0xFFFFFFFF << 224, m, 2 * m, 5 * m + 3, (1 << 255) + 12345]
         for a in wide + [rng.randrange(1 << 256) for _ in range(200)]:
             assert op(f, 10, a) == a * Rm % m
+    # fused dot products (lazy reduction): operands up to p itself, optional p - a operands
+    for f, m in ((0, P), (1, R)):
+        Ri = pow(1 << 256, -1, m)
+        edge = [0, 1, m - 1, m, m - 2, (1 << 253) + 5]
+        for n in (2, 3):
+            for trial in range(300):
+                src = edge if trial < 40 else None
+                a = [rng.choice(src) if src else rng.randrange(m) for _ in range(n)]
+                b = [rng.choice(src) if src else rng.randrange(m) for _ in range(n)]
+                neg = rng.randrange(1 << n)
+                out = (ctypes.c_uint32 * 8)()
+                lib.host_fe_dot(f, n, neg, limbs(a), limbs(b), out)
+                want = sum((-x if neg >> k & 1 else x) * y for k, (x, y) in enumerate(zip(a, b))) * Ri % m
+                assert rd(out, 1)[0] == want, (f, n, a, b, neg)
     for a in [rng.randrange(P) for _ in range(8)]:
         Rm = (1 << 256) % P
         assert op(0, 5, a * Rm % P) == pow(a, (P + 1) // 4, P) * Rm % P

@@ -47,6 +47,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--max-log-n", type=int, default=24)
     ap.add_argument("--decide-n", type=int, default=65536)
+    ap.add_argument("--only", choices=["all", "msm", "latency", "decide"], default="all")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     ctx = V.Context(0)
@@ -78,7 +79,7 @@ def main():
     stream.synchronize()
     out = torch.zeros(64, dtype=torch.uint8, device=dev)
     st = torch.zeros(1, dtype=torch.int32, device=dev)
-    for lg in range(16, args.max_log_n + 1, 2):
+    for lg in range(16, args.max_log_n + 1, 2) if args.only in ("all", "msm") else []:
         n = 1 << lg
         with torch.cuda.stream(stream):
             sc = rand_scalars(n, dev, 1000 + lg)
@@ -97,30 +98,22 @@ def main():
                           "kernels_ms": {k: round(v, 3) for k, v in prof.items()}}))
     del pts, dl
 
-    # ---- config 1: one SHPLONK proof, full PlonkVerifier::verify (succinct verify + fold of one + pairing), latency
-    g = load_golden()
-    pv1 = V.PlonkVerifier(ctx, g["dk"], g["protocol"], V.SHPLONK)
-    sn = g["schemes"]["bdfg21"]["snarks"][0]
-    import time as _t
-    pv1.verify_one(sn)
-    t0 = _t.perf_counter()
-    for _ in range(5):
+    # ---- config 1: one SHPLONK proof, full PlonkVerifier::verify (succinct verify + fold of one + pairing), latency.
+    # The CPU figure beside it is bench.py's `cpu_baseline` (1-thread port: ~4 ms per proof incl. the pairing).
+    if args.only in ("all", "latency"):
+        g = load_golden()
+        pv1 = V.PlonkVerifier(ctx, g["dk"], g["protocol"], V.SHPLONK)
+        sn = g["schemes"]["bdfg21"]["snarks"][0]
+        import time as _t
         pv1.verify_one(sn)
-    gpu_ms = 1e3 * (_t.perf_counter() - t0) / 5
-    try:
-        from oracle import forge
-        from oracle.c import cref
-        S_ = forge.Setup(0)
-        tr_ = cref.Trace(S_, "bdfg21")
         t0 = _t.perf_counter()
         for _ in range(5):
-            accs_, st_ = cref.replay(tr_, [sn.proof], [sn.instances], 1)
-            assert cref.decide(accs_[0], S_.dk)
-        cpu_ms = 1e3 * (_t.perf_counter() - t0) / 5
-    except Exception as e:  # oracle not available
-        cpu_ms = None
-    print(json.dumps({"config": "single_proof_verify_latency", "gpu_ms_host_call": gpu_ms, "cpu_port_ms_1_thread": cpu_ms,
-                      "note": "one proof cannot fill a GPU: the B200 path is a throughput device (batch configs)"}))
+            pv1.verify_one(sn)
+        gpu_ms = 1e3 * (_t.perf_counter() - t0) / 5
+        print(json.dumps({"config": "single_proof_verify_latency", "gpu_ms_host_call": gpu_ms,
+                          "note": "one proof cannot fill a GPU: the B200 path is a throughput device (batch configs)"}))
+    if args.only not in ("all", "decide"):
+        return
 
     # ---- config 5
     g = load_golden()
