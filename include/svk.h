@@ -35,7 +35,10 @@ enum {
   SVK_INVALID_INSTANCES = 1, /* Error::InvalidInstances   verifier/plonk/proof.rs:66-69 */
   SVK_INVALID_PROTOCOL = 2,  /* Error::InvalidProtocol    verifier/plonk/proof.rs:216,223,232,273 */
   SVK_ASSERTION_FAILURE = 3, /* Error::AssertionFailure   pcs/kzg/decider.rs:67 */
-  SVK_TRANSCRIPT = 4         /* Error::Transcript         system/halo2/transcript/halo2.rs:214-260 */
+  SVK_TRANSCRIPT = 4,        /* Error::Transcript         system/halo2/transcript/halo2.rs:214-260 */
+  SVK_ACCUMULATOR_PANIC = 5  /* the reference PANICS here: an old accumulator's limbs do not decode to curve points
+                                (`fe_from_big` / `from_xy(..).unwrap()`, util/arithmetic.rs:237-243, pcs/kzg/accumulator.rs:72-73);
+                                a Rust shim re-raises it as a panic */
 };
 /* sub-codes stored in bits 8.. of a status word when the low byte is SVK_TRANSCRIPT */
 enum { SVK_T_EOF = 1, SVK_T_SCALAR_RANGE = 2, SVK_T_POINT_INVALID = 3, SVK_T_POINT_IDENTITY = 4 };
@@ -85,18 +88,22 @@ int svk_kzg_decide_batch_dev(svk_ctx* ctx, int dk, size_t n, const void* d_accs,
  * reference would reject with Error::InvalidProtocol still compiles; its proofs get that status. */
 int svk_protocol_compile(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos, int dk); /* Poseidon transcript */
 int svk_protocol_compile_ex(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos, int transcript_kind, int dk);
-/* out[16] = { proof_len, n_instances, n_challenges, n_regs, n_ops, n_poseidon_perms, verify_valid,
+/* out[20] = { proof_len, n_instances, n_challenges, n_regs, n_ops, n_poseidon_perms, verify_valid,
  *             n_fr_mul, n_lhs_terms, n_rhs_terms, n_points, n_scalar_slots, msm_modmul_per_proof (all three MSM
- *             kernels), msm_var_modmul_per_proof (k_msm_var only), n_var_terms, var_lanes } */
+ *             kernels), msm_var_modmul_per_proof (k_msm_var only), n_var_terms, var_lanes,
+ *             n_old_accumulators, acc_limbs, acc_bits, transcript_kind } */
 int svk_protocol_info(svk_ctx* ctx, int proto, uint32_t* out);
 
 /* ---- PlonkSuccinctVerifier::{read_proof, verify} (verifier/plonk.rs:32-93) over a batch ----------
  * For each of the n proofs (proof i = proofs + i*proof_stride, length proof_lens[i] or proof_stride
  * when proof_lens == NULL; trailing bytes are ignored like the reference's reader):
- *   out_acc[i]        = the KzgAccumulator {lhs, rhs} (zeros when status != 0)
+ *   out_acc[i][0]     = the KzgAccumulator {lhs, rhs} (zeros when status != 0); a protocol with `accumulator_indices`
+ *                       (aggregation snarks; n_old = svk_protocol_info[16]) yields 1 + n_old records per proof:
+ *                       out_acc[i][1 + a] = old accumulator a, `LimbsEncoding<LIMBS, BITS>::from_repr` of the instances it
+ *                       names (pcs/kzg/accumulator.rs:57-77) -- the `Vec<KzgAccumulator>` of verifier/plonk.rs:86-91
  *   out_challenges[i] = every squeezed challenge in order (n_challenges each; may be NULL)
  *   out_status[i]     = SVK_OK / SVK_INVALID_INSTANCES / SVK_INVALID_PROTOCOL /
- *                       SVK_TRANSCRIPT | subcode << 8
+ *                       SVK_TRANSCRIPT | subcode << 8 / SVK_ACCUMULATOR_PANIC
  * instances: n * n_instances field elements (all instance columns of a proof, concatenated);
  * n_instances != sum(protocol.num_instance) => SVK_INVALID_INSTANCES for every proof (proof.rs:66-69). */
 int svk_plonk_succinct_verify_batch(svk_ctx* ctx, int proto, size_t n, const svk_fe* instances, uint32_t n_instances,
@@ -135,7 +142,9 @@ int svk_kzg_as_fold_dev(svk_ctx* ctx, size_t n, const void* d_accs, size_t group
  * locate_failures != 0: when all proofs read fine but the folded pairing fails, every accumulator is
  * decided on its own and the offenders get SVK_ASSERTION_FAILURE (what per-proof
  * `PlonkVerifier::verify` would have returned).
- * _dev: d_out_accs n*128 B, d_out_status n*4 B, d_out_folded 256 B =
+ * With old accumulators every proof contributes 1 + n_old accumulators to the fold, new one first (the flattening of
+ * snark-verifier-sdk/src/halo2/aggregation.rs:216-245), and `locate_failures` is `decide_all` over each proof's own list.
+ * _dev: d_out_accs n*(1+n_old)*128 B, d_out_status n*4 B, d_out_folded 256 B =
  *       { svk_acc folded; svk_fe r; int32 fold_status; uint8 decide_ok; uint8 ok }. */
 int svk_plonk_verify_batch(svk_ctx* ctx, int proto, size_t n, const svk_fe* instances, uint32_t n_instances, const uint8_t* proofs,
                            size_t proof_stride, const uint32_t* proof_lens, size_t group_size, int locate_failures,

@@ -11,12 +11,12 @@ from . import bn254
 from .kzg import KzgAccumulator, KzgAsBdfg21, KzgAsGwc19
 from .loader import NativeLoader
 from .plonk import PlonkSuccinctVerifier, PlonkVerifier
-from .transcript import PoseidonTranscript, VerifyError, make_transcript
+from .transcript import PoseidonTranscript, ReferencePanic, VerifyError, make_transcript
 
 SCHEMES = {"bdfg21": KzgAsBdfg21, "gwc19": KzgAsGwc19}
 
 # FFI status codes (include/svk.h) <- `Error` (snark-verifier/src/lib.rs:21-30)
-STATUS = {"OK": 0, "InvalidInstances": 1, "InvalidProtocol": 2, "AssertionFailure": 3, "Transcript": 4}
+STATUS = {"OK": 0, "InvalidInstances": 1, "InvalidProtocol": 2, "AssertionFailure": 3, "Transcript": 4, "Panic": 5}
 
 
 def succinct_verify(svk, protocol, instances, proof_bytes, scheme, loader=None, want_proof=False, transcript="poseidon"):
@@ -50,6 +50,8 @@ def status_of(fn, *a, **kw):
         return STATUS["OK"]
     except VerifyError as e:
         return STATUS[e.kind]
+    except ReferencePanic:
+        return STATUS["Panic"]
 
 
 def fold(accumulators, group_size=0, loader=None):

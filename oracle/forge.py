@@ -17,7 +17,7 @@ import random
 
 from . import bn254
 from .bn254 import R
-from .halo2_system import standard_plonk_protocol
+from .halo2_system import compile_protocol, standard_plonk_protocol, standard_plonk_shape
 from .kzg import KzgAsBdfg21, KzgAsGwc19, KzgDecidingKey, gwc19_query_sets
 from .loader import EcPoint, NativeLoader
 from .plonk import CommonPolynomialEvaluation, PlonkProof
@@ -79,7 +79,9 @@ class DlogLoader(NativeLoader):
 class Setup:
     """SRS trapdoor + a StandardPlonk verifying key with known dlogs (seeded, reproducible)."""
 
-    def __init__(self, seed=0, k=8):
+    def __init__(self, seed=0, k=8, num_instance=1, accumulator_indices=()):
+        """`num_instance` rows in the single instance column; `accumulator_indices`: lists of 12 (column, row) pairs naming
+        the limbs of old accumulators (an aggregation-circuit-shaped protocol, sdk/src/halo2/aggregation.rs:423-425)."""
         rng = random.Random(seed)
         self.k = k
         self.s = rng.randrange(1, R)
@@ -89,7 +91,11 @@ class Setup:
         self.vk_dlogs = [rng.randrange(1, R) for _ in range(8)]
         self.preprocessed = [g_mul(d) for d in self.vk_dlogs]
         self.transcript_initial_state = rng.randrange(R)  # stands in for the vk digest (system/halo2.rs:137)
-        self.protocol = standard_plonk_protocol(k, self.preprocessed, self.transcript_initial_state)
+        if num_instance == 1 and not accumulator_indices:
+            self.protocol = standard_plonk_protocol(k, self.preprocessed, self.transcript_initial_state)
+        else:
+            self.protocol = compile_protocol(k, standard_plonk_shape(), self.preprocessed, self.transcript_initial_state, [num_instance])
+            self.protocol.accumulator_indices = [list(x) for x in accumulator_indices]
         self.dk = KzgDecidingKey.new(self.g1, self.g2, self.s_g2)
         self.known = {self.g1: 1}
         for d, p in zip(self.vk_dlogs, self.preprocessed):
@@ -103,7 +109,18 @@ def _msm_dlog(msm):
     return d
 
 
-def forge_proof(setup, scheme, seed, transcript="poseidon"):
+def old_accumulator_limbs(setup, d, limbs=3, bits=88, valid=True):
+    """The 4 * LIMBS instance values of an old accumulator (lhs, rhs) = (s d G, d G) -- or, with valid=False,
+    ((s d + 1) G, d G): well-formed points that fail the pairing check: `fe_to_limbs` of x, y of both points
+    (util/arithmetic.rs:278-290; what the aggregation circuit exposes)."""
+    lhs, rhs = g_mul((setup.s * d + (0 if valid else 1)) % R), g_mul(d)
+    out = []
+    for v in (lhs[0], lhs[1], rhs[0], rhs[1]):
+        out += [(v >> (bits * i)) & ((1 << bits) - 1) for i in range(limbs)]
+    return out
+
+
+def forge_proof(setup, scheme, seed, transcript="poseidon", old_valid=True):
     """Returns (instances [[int]], proof bytes) accepted by PlonkVerifier<KzgAs<Bn256, scheme>>.
     scheme in {"bdfg21", "gwc19"}; transcript "poseidon" (compressed LE points, LE scalars) or "evm"
     (Keccak EvmTranscript: uncompressed BE points, BE scalars)."""
@@ -122,6 +139,9 @@ def forge_proof(setup, scheme, seed, transcript="poseidon"):
         return p
 
     instances = [[rng.randrange(R) for _ in range(n)] for n in protocol.num_instance]
+    for idx in protocol.accumulator_indices:
+        for (i, j), limb in zip(idx, old_accumulator_limbs(setup, rng.randrange(1, R), valid=old_valid)):
+            instances[i][j] = limb
     wit = [rand_point() for _ in range(n_w)]
     quo = [rand_point() for _ in range(n_q)]
     evals = [rng.randrange(R) for _ in protocol.evaluations]

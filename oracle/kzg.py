@@ -47,17 +47,24 @@ class LimbsEncoding:
         self.limbs, self.bits = limbs, bits
 
     def from_repr(self, limbs, loader):
+        from .transcript import ReferencePanic
+
         assert len(limbs) == 4 * self.limbs
         coords = []
         for i in range(4):
             v = fe_from_limbs([l.v for l in limbs[i * self.limbs : (i + 1) * self.limbs]], self.bits)
-            assert v < bn254.P, "fe_from_big: from_repr().unwrap() panics"  # arithmetic.rs:237-243
+            if v >= bn254.P:  # `assert!(bytes.len() <= 32)` / `from_repr().unwrap()` of fe_from_big (arithmetic.rs:237-243)
+                raise ReferencePanic("fe_from_big")
             coords.append(v)
-        lhs = (coords[0], coords[1])
-        rhs = (coords[2], coords[3])
-        # `C::from_xy(..).unwrap()` panics when off-curve (accumulator.rs:72-73)
-        assert bn254.g1_is_on_curve(lhs) and bn254.g1_is_on_curve(rhs), "from_xy().unwrap() panics"
-        return KzgAccumulator(loader.ec_point_load_const(lhs), loader.ec_point_load_const(rhs))
+        pts = []
+        for x, y in ((coords[0], coords[1]), (coords[2], coords[3])):
+            if (x, y) == (0, 0):  # halo2curves `from_xy`: `is_on_curve() | is_identity()` accepts (0, 0) as the identity
+                pts.append(None)
+            elif bn254.g1_is_on_curve((x, y)):
+                pts.append((x, y))
+            else:  # `C::from_xy(..).unwrap()` panics when off-curve (accumulator.rs:72-73)
+                raise ReferencePanic("from_xy().unwrap()")
+        return KzgAccumulator(loader.ec_point_load_const(pts[0]), loader.ec_point_load_const(pts[1]))
 
 
 # ================================================================ SHPLONK (bdfg21.rs)

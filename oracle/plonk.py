@@ -315,6 +315,10 @@ class PlonkProof:
         self.z = transcript.squeeze_challenge()
         self.evaluations = transcript.read_n_scalars(len(protocol.evaluations))
         self.pcs = AS.read_proof(svk, cls.empty_queries(protocol), transcript)
+        if AE is None and protocol.accumulator_indices:
+            from .kzg import LimbsEncoding
+
+            AE = LimbsEncoding(3, 88)  # the SDK's verifier type (snark-verifier-sdk/src/lib.rs:33-40)
         self.old_accumulators = [
             AE.from_repr([instances[i][j] for i, j in idx], loader) for idx in protocol.accumulator_indices
         ]

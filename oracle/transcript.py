@@ -19,6 +19,10 @@ class VerifyError(Exception):
         self.msg = msg
 
 
+class ReferencePanic(Exception):
+    """The reference does not return an `Err` here: it panics (`unwrap()` / `assert!`)."""
+
+
 class PoseidonTranscript:
     def __init__(self, loader, stream=b"", spec=None):
         self.loader = loader

@@ -71,6 +71,7 @@ struct Reader {
     return v;
   }
   int32_t i32_() { return (int32_t)u32_(); }
+  bool at_end() const { return pos >= n; }
   uint8_t u8_() {
     need(1);
     return p[pos++];
@@ -173,6 +174,7 @@ struct ProtocolDesc {
   Fr initial_state;
   uint8_t linearization = 0;  // 0 None, 1 WithoutConstant, 2 MinusVanishingTimesQuotient
   std::vector<std::vector<std::pair<u32, u32>>> accumulator_indices;
+  u32 acc_limbs = 3, acc_bits = 88;  // `LimbsEncoding<LIMBS, BITS>` (pcs/kzg/accumulator.rs:34); SDK: snark-verifier-sdk/src/lib.rs:33-40
 
   Fr rotate_one(int32_t rot) const {  // Domain::rotate_scalar(1, rot), arithmetic.rs:154-161
     if (rot == 0) return Fr::one();
@@ -223,8 +225,21 @@ inline ProtocolDesc parse_protocol(const uint8_t* blob, size_t len) {
     for (u32 j = count(1 << 16); j--;) { u32 a = r.u32_(), b = r.u32_(); v.push_back({a, b}); }
     p.accumulator_indices.push_back(v);
   }
-  if (!p.accumulator_indices.empty())
-    throw CompileError(-1, "old accumulators (LimbsEncoding) are not supported yet (SURVEY 8f-3)");
+  if (!r.at_end()) {  // optional trailer: the accumulator encoding's type parameters
+    p.acc_limbs = r.u8_();
+    p.acc_bits = r.u8_();
+  }
+  if (!p.accumulator_indices.empty()) {
+    if (p.acc_limbs == 0 || p.acc_bits == 0 || (p.acc_limbs - 1) * p.acc_bits + 256 > 1024)
+      throw CompileError(-1, "LimbsEncoding parameters out of range");
+    for (auto& v : p.accumulator_indices) {
+      // `assert_eq!(limbs.len(), 4 * LIMBS)` (accumulator.rs:61) and `instances[i][j]` (proof.rs:139-146) panic in the reference
+      if (v.size() != 4 * (size_t)p.acc_limbs) throw CompileError(-1, "accumulator_indices entry must name 4 * LIMBS instances");
+      for (auto& ij : v)
+        if (ij.first >= p.num_instance.size() || ij.second >= p.num_instance[ij.first])
+          throw CompileError(-1, "accumulator index out of the instance ranges");
+    }
+  }
   return p;
 }
 
@@ -532,6 +547,9 @@ struct CompiledProtocol {
   std::vector<svk_g1> preprocessed;
   int n_perm = 0;
   size_t n_fr_mul = 0;             // tape statistics
+  // old accumulators (`protocol.accumulator_indices`, proof.rs:139-146): flat instance indices, 4 * acc_limbs per accumulator
+  std::vector<u32> old_acc_idx;
+  u32 n_old = 0, acc_limbs = 3, acc_bits = 88;
 };
 
 struct PcsQuery {
@@ -1117,6 +1135,13 @@ inline CompiledProtocol compile_protocol(const uint8_t* blob, size_t len, int mo
   Compiler c(p, mos, transcript_kind);
   CompiledProtocol out = c.run();
   out.transcript_kind = transcript_kind;
+  std::vector<u32> col_off(p.num_instance.size() + 1, 0);
+  for (size_t i = 0; i < p.num_instance.size(); i++) col_off[i + 1] = col_off[i] + p.num_instance[i];
+  for (auto& v : p.accumulator_indices)
+    for (auto& ij : v) out.old_acc_idx.push_back(col_off[ij.first] + ij.second);
+  out.n_old = (u32)p.accumulator_indices.size();
+  out.acc_limbs = p.acc_limbs;
+  out.acc_bits = p.acc_bits;
   return out;
 }
 

@@ -264,6 +264,10 @@ int svk_protocol_compile_ex(svk_ctx* ctx, const uint8_t* blob, size_t len, int m
   pd->n_perm = cp.n_perm;
   pd->n_fr_mul = cp.n_fr_mul;
   pd->num_instance = cp.num_instance;
+  pd->n_old = cp.n_old;
+  pd->acc_limbs = cp.acc_limbs;
+  pd->acc_bits = cp.acc_bits;
+  if (pd->n_old && upload(ctx, &pd->d_old_idx, cp.old_acc_idx)) { delete pd; return -1; }
   pd->n_pre = (u32)cp.preprocessed.size();
   for (auto& p : cp.points) pd->points.push_back({p.byte_offset, (u32)(p.val_x < 0 ? 0 : p.val_x), (u32)(p.val_y < 0 ? 0 : p.val_y)});
   std::vector<G1Affine> fixed;
@@ -352,6 +356,7 @@ int svk_protocol_info(svk_ctx* ctx, int proto, uint32_t* out) {
   out[0] = pd->proof_len; out[1] = pd->n_instances; out[2] = pd->n_challenges; out[3] = pd->n_regs; out[4] = pd->n_ops;
   out[5] = (u32)pd->n_perm; out[6] = pd->verify_valid ? 1 : 0; out[7] = (u32)pd->n_fr_mul; out[8] = pd->n_lhs; out[9] = pd->n_rhs;
   out[10] = (u32)pd->points.size(); out[11] = pd->n_scalar_slots; out[12] = (u32)pd->msm_work_modmul; out[13] = (u32)(pd->n_var * (161 + 64 * 16) + pd->var_lanes_total * 252 * 7); out[14] = pd->n_var; out[15] = pd->var_lanes_total;
+  out[16] = pd->n_old; out[17] = pd->acc_limbs; out[18] = pd->acc_bits; out[19] = (u32)pd->transcript_kind;
   return 0;
 }
 
@@ -369,7 +374,7 @@ int svk_plonk_msm_scalars_batch(svk_ctx* ctx, int proto, size_t n, const svk_fe*
                                 int32_t* out_status) {
   if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
   ProtocolDevice* pd = ctx->protocols[proto];
-  std::vector<svk_acc> accs(n);
+  std::vector<svk_acc> accs(n * pd->accs_per_proof());
   if (svk_plonk_succinct_verify_batch(ctx, proto, n, instances, n_instances, proofs, proof_stride, proof_lens, accs.data(), out_challenges,
                                       out_status))
     return -1;
@@ -403,7 +408,7 @@ int svk_plonk_succinct_verify_batch(svk_ctx* ctx, int proto, size_t n, const svk
   size_t inst_bytes = n * (size_t)n_instances * 32, proof_bytes = n * proof_stride, chal_bytes = n * (size_t)pd->n_challenges * 32;
   uint8_t* d_io;
   size_t off_inst = 0, off_proofs = (inst_bytes + 255) / 256 * 256, off_lens = off_proofs + (proof_bytes + 255) / 256 * 256,
-         off_acc = off_lens + (n * 4 + 255) / 256 * 256, off_chal = off_acc + n * 128, off_status = off_chal + (chal_bytes + 255) / 256 * 256,
+         off_acc = off_lens + (n * 4 + 255) / 256 * 256, off_chal = off_acc + n * 128 * pd->accs_per_proof(), off_status = off_chal + (chal_bytes + 255) / 256 * 256,
          total = off_status + n * 4;
   if (svk_scratch(ctx, 0, total, (void**)&d_io)) return -1;
   if (inst_bytes) SVK_CUDA(ctx, cudaMemcpyAsync(d_io + off_inst, instances, inst_bytes, cudaMemcpyHostToDevice, s));
@@ -413,7 +418,7 @@ int svk_plonk_succinct_verify_batch(svk_ctx* ctx, int proto, size_t n, const svk
                                  proof_lens ? (const u32*)(d_io + off_lens) : nullptr, d_io + off_acc, (u32*)(d_io + off_chal),
                                  (int32_t*)(d_io + off_status)))
     return -1;
-  SVK_CUDA(ctx, cudaMemcpyAsync(out_acc, d_io + off_acc, n * 128, cudaMemcpyDeviceToHost, s));
+  SVK_CUDA(ctx, cudaMemcpyAsync(out_acc, d_io + off_acc, n * 128 * pd->accs_per_proof(), cudaMemcpyDeviceToHost, s));
   if (out_challenges && chal_bytes) SVK_CUDA(ctx, cudaMemcpyAsync(out_challenges, d_io + off_chal, chal_bytes, cudaMemcpyDeviceToHost, s));
   SVK_CUDA(ctx, cudaMemcpyAsync(out_status, d_io + off_status, n * 4, cudaMemcpyDeviceToHost, s));
   if (svk_wait(ctx)) return -1;
@@ -467,7 +472,8 @@ int svk_plonk_verify_multi_dev(svk_ctx* ctx, int proto, size_t n_batches, size_t
   if (svk_succinct_verify_launch(ctx, pd, n, (const uint8_t*)d_instances, n_instances, (const uint8_t*)d_proofs, proof_stride,
                                  (const u32*)d_proof_lens, (uint8_t*)d_out_accs, nullptr, (int32_t*)d_out_status))
     return -1;
-  if (svk_fold_launch_seg(ctx, n_batches, batch_size, (const uint8_t*)d_out_accs, group_size, rec, 256)) return -1;
+  // a proof contributes its new accumulator and the old ones it carries, in that order (verifier/plonk.rs:86-91)
+  if (svk_fold_launch_seg(ctx, n_batches, batch_size * pd->accs_per_proof(), (const uint8_t*)d_out_accs, group_size, rec, 256)) return -1;
   if (svk_decide_launch_strided(ctx, pd->dk, n_batches, rec, 256, rec + 164, 256)) return -1;
   return svk_batch_verdict_launch(ctx, n_batches, batch_size, (const int32_t*)d_out_status, rec, 256);
 }
@@ -486,11 +492,12 @@ int svk_plonk_verify_multi(svk_ctx* ctx, int proto, size_t n_batches, size_t bat
   if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
   if (n_batches == 0 || batch_size == 0) return svk_fail(ctx, "empty batch");
   size_t n = n_batches * batch_size;
+  size_t apk = ctx->protocols[proto]->accs_per_proof();
   cudaStream_t s = ctx->stream;
   size_t inst_bytes = n * (size_t)n_instances * 32, proof_bytes = n * proof_stride;
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
-  size_t off_proofs = al(inst_bytes), off_lens = off_proofs + al(proof_bytes), off_accs = off_lens + al(n * 4), off_status = off_accs + n * 128,
-         off_rec = off_status + al(n * 4), off_dec = off_rec + n_batches * 256, total = off_dec + al(n);
+  size_t off_proofs = al(inst_bytes), off_lens = off_proofs + al(proof_bytes), off_accs = off_lens + al(n * 4), off_status = off_accs + n * apk * 128,
+         off_rec = off_status + al(n * 4), off_dec = off_rec + n_batches * 256, total = off_dec + al(n * apk);
   uint8_t* d;
   if (svk_scratch(ctx, 0, total, (void**)&d)) return -1;
   if (inst_bytes) SVK_CUDA(ctx, cudaMemcpyAsync(d, instances, inst_bytes, cudaMemcpyHostToDevice, s));
@@ -510,12 +517,12 @@ int svk_plonk_verify_multi(svk_ctx* ctx, int proto, size_t n_batches, size_t bat
       bool all_ok = true;
       for (size_t i = 0; i < batch_size; i++) all_ok = all_ok && out_status[b * batch_size + i] == 0;
       if (!all_ok) continue;
-      std::vector<uint8_t> oks(batch_size);
-      if (svk_decide_launch(ctx, ctx->protocols[proto]->dk, batch_size, d + off_accs + b * batch_size * 128, d + off_dec)) return -1;
-      SVK_CUDA(ctx, cudaMemcpyAsync(oks.data(), d + off_dec, batch_size, cudaMemcpyDeviceToHost, s));
+      std::vector<uint8_t> oks(batch_size * apk);  // `decide_all` over [new, old...] of every proof (verifier/plonk.rs:131-134)
+      if (svk_decide_launch(ctx, ctx->protocols[proto]->dk, batch_size * apk, d + off_accs + b * batch_size * apk * 128, d + off_dec)) return -1;
+      SVK_CUDA(ctx, cudaMemcpyAsync(oks.data(), d + off_dec, batch_size * apk, cudaMemcpyDeviceToHost, s));
       if (svk_wait(ctx)) return -1;
-      for (size_t i = 0; i < batch_size; i++)
-        if (!oks[i]) out_status[b * batch_size + i] = SVK_ASSERTION_FAILURE;
+      for (size_t i = 0; i < batch_size * apk; i++)
+        if (!oks[i]) out_status[b * batch_size + i / apk] = SVK_ASSERTION_FAILURE;
     }
   }
   return 0;

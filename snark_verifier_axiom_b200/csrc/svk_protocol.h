@@ -71,4 +71,8 @@ struct ProtocolDevice {
   G1Affine* d_fixed = nullptr;  // preprocessed..., then g at index n_pre
   u32 n_pre = 0;
   int dk = -1;                  // deciding key whose g1 is baked in as `svk.g`
+  // old accumulators carried in the instances (`LimbsEncoding::from_repr`, pcs/kzg/accumulator.rs:36-79)
+  u32 n_old = 0, acc_limbs = 3, acc_bits = 88;
+  u32* d_old_idx = nullptr;     // [n_old][4 * acc_limbs] flat instance indices
+  u32 accs_per_proof() const { return 1 + n_old; }
 };

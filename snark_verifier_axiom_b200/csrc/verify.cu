@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(128) k_msm_sum(size_t n_items, const MsmWork* 
   if (active && lane == 0) sums[(size_t)blockIdx.y * n_items + item] = acc;
 }
 
-__global__ void __launch_bounds__(128) k_to_affine(size_t n_items, const G1Jac* sums, const u32* err, uint8_t* out_acc) {
+__global__ void __launch_bounds__(128) k_to_affine(size_t n_items, const G1Jac* sums, const u32* err, uint8_t* out_acc, size_t acc_stride) {
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= 2 * n_items) return;
   size_t item = gid % n_items;
@@ -284,11 +284,81 @@ __global__ void __launch_bounds__(128) k_to_affine(size_t n_items, const G1Jac* 
   bool bad = err[item] != SVK_NO_ERR;
   G1Affine a = bad ? G1Affine::identity() : sums[gid].to_affine();
   Fq x = a.x.from_mont(), y = a.y.from_mont();
-  uint4* o = reinterpret_cast<uint4*>(out_acc + item * 128 + (side ? 64 : 0));
+  uint4* o = reinterpret_cast<uint4*>(out_acc + item * acc_stride + (side ? 64 : 0));
   o[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
   o[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
   o[2] = make_uint4(y.v[0], y.v[1], y.v[2], y.v[3]);
   o[3] = make_uint4(y.v[4], y.v[5], y.v[6], y.v[7]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Old accumulators carried in the instances: `LimbsEncoding<LIMBS, BITS>::from_repr` (pcs/kzg/accumulator.rs:57-77) over
+// `protocol.accumulator_indices` (verifier/plonk/proof.rs:139-146).  Each coordinate is sum_k limb_k << (BITS k) as an
+// integer (`fe_from_limbs`, util/arithmetic.rs:262-274); the reference PANICS when that integer does not fit 32 bytes or is
+// >= p (`fe_from_big`, :237-243) or when (x, y) is not on the curve (`from_xy(..).unwrap()`, accumulator.rs:72-73; (0, 0) is
+// the identity and passes).  Here those proofs get status SVK_ACCUMULATOR_PANIC.  One proof per thread; its old accumulators
+// land behind its new one: out_acc[item][1 + a].  A proof that already failed gets zeros, like its new accumulator.
+#define SVK_ERR_ACC_PANIC 0xfffffefeu
+__global__ void __launch_bounds__(64) k_old_accumulators(size_t n_items, u32 n_old, u32 limbs, u32 bits, const u32* idx, const uint8_t* instances,
+                                                        u32 n_instances, u32* err, uint8_t* out_acc, size_t acc_stride) {
+  size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= n_items) return;
+  bool bad = err[item] != SVK_NO_ERR;
+  const uint8_t* inst = instances + item * (size_t)n_instances * 32;
+  for (u32 a = 0; a < n_old && !bad; a++) {
+    G1Affine pt[2];
+    for (u32 c = 0; c < 4 && !bad; c++) {
+      u32 acc[33];
+      for (int i = 0; i < 33; i++) acc[i] = 0;
+      for (u32 k = 0; k < limbs; k++) {
+        u32 w[8];
+        fe_load_le(w, inst + 32 * (size_t)idx[(a * 4 + c) * limbs + k]);
+        if (!Fr::is_canonical(w)) bad = true;  // not an `Fr`: the tape reports it as InvalidInstances first (lower error word)
+        u32 sh = bits * k, wo = sh >> 5, bo = sh & 31;
+        u64 carry = 0;
+        for (int i = 0; i < 9; i++) {
+          u32 lo = i < 8 ? w[i] : 0, prev = i > 0 ? w[i - 1] : 0;
+          u32 piece = bo ? ((lo << bo) | (prev >> (32 - bo))) : lo;
+          u64 t = (u64)acc[wo + i] + piece + carry;
+          acc[wo + i] = (u32)t;
+          carry = t >> 32;
+        }
+        for (u32 i = wo + 9; carry && i < 33; i++) {
+          u64 t = (u64)acc[i] + carry;
+          acc[i] = (u32)t;
+          carry = t >> 32;
+        }
+      }
+      for (int i = 8; i < 33; i++) bad = bad || acc[i] != 0;
+      Fq v;
+      for (int i = 0; i < 8; i++) v.v[i] = acc[i];
+      bad = bad || !Fq::is_canonical(v.v);
+      if (c & 1) pt[c >> 1].y = v; else pt[c >> 1].x = v;
+    }
+    for (int sde = 0; sde < 2 && !bad; sde++) {
+      G1Affine m = pt[sde];
+      if (!(m.x.is_zero() && m.y.is_zero())) {
+        m.x = m.x.to_mont();
+        m.y = m.y.to_mont();
+        bad = !g1_on_curve(m);
+      }
+    }
+    if (!bad) {
+      uint4* o = reinterpret_cast<uint4*>(out_acc + item * acc_stride + 128 * (size_t)(1 + a));
+      for (int sde = 0; sde < 2; sde++) {
+        const Fq &x = pt[sde].x, &y = pt[sde].y;
+        o[4 * sde + 0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+        o[4 * sde + 1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+        o[4 * sde + 2] = make_uint4(y.v[0], y.v[1], y.v[2], y.v[3]);
+        o[4 * sde + 3] = make_uint4(y.v[4], y.v[5], y.v[6], y.v[7]);
+      }
+    }
+  }
+  if (bad) {
+    if (err[item] == SVK_NO_ERR) err[item] = SVK_ERR_ACC_PANIC;
+    uint4* o = reinterpret_cast<uint4*>(out_acc + item * acc_stride + 128);
+    for (u32 i = 0; i < n_old * 8; i++) o[i] = make_uint4(0, 0, 0, 0);
+  }
 }
 
 int svk_fixed_tables_launch(svk_ctx* ctx, ProtocolDevice* pd) {
@@ -308,6 +378,7 @@ __global__ void k_status(size_t n_items, const u32* err, int mode, int32_t* stat
   u32 e = err[i];
   int32_t s = SVK_OK;
   if (mode == 1) s = SVK_INVALID_INSTANCES;
+  else if (e == SVK_ERR_ACC_PANIC) s = SVK_ACCUMULATOR_PANIC;
   else if (e != SVK_NO_ERR) s = ((e & 0xff) == 0) ? SVK_INVALID_INSTANCES : (SVK_TRANSCRIPT | (int32_t)((e & 0xff) << 8));
   else if (mode == 2) s = SVK_INVALID_PROTOCOL;
   status[i] = s;
@@ -324,6 +395,7 @@ int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const
                                u32* d_out_challenges, int32_t* d_out_status) {
   if (n == 0) return 0;
   cudaStream_t s = ctx->stream;
+  const size_t acc_stride = 128 * (size_t)pd->accs_per_proof();
   u32 *d_err, *d_regs, *d_scalars, *d_chal_scratch;
   G1Affine* d_pts;
   size_t n_pts = pd->points.size();
@@ -364,6 +436,11 @@ int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const
                                                                        d_proofs, proof_stride, d_proof_lens, d_instances, pd->n_instances,
                                                                        d_scalars, d_out_challenges, pd->n_challenges, d_err));
   }
+  // `PlonkProof::read` ends with the old accumulators (proof.rs:139-146): their panic precedes anything `verify` reports
+  if (pd->n_old && mode != 1)
+    SVK_LAUNCH(ctx, "k_old_accumulators",
+               k_old_accumulators<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(n, pd->n_old, pd->acc_limbs, pd->acc_bits, pd->d_old_idx, d_instances,
+                                                                          pd->n_instances, d_err, d_out_acc, acc_stride));
   if (mode == 0) {
     G1Jac *d_partials, *d_sums, *d_tables;
     u32 vpl = pd->var_lanes_total;
@@ -381,9 +458,9 @@ int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const
                k_msm_sum<<<grid, 128, 0, s>>>(n, pd->d_work_lhs, pd->d_lane_off_lhs, pd->d_work_rhs, pd->d_lane_off_rhs, pd->d_fixed_lhs,
                                               pd->fixed_per_lhs, pd->d_fixed_rhs, pd->fixed_per_rhs, pd->d_fixed,
                                               pd->d_fixed_tables, d_pts, d_scalars, d_partials, d_sums));
-    SVK_LAUNCH(ctx, "k_to_affine", k_to_affine<<<(unsigned)((2 * n + 127) / 128), 128, 0, s>>>(n, d_sums, d_err, d_out_acc));
+    SVK_LAUNCH(ctx, "k_to_affine", k_to_affine<<<(unsigned)((2 * n + 127) / 128), 128, 0, s>>>(n, d_sums, d_err, d_out_acc, acc_stride));
   } else {
-    SVK_CUDA(ctx, cudaMemsetAsync(d_out_acc, 0, n * 128, s));
+    SVK_CUDA(ctx, cudaMemsetAsync(d_out_acc, 0, n * acc_stride, s));
   }
   SVK_LAUNCH(ctx, "k_status", k_status<<<(unsigned)((n + b - 1) / b), b, 0, s>>>(n, d_err, mode, d_out_status));
   SVK_CUDA(ctx, cudaGetLastError());

@@ -74,7 +74,8 @@ class ShardedBatchVerifier:
 
     def _ensure(self, n):
         if self._n < n:
-            self.d_accs = torch.zeros(n * 128, dtype=torch.uint8, device=self.device)
+            apk = 1 + getattr(self.pv, "info", {}).get("n_old_accumulators", 0)  # [new, old...] per proof (verifier/plonk.rs:86-91)
+            self.d_accs = torch.zeros(n * apk * 128, dtype=torch.uint8, device=self.device)
             self.d_status = torch.zeros(n, dtype=torch.int32, device=self.device)
             self._n = n
 

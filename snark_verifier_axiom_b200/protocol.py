@@ -207,6 +207,7 @@ class PlonkProtocol:
     instance_committing_key: Optional[object] = None
     linearization: Optional[int] = None
     accumulator_indices: List[List[Tuple[int, int]]] = field(default_factory=list)
+    accumulator_encoding: Tuple[int, int] = (3, 88)  # `LimbsEncoding<LIMBS, BITS>` of the verifier type (sdk/lib.rs:33-40)
 
     def to_bytes(self) -> bytes:
         out = bytearray()
@@ -239,4 +240,5 @@ class PlonkProtocol:
             out += struct.pack("<I", len(idx))
             for i, j in idx:
                 out += struct.pack("<II", i, j)
+        out += bytes(self.accumulator_encoding)
         return bytes(out)

@@ -25,7 +25,7 @@ GWC = GWC19 = 1
 POSEIDON_TRANSCRIPT = 0  # sdk `PoseidonTranscript` (snark-verifier-sdk/src/halo2.rs:58-67)
 EVM_TRANSCRIPT = 1       # Keccak `EvmTranscript` (snark-verifier/src/system/halo2/transcript/evm.rs)
 
-STATUS_NAMES = {0: "Ok", 1: "InvalidInstances", 2: "InvalidProtocol", 3: "AssertionFailure", 4: "Transcript"}
+STATUS_NAMES = {0: "Ok", 1: "InvalidInstances", 2: "InvalidProtocol", 3: "AssertionFailure", 4: "Transcript", 5: "AccumulatorPanic"}
 
 
 class Error(Exception):
@@ -145,11 +145,11 @@ class Context:
         return self._check(self._L.svk_protocol_compile_ex(self._c, blob, len(blob), mos, transcript, dk_id))
 
     def protocol_info(self, pid: int) -> dict:
-        out = (ctypes.c_uint32 * 16)()
+        out = (ctypes.c_uint32 * 20)()
         self._check(self._L.svk_protocol_info(self._c, pid, out))
         keys = ["proof_len", "n_instances", "n_challenges", "n_regs", "n_ops", "n_poseidon_perms", "verify_valid", "n_fr_mul",
                 "n_lhs_terms", "n_rhs_terms", "n_points", "n_scalar_slots", "msm_modmul_per_proof", "msm_var_modmul_per_proof",
-                "n_var_terms", "var_lanes"]
+                "n_var_terms", "var_lanes", "n_old_accumulators", "acc_limbs", "acc_bits", "transcript_kind"]
         return dict(zip(keys, [int(x) for x in out]))
 
     def modmul_peak(self, iters: int = 4000):
@@ -245,17 +245,23 @@ class PlonkVerifier:
 
     # ---- PlonkSuccinctVerifier::{read_proof, verify} ------------------------------------------------
     def succinct_verify(self, snarks: Sequence[Snark]):
-        """-> (accumulators [KzgAccumulator|None], challenges [[int]], status int32[n])"""
+        """-> (accumulators [KzgAccumulator|None], challenges [[int]], status int32[n]).
+        For a protocol with `accumulator_indices` (an aggregation snark) entry i is the list [new, old_0, ...] of
+        verifier/plonk.rs:86-91 instead of a single accumulator."""
         n = len(snarks)
         inst, n_inst, proofs, lens = self.pack(snarks)
         nch = self.info["n_challenges"]
-        acc = np.zeros((n, 128), np.uint8)
+        apk = 1 + self.info["n_old_accumulators"]
+        acc = np.zeros((n, apk, 128), np.uint8)
         ch = np.zeros((n, max(nch, 1), 32), np.uint8)
         st = np.zeros(n, np.int32)
         L, c = self.ctx._L, self.ctx._c
         self.ctx._check(L.svk_plonk_succinct_verify_batch(c, self.pid, n, _ptr(inst), n_inst, _ptr(proofs), proofs.shape[1], _ptr(lens),
                                                           _ptr(acc), _ptr(ch), _ptr(st)))
-        accs = [KzgAccumulator.from_bytes(acc[i].tobytes()) if st[i] == 0 else None for i in range(n)]
+        if apk == 1:
+            accs = [KzgAccumulator.from_bytes(acc[i, 0].tobytes()) if st[i] == 0 else None for i in range(n)]
+        else:
+            accs = [[KzgAccumulator.from_bytes(acc[i, k].tobytes()) for k in range(apk)] if st[i] == 0 else None for i in range(n)]
         chals = [[int.from_bytes(ch[i, j].tobytes(), "little") for j in range(nch)] for i in range(n)]
         return accs, chals, st
 

@@ -109,3 +109,30 @@ def test_golden_fixture_matches_oracle(S):
             e = s["expect"][i]
             assert int(e["lhs"][0], 16) == accs[0].lhs.pt[0] and int(e["rhs"][1], 16) == accs[0].rhs.pt[1]
             assert int(e["challenges"][4], 16) == proof.z.v
+
+
+def test_old_accumulators_limbs_encoding():
+    """`accumulator_indices` + `LimbsEncoding<3, 88>` (pcs/kzg/accumulator.rs:57-77, verifier/plonk.rs:86-91, 131-134)."""
+    from oracle.loader import fe_to_limbs
+    from oracle.transcript import ReferencePanic
+
+    S2 = forge.Setup(0, num_instance=14, accumulator_indices=[[(0, 1 + i) for i in range(12)]])
+    inst, proof = forge.forge_proof(S2, "bdfg21", 41)
+    accs = api.succinct_verify(S2.dk.svk, S2.protocol, inst, proof, "bdfg21")
+    assert len(accs) == 2
+    old = accs[1]
+    want = []
+    for v in (old.lhs.pt[0], old.lhs.pt[1], old.rhs.pt[0], old.rhs.pt[1]):
+        want += fe_to_limbs(v, 3, 88)
+    assert inst[0][1:13] == want  # from_repr inverts fe_to_limbs
+    assert api.status_of(api.verify, S2.dk, S2.protocol, inst, proof, "bdfg21") == 0
+    # a well-formed old accumulator that fails the pairing: only decide_all notices
+    inst_b, proof_b = forge.forge_proof(S2, "bdfg21", 41, old_valid=False)
+    assert len(api.succinct_verify(S2.dk.svk, S2.protocol, inst_b, proof_b, "bdfg21")) == 2
+    assert api.status_of(api.verify, S2.dk, S2.protocol, inst_b, proof_b, "bdfg21") == 3
+    # off-curve limbs: the reference panics
+    bad = [list(inst[0])]
+    bad[0][1] ^= 1
+    with pytest.raises(ReferencePanic):
+        api.succinct_verify(S2.dk.svk, S2.protocol, bad, proof, "bdfg21")
+    assert api.status_of(api.verify, S2.dk, S2.protocol, bad, proof, "bdfg21") == 5
