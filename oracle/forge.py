@@ -79,22 +79,27 @@ class DlogLoader(NativeLoader):
 class Setup:
     """SRS trapdoor + a StandardPlonk verifying key with known dlogs (seeded, reproducible)."""
 
-    def __init__(self, seed=0, k=8, num_instance=1, accumulator_indices=()):
+    def __init__(self, seed=0, k=8, num_instance=1, accumulator_indices=(), shape=None, num_proof=1):
         """`num_instance` rows in the single instance column; `accumulator_indices`: lists of 12 (column, row) pairs naming
-        the limbs of old accumulators (an aggregation-circuit-shaped protocol, sdk/src/halo2/aggregation.rs:423-425)."""
+        the limbs of old accumulators (an aggregation-circuit-shaped protocol, sdk/src/halo2/aggregation.rs:423-425).
+        `shape`: another circuit than StandardPlonk (a `ConstraintSystemShape`: lookups, phases, ...); `num_proof` > 1:
+        one protocol verifying several proofs of that circuit at once (system/halo2.rs:57-63)."""
         rng = random.Random(seed)
         self.k = k
         self.s = rng.randrange(1, R)
         self.g1 = bn254.G1_GEN
         self.g2 = bn254.G2_GEN
         self.s_g2 = bn254.g2_mul(bn254.G2_GEN, self.s)
-        self.vk_dlogs = [rng.randrange(1, R) for _ in range(8)]
+        n_pre = 8 if shape is None else shape.num_fixed + len(shape.permutation_columns)
+        self.vk_dlogs = [rng.randrange(1, R) for _ in range(n_pre)]
         self.preprocessed = [g_mul(d) for d in self.vk_dlogs]
         self.transcript_initial_state = rng.randrange(R)  # stands in for the vk digest (system/halo2.rs:137)
-        if num_instance == 1 and not accumulator_indices:
+        if shape is None and num_instance == 1 and not accumulator_indices and num_proof == 1:
             self.protocol = standard_plonk_protocol(k, self.preprocessed, self.transcript_initial_state)
         else:
-            self.protocol = compile_protocol(k, standard_plonk_shape(), self.preprocessed, self.transcript_initial_state, [num_instance])
+            num_instance = [num_instance] if isinstance(num_instance, int) else list(num_instance)
+            self.protocol = compile_protocol(k, shape or standard_plonk_shape(), self.preprocessed, self.transcript_initial_state,
+                                             num_instance, num_proof=num_proof)
             self.protocol.accumulator_indices = [list(x) for x in accumulator_indices]
         self.dk = KzgDecidingKey.new(self.g1, self.g2, self.s_g2)
         self.known = {self.g1: 1}

@@ -1,8 +1,8 @@
 """halo2 `VerifyingKey` -> `PlonkProtocol` front-end -- oracle restatement.  TEST INFRASTRUCTURE ONLY.
 
-Follows snark-verifier/src/system/halo2.rs:82-156 (`compile`), :164-668 (`Polynomials`), for
-circuits WITHOUT lookups and with single-phase advice (the StandardPlonk family used by the
-BASELINE configs).  halo2's `ConstraintSystem` itself (halo2_proofs, Cargo.lock:1751-1753) is not
+Follows snark-verifier/src/system/halo2.rs:82-156 (`compile`), :164-684 (`Polynomials`): gates, permutation argument,
+lookup arguments, multi-phase advice / challenges, `num_proof` > 1, accumulator indices (zk = true, the only mode the
+reference implements).  halo2's `ConstraintSystem` itself (halo2_proofs, Cargo.lock:1751-1753) is not
 in the tree; its derived quantities (`degree()`, `blinding_factors()`, query lists) are passed in
 as a small `ConstraintSystemShape` and were derived by hand for StandardPlonk.
 """
@@ -39,28 +39,46 @@ class ConstraintSystemShape:
     advice_queries: List[Tuple[int, int]]  # (column, rotation)
     fixed_queries: List[Tuple[int, int]]
     instance_queries: List[Tuple[int, int]]
-    gates: List[Any]  # expressions over ("fixed", i, rot) / ("advice", i, rot) / ("instance", i, rot)
+    gates: List[Any]  # expressions over ("fixed", i, rot) / ("advice", i, rot) / ("instance", i, rot) / ("challenge", i)
     degree: int
     blinding_factors: int
+    advice_column_phase: List[int] = field(default_factory=list)  # per advice column; [] = all first phase
+    challenge_phase: List[int] = field(default_factory=list)      # per user challenge (`cs.challenge_phase()`)
+    lookups: List[Tuple[List[Any], List[Any]]] = field(default_factory=list)  # (input_expressions, table_expressions)
+
+
+def _remapping(phase, num_phase):
+    """system/halo2.rs:199-213"""
+    num = [0] * num_phase
+    index = []
+    for ph in phase:
+        index.append(num[ph])
+        num[ph] += 1
+    return num, index
 
 
 class Polynomials:
-    """system/halo2.rs:164-668 with zk = true, num_proof = 1, no lookups, one advice phase."""
+    """system/halo2.rs:164-668 with zk = true (the only mode the reference implements, :189)."""
 
-    def __init__(self, cs: ConstraintSystemShape, query_instance: bool, num_instance: List[int]):
+    def __init__(self, cs: ConstraintSystemShape, query_instance: bool, num_instance: List[int], num_proof: int = 1):
         self.cs = cs
         self.zk = True
         self.query_instance = query_instance
-        self.num_proof = 1
+        assert num_proof > 0
+        self.num_proof = num_proof
         self.num_fixed = cs.num_fixed
         self.num_permutation_fixed = len(cs.permutation_columns)
         self._num_instance = list(num_instance)
-        self.num_advice = [cs.num_advice]
-        self._num_challenge = [0]
-        self.num_lookup_permuted = 0
+        adv_phase = list(cs.advice_column_phase) or [0] * cs.num_advice
+        assert len(adv_phase) == cs.num_advice
+        num_phase = max(adv_phase, default=0) + 1
+        self.advice_phase = adv_phase
+        self.num_advice, self.advice_index = _remapping(adv_phase, num_phase)
+        self._num_challenge, self.challenge_index = _remapping(list(cs.challenge_phase), num_phase)
+        self.num_lookup_permuted = 2 * len(cs.lookups)
         self.permutation_chunk_size = cs.degree - 2  # zk => degree - 2 (:190-196)
         self.num_permutation_z = -(-len(cs.permutation_columns) // self.permutation_chunk_size)
-        self.num_lookup_z = 0
+        self.num_lookup_z = len(cs.lookups)
 
     def num_preprocessed(self):
         return self.num_fixed + self.num_permutation_fixed
@@ -97,16 +115,19 @@ class Polynomials:
         elif column_type == "instance":
             offset = self.instance_offset() + t * len(self._num_instance)
         else:
-            offset = self.witness_offset() + t * self.num_advice[0]
+            phase = self.advice_phase[column_index]
+            column_index = self.advice_index[column_index]
+            phase_offset = self.num_proof * sum(self.num_advice[:phase])
+            offset = self.witness_offset() + phase_offset + t * self.num_advice[phase]
         return (offset + column_index, rotation)
 
-    def instance_queries(self):
+    def instance_queries(self, t=0):
         if not self.query_instance:
             return []
-        return [self.query("instance", c, r) for c, r in self.cs.instance_queries]
+        return [self.query("instance", c, r, t) for c, r in self.cs.instance_queries]
 
-    def advice_queries(self):
-        return [self.query("advice", c, r) for c, r in self.cs.advice_queries]
+    def advice_queries(self, t=0):
+        return [self.query("advice", c, r, t) for c, r in self.cs.advice_queries]
 
     def fixed_queries(self):
         return [self.query("fixed", c, r) for c, r in self.cs.fixed_queries]
@@ -121,22 +142,41 @@ class Polynomials:
     def rotation_last(self):
         return -(self.cs.blinding_factors + 1)
 
-    def permutation_z_queries(self, eval_order):
+    def permutation_z_queries(self, eval_order, t=0):
         """:336-370 (zk = true)"""
         n = self.num_permutation_z
         out = []
         if eval_order:
             for i in range(n):
-                z = self.permutation_poly(0, i)
+                z = self.permutation_poly(t, i)
                 out += [(z, 0), (z, 1)]
                 if i != n - 1:
                     out.append((z, self.rotation_last()))
         else:
             for i in range(n):
-                z = self.permutation_poly(0, i)
+                z = self.permutation_poly(t, i)
                 out += [(z, 0), (z, 1)]
             for i in reversed(range(n - 1)):
-                out.append((self.permutation_poly(0, i), self.rotation_last()))
+                out.append((self.permutation_poly(t, i), self.rotation_last()))
+        return out
+
+    def lookup_poly(self, t, i):
+        """:372-381"""
+        permuted_offset = self.cs_witness_offset()
+        z_offset = permuted_offset + self.num_witness()[len(self.num_advice)] + self.num_proof * self.num_permutation_z
+        z = z_offset + t * self.num_lookup_z + i
+        permuted_input = permuted_offset + 2 * (t * self.num_lookup_z + i)
+        return z, permuted_input, permuted_input + 1
+
+    def lookup_queries(self, eval_order, t=0):
+        """:383-408"""
+        out = []
+        for i in range(self.num_lookup_z):
+            z, pi, pt = self.lookup_poly(t, i)
+            if eval_order:
+                out += [(z, 0), (z, 1), (pi, 0), (pi, -1), (pt, 0)]
+            else:
+                out += [(z, 0), (pi, 0), (pt, 0), (pi, -1), (z, 1)]
         return out
 
     def quotient_query(self):
@@ -145,21 +185,24 @@ class Polynomials:
     def random_query(self):
         return (self.witness_offset() + sum(self.num_witness()) - 1, 0)
 
-    def convert(self, e):
+    def convert(self, e, t=0):
         """:419-449"""
         tag = e[0]
         if tag == "const":
             return Const(e[1] % R)
         if tag in ("fixed", "advice", "instance"):
-            return Poly(*self.query(tag, e[1], e[2]))
+            return Poly(*self.query(tag, e[1], e[2], t))
+        if tag == "challenge":
+            phase = self.cs.challenge_phase[e[1]]
+            return Challenge(sum(self._num_challenge[:phase]) + self.challenge_index[e[1]])
         if tag == "neg":
-            return ("neg", self.convert(e[1]))
+            return ("neg", self.convert(e[1], t))
         if tag == "sum":
-            return Sum(self.convert(e[1]), self.convert(e[2]))
+            return Sum(self.convert(e[1], t), self.convert(e[2], t))
         if tag == "product":
-            return Product(self.convert(e[1]), self.convert(e[2]))
+            return Product(self.convert(e[1], t), self.convert(e[2], t))
         if tag == "scaled":
-            return Scaled(self.convert(e[1]), e[2] % R)
+            return Scaled(self.convert(e[1], t), e[2] % R)
         raise ValueError(tag)
 
     def l_last(self):
@@ -187,7 +230,7 @@ class Polynomials:
     def alpha(self):
         return Challenge(self.system_challenge_offset() + 3)
 
-    def permutation_constraints(self):
+    def permutation_constraints(self, t=0):
         """:501-591 (zk = true)"""
         one = Const(1)
         l_0 = Lagrange(0)
@@ -195,11 +238,11 @@ class Polynomials:
         l_active = self.l_active()
         identity = Identity()
         beta, gamma = self.beta(), self.gamma()
-        polys = [Poly(*self.query(ct, ci, 0)) for ct, ci in self.cs.permutation_columns]
+        polys = [Poly(*self.query(ct, ci, 0, t)) for ct, ci in self.cs.permutation_columns]
         permutation_fixeds = [Poly(self.num_fixed + i, 0) for i in range(self.num_permutation_fixed)]
         zs = []
         for i in range(self.num_permutation_z):
-            z = self.permutation_poly(0, i)
+            z = self.permutation_poly(t, i)
             zs.append((Poly(z, 0), Poly(z, 1), Poly(z, self.rotation_last())))
         out = []
         if zs:
@@ -227,30 +270,75 @@ class Polynomials:
             out.append(Product(l_active, Sub(left, right)))
         return out
 
+    def lookup_constraints(self, t=0):
+        """:593-655 (zk = true)"""
+        one = Const(1)
+        l_0 = Lagrange(0)
+        l_last = self.l_last()
+        l_active = self.l_active()
+        beta, gamma = self.beta(), self.gamma()
+        out = []
+        for i, (input_exprs, table_exprs) in enumerate(self.cs.lookups):
+            zq, pi, pt = self.lookup_poly(t, i)
+            z, z_omega = Poly(zq, 0), Poly(zq, 1)
+            permuted_input, permuted_input_omega_inv, permuted_table = Poly(pi, 0), Poly(pi, -1), Poly(pt, 0)
+            inp = DistributePowers([self.convert(e, t) for e in input_exprs], self.theta())
+            table = DistributePowers([self.convert(e, t) for e in table_exprs], self.theta())
+            out.append(Product(l_0, Sub(one, z)))
+            out.append(Product(l_last, Sub(Product(z, z), z)))
+            out.append(
+                Product(
+                    l_active,
+                    Sub(
+                        Product(Product(z_omega, Sum(permuted_input, beta)), Sum(permuted_table, gamma)),
+                        Product(Product(z, Sum(inp, beta)), Sum(table, gamma)),
+                    ),
+                )
+            )
+            out.append(Product(l_0, Sub(permuted_input, permuted_table)))
+            out.append(
+                Product(Product(l_active, Sub(permuted_input, permuted_table)), Sub(permuted_input, permuted_input_omega_inv))
+            )
+        return out
+
     def quotient(self):
         """:657-668"""
-        constraints = [self.convert(g) for g in self.cs.gates] + self.permutation_constraints()
+        constraints = []
+        for t in range(self.num_proof):
+            constraints += [self.convert(g, t) for g in self.cs.gates]
+            constraints += self.permutation_constraints(t)
+            constraints += self.lookup_constraints(t)
         return QuotientPolynomial(1, DistributePowers(constraints, self.alpha()))
+
+    def accumulator_indices(self, accumulator_indices):
+        """:670-684"""
+        return [[(poly + t * len(self._num_instance), row) for poly, row in accumulator_indices] for t in range(self.num_proof)]
 
 
 def compile_protocol(k, cs: ConstraintSystemShape, preprocessed, transcript_initial_state, num_instance,
-                     query_instance=False):
-    """`compile(params, vk, Config::kzg().with_num_instance(..))` (system/halo2.rs:82-156)."""
+                     query_instance=False, num_proof=1, accumulator_indices=None):
+    """`compile(params, vk, Config::kzg().with_num_instance(..).with_num_proof(..).with_accumulator_indices(..))`
+    (system/halo2.rs:82-156)."""
     assert len(preprocessed) == cs.num_fixed + len(cs.permutation_columns)
+    assert not query_instance, "instance_committing_key needs the SRS Lagrange basis (KZG path never sets it, SURVEY App. A)"
     domain = Domain(k)
-    p = Polynomials(cs, query_instance, num_instance)
+    p = Polynomials(cs, query_instance, num_instance, num_proof)
+    T = range(num_proof)
     evaluations = (
-        p.instance_queries()
-        + p.advice_queries()
+        [q for t in T for q in p.instance_queries(t)]
+        + [q for t in T for q in p.advice_queries(t)]
         + p.fixed_queries()
         + [p.random_query()]
         + p.permutation_fixed_queries()
-        + p.permutation_z_queries(True)
+        + [q for t in T for q in p.permutation_z_queries(True, t)]
+        + [q for t in T for q in p.lookup_queries(True, t)]
     )
     queries = (
-        p.instance_queries()
-        + p.advice_queries()
-        + p.permutation_z_queries(False)
+        [
+            q
+            for t in T
+            for q in p.instance_queries(t) + p.advice_queries(t) + p.permutation_z_queries(False, t) + p.lookup_queries(False, t)
+        ]
         + p.fixed_queries()
         + p.permutation_fixed_queries()
         + [p.quotient_query()]
@@ -268,7 +356,7 @@ def compile_protocol(k, cs: ConstraintSystemShape, preprocessed, transcript_init
         transcript_initial_state=transcript_initial_state,
         instance_committing_key=None,
         linearization=None,
-        accumulator_indices=[],
+        accumulator_indices=p.accumulator_indices(accumulator_indices) if accumulator_indices else [],
     )
 
 

@@ -209,3 +209,40 @@ def test_compiler_and_tape_evm_transcript(lib, scheme, mos):
     exp = [c.v for c in proof.challenges] + [proof.z.v]
     exp += [proof.pcs.mu.v, proof.pcs.gamma.v, proof.pcs.z_prime.v] if scheme == "bdfg21" else [proof.pcs.v.v, proof.pcs.u.v]
     assert rd(ch, info[3]) == exp and info[5] == len(pf) and info[6] == 0xFFFFFFFF
+
+
+@pytest.mark.parametrize("scheme,mos", [("bdfg21", 0), ("gwc19", 1)])
+def test_compiler_general_protocol(lib, scheme, mos):
+    """The tape compiler on a protocol beyond StandardPlonk: lookup argument, two advice phases with a user
+    challenge, rotations, two permutation grand products, num_proof = 2 (system/halo2.rs:199-243, 372-408, 593-668;
+    verifier/plonk/proof.rs:179-318).  Challenges and the evaluated accumulator Msm equal the oracle's."""
+    from .util import lookup_two_phase_shape
+
+    S = forge.Setup(3, shape=lookup_two_phase_shape(), num_instance=[2], num_proof=2)
+    P_ = S.protocol
+    blob = to_product_protocol(P_).to_bytes()
+    inst, pf = forge.forge_proof(S, scheme, 9)
+    accs, proof = api.succinct_verify(S.dk.svk, P_, inst, pf, scheme, want_proof=True)
+    ch, sc = (ctypes.c_uint32 * (8 * 64))(), (ctypes.c_uint32 * (8 * 512))()
+    terms, info, err = (ctypes.c_int * 1500)(), (ctypes.c_longlong * 10)(), ctypes.create_string_buffer(256)
+    instb = b"".join(int(x).to_bytes(32, "little") for col in inst for x in col)
+    nt = lib.host_compile_run(blob, len(blob), mos, pf, len(pf), instb, len(instb) // 32, ch, sc, terms, 500, info, err, 256)
+    assert nt > 0, err.value
+    assert info[5] == len(pf) and info[6] == 0xFFFFFFFF and info[7] == 1 and info[4] <= 512 and info[3] <= 64
+    exp_ch = [c.v for c in proof.challenges] + [proof.z.v]
+    exp_ch += [proof.pcs.mu.v, proof.pcs.gamma.v, proof.pcs.z_prime.v] if scheme == "bdfg21" else [proof.pcs.v.v, proof.pcs.u.v]
+    assert rd(ch, info[3]) == exp_ch
+    npre = len(P_.preprocessed)
+    n_first = sum(P_.num_witness) + P_.quotient.num_chunk()
+    offs = [32 * i for i in range(n_first)]
+    tail = 32 * (n_first + len(P_.evaluations))
+    offs += [tail + 32 * i for i in range((len(pf) - tail) // 32)]
+    pts = [bn254.g1_from_bytes(pf[o : o + 32])[1] for o in offs]
+    assert info[9] == len(pts)
+    res = [None, None]
+    scal = rd(sc, info[4])
+    for t in range(nt):
+        which, base, slot = terms[3 * t], terms[3 * t + 1], terms[3 * t + 2]
+        b = bn254.G1_GEN if base == -1 else (P_.preprocessed[base] if base < npre else pts[base - npre])
+        res[which] = bn254.g1_add(res[which], bn254.g1_mul(b, 1 if slot < 0 else scal[slot]))
+    assert res[0] == accs[0].lhs.pt and res[1] == accs[0].rhs.pt

@@ -85,3 +85,43 @@ def to_product_protocol(op):
         linearization=lin,
         accumulator_indices=[list(x) for x in op.accumulator_indices],
     )
+
+
+def lookup_two_phase_shape():
+    """A circuit shape exercising what StandardPlonk does not (system/halo2.rs:199-243, 372-408, 419-449, 593-655):
+    two advice phases with a user challenge between them, rotations -1 / +1, a lookup argument with two compressed
+    expressions, an instance column inside the permutation argument, and enough permutation columns for two grand-product
+    polynomials (degree 5 => chunks of 3)."""
+    from oracle.halo2_system import ConstraintSystemShape
+
+    def S(x, y):
+        return ("sum", x, y)
+
+    def M(x, y):
+        return ("product", x, y)
+
+    a, b, c, d = (("advice", i, 0) for i in range(4))
+    a_next, c_prev = ("advice", 0, 1), ("advice", 2, -1)
+    q, t0, q_lookup = (("fixed", i, 0) for i in range(3))
+    inst = ("instance", 0, 0)
+    ch = ("challenge", 0)
+    gates = [
+        M(q, S(M(a, b), ("neg", c))),
+        M(q, S(d, ("neg", M(ch, a_next)))),
+        S(("scaled", M(q, c_prev), 7), S(M(M(ch, ch), b), inst)),
+    ]
+    return ConstraintSystemShape(
+        num_fixed=3,
+        num_advice=4,
+        num_instance_columns=1,
+        permutation_columns=[("advice", 0), ("advice", 1), ("advice", 2), ("instance", 0)],
+        advice_queries=[(0, 0), (1, 0), (2, 0), (3, 0), (0, 1), (2, -1)],
+        fixed_queries=[(0, 0), (1, 0), (2, 0)],
+        instance_queries=[(0, 0)],
+        gates=gates,
+        degree=5,
+        blinding_factors=5,
+        advice_column_phase=[0, 0, 1, 1],
+        challenge_phase=[0],
+        lookups=[([M(q_lookup, a), M(q_lookup, b)], [t0, M(t0, t0)])],
+    )
