@@ -88,6 +88,15 @@ int svk_kzg_decide_batch_dev(svk_ctx* ctx, int dk, size_t n, const void* d_accs,
  * reference would reject with Error::InvalidProtocol still compiles; its proofs get that status. */
 int svk_protocol_compile(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos, int dk); /* Poseidon transcript */
 int svk_protocol_compile_ex(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos, int transcript_kind, int dk);
+/* The same from the reference's own wire format: `bincode::serialize(&protocol)` of a `PlonkProtocol<G1Affine>` (bincode 1.3.3 default
+ * options: what `Snark` files hold, snark-verifier-sdk/src/lib.rs:44-50, sdk/src/halo2.rs:262-269) -- the call a Rust shim
+ * makes.  fe_encoding: how halo2curves' serde writes Fr / Fq -- SVK_FE_MONTGOMERY (raw `[u64; 4]` Montgomery
+ * limbs, the `derive_serde` of halo2curves 0.3.x), SVK_FE_CANONICAL (32-byte LE `to_repr`), SVK_FE_AUTO (whichever makes
+ * `domain.n_inv * n == 1`).  *consumed (may be NULL) = bytes of `bytes` the protocol occupied, so that the `instances` and
+ * `proof` fields of a `Snark` that follow can be located.  The accumulator encoding is `LimbsEncoding<3, 88>` (sdk/src/lib.rs:33-40). */
+enum { SVK_FE_AUTO = 0, SVK_FE_MONTGOMERY = 1, SVK_FE_CANONICAL = 2 };
+int svk_protocol_compile_bincode(svk_ctx* ctx, const uint8_t* bytes, size_t len, int fe_encoding, int mos, int transcript_kind, int dk,
+                                 size_t* consumed, int* fe_used /* may be NULL: the encoding AUTO settled on */);
 /* out[20] = { proof_len, n_instances, n_challenges, n_regs, n_ops, n_poseidon_perms, verify_valid,
  *             n_fr_mul, n_lhs_terms, n_rhs_terms, n_points, n_scalar_slots, msm_modmul_per_proof (all three MSM
  *             kernels), msm_var_modmul_per_proof (k_msm_var only), n_var_terms, var_lanes,

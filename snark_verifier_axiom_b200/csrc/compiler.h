@@ -188,6 +188,19 @@ struct ProtocolDesc {
   }
 };
 
+inline void validate_accumulator_indices(const ProtocolDesc& p) {
+  if (p.accumulator_indices.empty()) return;
+  if (p.acc_limbs == 0 || p.acc_bits == 0 || (p.acc_limbs - 1) * p.acc_bits + 256 > 1024)
+    throw CompileError(-1, "LimbsEncoding parameters out of range");
+  for (auto& v : p.accumulator_indices) {
+    // `assert_eq!(limbs.len(), 4 * LIMBS)` (accumulator.rs:61) and `instances[i][j]` (proof.rs:139-146) panic in the reference
+    if (v.size() != 4 * (size_t)p.acc_limbs) throw CompileError(-1, "accumulator_indices entry must name 4 * LIMBS instances");
+    for (auto& ij : v)
+      if (ij.first >= p.num_instance.size() || ij.second >= p.num_instance[ij.first])
+        throw CompileError(-1, "accumulator index out of the instance ranges");
+  }
+}
+
 inline ProtocolDesc parse_protocol(const uint8_t* blob, size_t len) {
   Reader r(blob, len);
   if (r.u32_() != 0x504b5653u) throw CompileError(-1, "bad magic (want 'SVKP')");
@@ -229,18 +242,160 @@ inline ProtocolDesc parse_protocol(const uint8_t* blob, size_t len) {
     p.acc_limbs = r.u8_();
     p.acc_bits = r.u8_();
   }
-  if (!p.accumulator_indices.empty()) {
-    if (p.acc_limbs == 0 || p.acc_bits == 0 || (p.acc_limbs - 1) * p.acc_bits + 256 > 1024)
-      throw CompileError(-1, "LimbsEncoding parameters out of range");
-    for (auto& v : p.accumulator_indices) {
-      // `assert_eq!(limbs.len(), 4 * LIMBS)` (accumulator.rs:61) and `instances[i][j]` (proof.rs:139-146) panic in the reference
-      if (v.size() != 4 * (size_t)p.acc_limbs) throw CompileError(-1, "accumulator_indices entry must name 4 * LIMBS instances");
-      for (auto& ij : v)
-        if (ij.first >= p.num_instance.size() || ij.second >= p.num_instance[ij.first])
-          throw CompileError(-1, "accumulator index out of the instance ranges");
-    }
-  }
+  validate_accumulator_indices(p);
   return p;
+}
+
+// ---- the reference's own wire format: `bincode::serialize(&PlonkProtocol<G1Affine>)` ----------------------------------------
+// bincode 1.3.3 with default options (snark-verifier-sdk/Cargo.toml:18; `bincode::deserialize_from`, sdk/src/halo2.rs:262-269):
+// fixed-width little-endian integers, usize as u64, enum variant index as u32, Option as one tag byte, Vec as u64 length +
+// elements, structs / tuples / Box as the plain concatenation of their fields in declaration order.  Field order from the
+// serde derives: PlonkProtocol (verifier/plonk/protocol.rs:20-63), Domain (util/arithmetic.rs:130-142), Query (:296-300),
+// Rotation (arithmetic.rs:99-100), QuotientPolynomial (:281-285), Expression (:308-319), CommonPolynomial (:180-185),
+// LinearizationStrategy (:503-513), InstanceCommittingKey (:515-519).
+// Field elements: halo2curves' `derive_serde` representation is NOT in the tree (Cargo.lock:1803-1826).  Two encodings are
+// accepted: SVK_FE_MONTGOMERY = the derived `Fr([u64; 4])` / `G1Affine { x, y }` (raw Montgomery limbs, R = 2^256 -- the 0.3.x
+// derive as far as it can be recalled without the source) and SVK_FE_CANONICAL = 32-byte little-endian `to_repr()` (later
+// halo2curves).  SVK_FE_AUTO picks the one under which `domain.n_inv * n == 1`.  FORMAT UNPINNED: no reference-written
+// file exists in the tree to check against; tests round-trip through a writer that follows the same rules.
+// SVK_FE_AUTO / SVK_FE_MONTGOMERY / SVK_FE_CANONICAL: include/svk.h
+
+struct BincodeReader {
+  Reader r;
+  int fe;
+  BincodeReader(const uint8_t* p, size_t n, int fe_) : r(p, n), fe(fe_) {}
+  u64 u64_() {
+    u64 lo = r.u32_(), hi = r.u32_();
+    return lo | (hi << 32);
+  }
+  u32 len_(u64 max) {
+    u64 v = u64_();
+    if (v > max) throw CompileError(-1, "bincode: length out of range");
+    return (u32)v;
+  }
+  u32 usize_() { return len_(0xffffffffull); }
+  bool option_() {
+    uint8_t t = r.u8_();
+    if (t > 1) throw CompileError(-1, "bincode: bad Option tag");
+    return t == 1;
+  }
+  template <class F>
+  F fe_() {  // -> Montgomery form
+    F x;
+    uint8_t b[32];
+    r.bytes(b, 32);
+    fe_load_le(x.v, b);
+    if (!F::is_canonical(x.v)) throw CompileError(-1, "bincode: field element out of range");
+    return fe == SVK_FE_CANONICAL ? x.to_mont() : x;
+  }
+  svk_g1 g1_() {  // -> canonical bytes (identity = zeros in both encodings)
+    Fq x = fe_<Fq>().from_mont(), y = fe_<Fq>().from_mont();
+    svk_g1 g;
+    fe_store_le(g.x.b, x.v);
+    fe_store_le(g.y.b, y.v);
+    return g;
+  }
+  Query query_() {
+    Query q;
+    q.poly = usize_();
+    q.rot = r.i32_();
+    return q;
+  }
+};
+
+inline std::unique_ptr<Expr> parse_expr_bincode(BincodeReader& b, int depth = 0) {
+  if (depth > 20000) throw CompileError(-1, "expression too deep");
+  auto e = std::make_unique<Expr>();
+  u32 v = b.r.u32_();
+  switch (v) {
+    case 0: e->tag = Expr::CONST; e->c = b.fe_<Fr>(); break;
+    case 1: {
+      u32 cp = b.r.u32_();
+      if (cp == 0) e->tag = Expr::IDENTITY;
+      else if (cp == 1) { e->tag = Expr::LAGRANGE; e->i = b.r.i32_(); }
+      else throw CompileError(-1, "bincode: bad CommonPolynomial variant");
+      break;
+    }
+    case 2: e->tag = Expr::POLY; e->q = b.query_(); break;
+    case 3: e->tag = Expr::CHALLENGE; e->i = (int32_t)b.usize_(); break;
+    case 4: e->tag = Expr::NEG; e->kids.push_back(parse_expr_bincode(b, depth + 1)); break;
+    case 5:
+    case 6:
+      e->tag = v == 5 ? Expr::SUM : Expr::PRODUCT;
+      e->kids.push_back(parse_expr_bincode(b, depth + 1));
+      e->kids.push_back(parse_expr_bincode(b, depth + 1));
+      break;
+    case 7:
+      e->tag = Expr::SCALED;
+      e->kids.push_back(parse_expr_bincode(b, depth + 1));
+      e->c = b.fe_<Fr>();
+      break;
+    case 8: {
+      e->tag = Expr::DISTRIBUTE;
+      u32 n = b.len_(65536);
+      if (n == 0) throw CompileError(-1, "bad DistributePowers arity");
+      for (u32 k = 0; k < n + 1; k++) e->kids.push_back(parse_expr_bincode(b, depth + 1));
+      break;
+    }
+    default: throw CompileError(-1, "bincode: bad Expression variant");
+  }
+  return e;
+}
+
+inline ProtocolDesc parse_protocol_bincode_as(const uint8_t* bytes, size_t len, int fe, size_t* consumed) {
+  BincodeReader b(bytes, len, fe);
+  ProtocolDesc p;
+  p.k = b.usize_();
+  if (p.k > 28) throw CompileError(-1, "domain k > 28");
+  p.n = 1ull << p.k;
+  if (b.u64_() != p.n) throw CompileError(-1, "bincode: domain.n != 2^k");
+  p.n_inv = b.fe_<Fr>();
+  p.gen = b.fe_<Fr>();
+  p.gen_inv = b.fe_<Fr>();
+  if (!(p.n_inv * fr_from_u64(p.n) == Fr::one()) || !(p.gen * p.gen_inv == Fr::one()))
+    throw CompileError(-3, "bincode: inconsistent Domain (wrong field-element encoding?)");
+  for (u32 i = b.len_(1 << 16); i--;) p.preprocessed.push_back(b.g1_());
+  for (u32 i = b.len_(1 << 16); i--;) p.num_instance.push_back(b.usize_());
+  for (u32 i = b.len_(1 << 16); i--;) p.num_witness.push_back(b.usize_());
+  for (u32 i = b.len_(1 << 16); i--;) p.num_challenge.push_back(b.usize_());
+  for (u32 i = b.len_(1 << 20); i--;) p.evaluations.push_back(b.query_());
+  for (u32 i = b.len_(1 << 20); i--;) p.queries.push_back(b.query_());
+  p.chunk_degree = b.usize_();
+  if (p.chunk_degree == 0) throw CompileError(-1, "chunk_degree == 0");
+  p.numerator = parse_expr_bincode(b);
+  p.has_initial_state = b.option_();
+  if (p.has_initial_state) p.initial_state = b.fe_<Fr>();
+  if (b.option_()) throw CompileError(-1, "instance_committing_key is not supported on the KZG path (SURVEY App. A)");
+  p.linearization = 0;
+  if (b.option_()) {
+    u32 v = b.r.u32_();
+    if (v > 1) throw CompileError(-1, "bincode: bad LinearizationStrategy variant");
+    p.linearization = (uint8_t)(v + 1);
+  }
+  for (u32 i = b.len_(1 << 16); i--;) {
+    std::vector<std::pair<u32, u32>> v;
+    for (u32 j = b.len_(1 << 16); j--;) { u32 a = b.usize_(), c = b.usize_(); v.push_back({a, c}); }
+    p.accumulator_indices.push_back(v);
+  }
+  validate_accumulator_indices(p);
+  if (consumed) *consumed = b.r.pos;
+  return p;
+}
+
+inline ProtocolDesc parse_protocol_bincode(const uint8_t* bytes, size_t len, int fe_encoding, size_t* consumed, int* fe_used = nullptr) {
+  if (fe_encoding < 0 || fe_encoding > 2) throw CompileError(-1, "unknown field-element encoding");
+  if (fe_encoding != SVK_FE_AUTO) {
+    if (fe_used) *fe_used = fe_encoding;
+    return parse_protocol_bincode_as(bytes, len, fe_encoding, consumed);
+  }
+  try {
+    if (fe_used) *fe_used = SVK_FE_MONTGOMERY;
+    return parse_protocol_bincode_as(bytes, len, SVK_FE_MONTGOMERY, consumed);
+  } catch (CompileError& e) {
+    if (e.kind != -3 && std::string(e.what()).find("out of range") == std::string::npos) throw;
+  }
+  if (fe_used) *fe_used = SVK_FE_CANONICAL;
+  return parse_protocol_bincode_as(bytes, len, SVK_FE_CANONICAL, consumed);
 }
 
 // ------------------------------------------------------------------ symbolic scalars + tape builder
@@ -1128,10 +1283,19 @@ class Compiler {
   }
 };
 
+inline CompiledProtocol compile_protocol_desc(const ProtocolDesc& p, int mos, int transcript_kind);
 inline CompiledProtocol compile_protocol(const uint8_t* blob, size_t len, int mos, int transcript_kind = 0) {
+  ProtocolDesc p = parse_protocol(blob, len);
+  return compile_protocol_desc(p, mos, transcript_kind);
+}
+inline CompiledProtocol compile_protocol_bincode(const uint8_t* bytes, size_t len, int fe_encoding, int mos, int transcript_kind,
+                                                 size_t* consumed, int* fe_used = nullptr) {
+  ProtocolDesc p = parse_protocol_bincode(bytes, len, fe_encoding, consumed, fe_used);
+  return compile_protocol_desc(p, mos, transcript_kind);
+}
+inline CompiledProtocol compile_protocol_desc(const ProtocolDesc& p, int mos, int transcript_kind) {
   if (mos != SVK_MOS_BDFG21 && mos != SVK_MOS_GWC19) throw CompileError(-1, "unknown multi-open scheme");
   if (transcript_kind != 0 && transcript_kind != 1) throw CompileError(-1, "unknown transcript kind");
-  ProtocolDesc p = parse_protocol(blob, len);
   Compiler c(p, mos, transcript_kind);
   CompiledProtocol out = c.run();
   out.transcript_kind = transcript_kind;

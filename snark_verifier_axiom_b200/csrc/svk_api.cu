@@ -239,6 +239,8 @@ int svk_protocol_compile(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos,
   return svk_protocol_compile_ex(ctx, blob, len, mos, SVK_TRANSCRIPT_POSEIDON, dk);
 }
 
+static int protocol_upload(svk_ctx* ctx, svk_host::CompiledProtocol& cp, int mos, int transcript_kind, int dk);
+
 int svk_protocol_compile_ex(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos, int transcript_kind, int dk) {
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   if (dk < 0 || dk >= (int)ctx->dks.size()) return svk_fail(ctx, "bad deciding-key id %d", dk);
@@ -248,6 +250,23 @@ int svk_protocol_compile_ex(svk_ctx* ctx, const uint8_t* blob, size_t len, int m
   } catch (svk_host::CompileError& e) {
     return svk_fail(ctx, "protocol compile: %s", e.what());
   }
+  return protocol_upload(ctx, cp, mos, transcript_kind, dk);
+}
+
+int svk_protocol_compile_bincode(svk_ctx* ctx, const uint8_t* bytes, size_t len, int fe_encoding, int mos, int transcript_kind, int dk,
+                                 size_t* consumed, int* fe_used) {
+  SVK_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (dk < 0 || dk >= (int)ctx->dks.size()) return svk_fail(ctx, "bad deciding-key id %d", dk);
+  svk_host::CompiledProtocol cp;
+  try {
+    cp = svk_host::compile_protocol_bincode(bytes, len, fe_encoding, mos, transcript_kind, consumed, fe_used);
+  } catch (svk_host::CompileError& e) {
+    return svk_fail(ctx, "protocol compile (bincode): %s", e.what());
+  }
+  return protocol_upload(ctx, cp, mos, transcript_kind, dk);
+}
+
+static int protocol_upload(svk_ctx* ctx, svk_host::CompiledProtocol& cp, int mos, int transcript_kind, int dk) {
   ProtocolDevice* pd = new ProtocolDevice();
   pd->mos = mos;
   pd->transcript_kind = transcript_kind;

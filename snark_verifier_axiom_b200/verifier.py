@@ -18,13 +18,15 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 from ._lib import SvkError, lib
-from .protocol import PlonkProtocol
+from .protocol import FR_MODULUS, PlonkProtocol
 
 SHPLONK = BDFG21 = 0
 GWC = GWC19 = 1
 POSEIDON_TRANSCRIPT = 0  # sdk `PoseidonTranscript` (snark-verifier-sdk/src/halo2.rs:58-67)
 EVM_TRANSCRIPT = 1       # Keccak `EvmTranscript` (snark-verifier/src/system/halo2/transcript/evm.rs)
 
+FE_AUTO, FE_MONTGOMERY, FE_CANONICAL = 0, 1, 2  # include/svk.h SVK_FE_*
+_R_INV = pow(1 << 256, -1, FR_MODULUS)
 STATUS_NAMES = {0: "Ok", 1: "InvalidInstances", 2: "InvalidProtocol", 3: "AssertionFailure", 4: "Transcript", 5: "AccumulatorPanic"}
 
 
@@ -144,6 +146,14 @@ class Context:
         blob = protocol.to_bytes()
         return self._check(self._L.svk_protocol_compile_ex(self._c, blob, len(blob), mos, transcript, dk_id))
 
+    def compile_protocol_bincode(self, data: bytes, mos: int, dk_id: int, transcript: int = 0, fe_encoding: int = 0):
+        """`bincode::serialize(&PlonkProtocol<G1Affine>)` bytes (the head of a `Snark` file) -> (protocol id, bytes consumed,
+        field-element encoding used).  include/svk.h `svk_protocol_compile_bincode`."""
+        consumed, fe_used = ctypes.c_size_t(0), ctypes.c_int(0)
+        pid = self._check(self._L.svk_protocol_compile_bincode(self._c, data, len(data), fe_encoding, mos, transcript, dk_id,
+                                                                ctypes.byref(consumed), ctypes.byref(fe_used)))
+        return pid, consumed.value, fe_used.value
+
     def protocol_info(self, pid: int) -> dict:
         out = (ctypes.c_uint32 * 20)()
         self._check(self._L.svk_protocol_info(self._c, pid, out))
@@ -213,15 +223,52 @@ class BatchResult:
 class PlonkVerifier:
     """`PlonkVerifier<KzgAs<Bn256, MOS>>` / `PlonkSuccinctVerifier<..>` for ONE protocol, over batches."""
 
-    def __init__(self, ctx: Context, dk: KzgDecidingKey, protocol: PlonkProtocol, mos: int = SHPLONK, kzg_as: Optional[KzgAs] = None,
-                 transcript: int = POSEIDON_TRANSCRIPT):
+    def __init__(self, ctx: Context, dk: KzgDecidingKey, protocol: Optional[PlonkProtocol], mos: int = SHPLONK, kzg_as: Optional[KzgAs] = None,
+                 transcript: int = POSEIDON_TRANSCRIPT, _pid: Optional[int] = None):
         self.ctx = ctx
         self.kzg_as = kzg_as or KzgAs(ctx, dk)
         self.mos = mos
         self.transcript = transcript
-        self.pid = ctx.compile_protocol(protocol, mos, self.kzg_as.dk_id, transcript)
+        self.pid = ctx.compile_protocol(protocol, mos, self.kzg_as.dk_id, transcript) if _pid is None else _pid
         self.info = ctx.protocol_info(self.pid)
         self.protocol = protocol
+
+    @classmethod
+    def from_snark_bincode(cls, ctx: Context, dk: KzgDecidingKey, data: bytes, mos: int = SHPLONK, kzg_as: Optional[KzgAs] = None,
+                           transcript: int = POSEIDON_TRANSCRIPT, fe_encoding: int = FE_AUTO):
+        """`read_snark` (snark-verifier-sdk/src/halo2.rs:262-269): a bincode `Snark { protocol, instances, proof }`
+        (sdk/src/lib.rs:44-50) -> (verifier for its protocol, Snark).  The protocol is parsed and compiled by the library
+        itself (`svk_protocol_compile_bincode`); only the two trailing vectors are read here.  As the reference warns, the
+        caller must know which multi-open scheme the snark was made with."""
+        kzg_as = kzg_as or KzgAs(ctx, dk)
+        pid, pos, fe_used = ctx.compile_protocol_bincode(data, mos, kzg_as.dk_id, transcript, fe_encoding)
+        pv = cls(ctx, dk, None, mos, kzg_as, transcript, _pid=pid)
+
+        def u64():
+            nonlocal pos
+            if pos + 8 > len(data):
+                raise ValueError("snark file truncated")
+            v = int.from_bytes(data[pos : pos + 8], "little")
+            pos += 8
+            return v
+
+        def fr():
+            nonlocal pos
+            if pos + 32 > len(data):
+                raise ValueError("snark file truncated")
+            v = int.from_bytes(data[pos : pos + 32], "little")
+            pos += 32
+            if v >= FR_MODULUS:
+                raise ValueError("instance out of range")
+            return v * _R_INV % FR_MODULUS if fe_used == FE_MONTGOMERY else v
+
+        instances = []
+        for _ in range(u64()):
+            instances.append([fr() for _ in range(u64())])
+        n = u64()
+        if pos + n > len(data):
+            raise ValueError("snark file truncated")
+        return pv, Snark(instances, bytes(data[pos : pos + n]))
 
     # ---- packing ------------------------------------------------------------------------------
     def pack(self, snarks: Sequence[Snark]):

@@ -201,6 +201,32 @@ int host_compile_run_ex(const uint8_t* blob, size_t blob_len, int mos, int trans
 }
 
 extern "C" {
+// Compiles the same protocol from the library's blob and from the reference's bincode form; returns 1 when the two compiled
+// tapes are identical (ops, constants, aux tables, point schedule, Msm terms, old-accumulator indices), 0 when they differ,
+// < 0 on a parse error.  *consumed / *fe_used as in svk_protocol_compile_bincode.
+int host_compile_compare_bincode(const uint8_t* blob, size_t blob_len, const uint8_t* bytes, size_t len, int fe_encoding, int mos,
+                                 int transcript_kind, size_t* consumed, int* fe_used, char* errbuf, int errbuf_len) {
+  try {
+    svk_host::CompiledProtocol a = svk_host::compile_protocol(blob, blob_len, mos, transcript_kind);
+    svk_host::CompiledProtocol b = svk_host::compile_protocol_bincode(bytes, len, fe_encoding, mos, transcript_kind, consumed, fe_used);
+    bool same = a.ops.size() == b.ops.size() && a.consts.size() == b.consts.size() && a.aux == b.aux && a.n_regs == b.n_regs &&
+                a.proof_len == b.proof_len && a.num_instance == b.num_instance && a.n_challenges == b.n_challenges &&
+                a.lhs.size() == b.lhs.size() && a.rhs.size() == b.rhs.size() && a.old_acc_idx == b.old_acc_idx &&
+                a.preprocessed.size() == b.preprocessed.size() && a.points.size() == b.points.size() && a.verify_valid == b.verify_valid;
+    if (!same) return 0;
+    if (memcmp(a.ops.data(), b.ops.data(), a.ops.size() * sizeof(TapeOp))) return 0;
+    if (memcmp(a.consts.data(), b.consts.data(), a.consts.size() * sizeof(Fr))) return 0;
+    if (a.preprocessed.size() && memcmp(a.preprocessed.data(), b.preprocessed.data(), a.preprocessed.size() * sizeof(svk_g1))) return 0;
+    for (size_t i = 0; i < a.lhs.size(); i++) if (a.lhs[i].base != b.lhs[i].base || a.lhs[i].slot != b.lhs[i].slot) return 0;
+    for (size_t i = 0; i < a.rhs.size(); i++) if (a.rhs[i].base != b.rhs[i].base || a.rhs[i].slot != b.rhs[i].slot) return 0;
+    for (size_t i = 0; i < a.points.size(); i++) if (a.points[i].byte_offset != b.points[i].byte_offset) return 0;
+    return 1;
+  } catch (svk_host::CompileError& e) {
+    snprintf(errbuf, errbuf_len, "%s", e.what());
+    return -1;
+  }
+}
+
 // returns 1 if cyclotomic_sqr == sqr on an element of the cyclotomic subgroup built from random input limbs
 int host_cyclotomic_check(const u32* limbs96) {
   static PairingConsts k = svk_host::make_pairing_consts();

@@ -61,3 +61,34 @@ def test_general_protocol_matches_oracle(env, scheme, mos, transcript):
     res = pv.verify(good + [snarks[1]], group_size=0)
     assert not res.ok and [int(x) for x in res.status] == [0, 0, 0, 0, 0, 3]
     assert api.status_of(api.verify, S.dk, S.protocol, insts[1], bytes(proofs[1]), scheme, transcript=transcript) == 3
+
+
+@pytest.mark.parametrize("fe", ["montgomery", "canonical"])
+def test_snark_file_ingestion(env, fe):
+    """`read_snark` + `PlonkVerifier::verify` on a bincode `Snark` (sdk/src/halo2.rs:262-269, sdk/src/lib.rs:44-50): the protocol
+    travels in the reference's own wire format and is compiled by the library."""
+    from oracle import bincode as obc
+
+    V, S, ctx, dk, AS, proto = env
+    inst, proof = forge.forge_proof(S, "bdfg21", 77)
+    data = obc.serialize_snark(S.protocol, inst, proof, fe)
+    pv, snark = V.PlonkVerifier.from_snark_bincode(ctx, dk, data, V.SHPLONK, kzg_as=AS)
+    assert snark.instances == inst and snark.proof == proof
+    assert pv.info["proof_len"] == len(proof) and pv.info["n_instances"] == 4
+    pv.verify_one(snark)
+    accs, _, st = pv.succinct_verify([snark])
+    o = api.succinct_verify(S.dk.svk, S.protocol, inst, proof, "bdfg21")
+    assert int(st[0]) == 0 and (accs[0].lhs, accs[0].rhs) == (o[0].lhs.pt, o[0].rhs.pt)
+    bad = bytearray(proof)
+    bad[-1] ^= 1
+    with pytest.raises(V.Error):
+        pv.verify_one(V.Snark(inst, bytes(bad)))
+    # an aggregation-shaped snark: old accumulators named by the protocol inside the file
+    S2 = forge.Setup(0, num_instance=14, accumulator_indices=[[(0, 1 + i) for i in range(12)]])
+    dk2 = V.KzgDecidingKey.new(S2.dk.svk.g, S2.dk.g2, S2.dk.s_g2)
+    inst2, proof2 = forge.forge_proof(S2, "gwc19", 78)
+    pv2, snark2 = V.PlonkVerifier.from_snark_bincode(ctx, dk2, obc.serialize_snark(S2.protocol, inst2, proof2, fe), V.GWC)
+    assert pv2.info["n_old_accumulators"] == 1
+    pv2.verify_one(snark2)
+    with pytest.raises(Exception):
+        V.PlonkVerifier.from_snark_bincode(ctx, dk, data[: len(data) // 2], V.SHPLONK, kzg_as=AS)

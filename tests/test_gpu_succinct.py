@@ -47,7 +47,7 @@ def test_succinct_verify_matches_oracle(env, scheme, mos):
     L, c, S, kid, blob = env
     pid = L.svk_protocol_compile(c, blob, len(blob), mos, kid)
     assert pid >= 0, L.svk_last_error(c)
-    info = (ctypes.c_uint32 * 16)()
+    info = (ctypes.c_uint32 * 20)()
     assert L.svk_protocol_info(c, pid, info) == 0
     plen, n_inst, n_ch = info[0], info[1], info[2]
     assert plen == (896 if scheme == "bdfg21" else 928) and n_inst == 1

@@ -246,3 +246,30 @@ def test_compiler_general_protocol(lib, scheme, mos):
         b = bn254.G1_GEN if base == -1 else (P_.preprocessed[base] if base < npre else pts[base - npre])
         res[which] = bn254.g1_add(res[which], bn254.g1_mul(b, 1 if slot < 0 else scal[slot]))
     assert res[0] == accs[0].lhs.pt and res[1] == accs[0].rhs.pt
+
+
+@pytest.mark.parametrize("fe,fe_id", [("montgomery", 1), ("canonical", 2)])
+def test_protocol_bincode_ingestion(lib, fe, fe_id):
+    """`bincode::serialize(&PlonkProtocol)` (the head of a `Snark` file, sdk/src/lib.rs:44-50, sdk/src/halo2.rs:262-269) compiles
+    to the same tape as the library's own blob; AUTO detects the field-element encoding; truncation is an error."""
+    from oracle import bincode as obc
+
+    from .util import lookup_two_phase_shape
+
+    cases = [forge.Setup(0), forge.Setup(0, num_instance=14, accumulator_indices=[[(0, 1 + i) for i in range(12)]]),
+             forge.Setup(3, shape=lookup_two_phase_shape(), num_instance=[2], num_proof=2)]
+    for S in cases:
+        blob = to_product_protocol(S.protocol).to_bytes()
+        data = obc.serialize_protocol(S.protocol, fe)
+        tail = b"trailing snark fields"
+        for enc in (0, fe_id):
+            for mos in (0, 1):
+                consumed, used, err = ctypes.c_size_t(0), ctypes.c_int(0), ctypes.create_string_buffer(256)
+                rc = lib.host_compile_compare_bincode(blob, len(blob), data + tail, len(data) + len(tail), enc, mos, 0,
+                                                      ctypes.byref(consumed), ctypes.byref(used), err, 256)
+                assert rc == 1, err.value
+                assert consumed.value == len(data) and used.value == fe_id
+        consumed, used, err = ctypes.c_size_t(0), ctypes.c_int(0), ctypes.create_string_buffer(256)
+        assert lib.host_compile_compare_bincode(blob, len(blob), data, len(data) - 9, 0, 0, 0, ctypes.byref(consumed), ctypes.byref(used), err, 256) == -1
+        wrong = 3 - fe_id  # forcing the other encoding: inconsistent Domain (or an out-of-range element)
+        assert lib.host_compile_compare_bincode(blob, len(blob), data, len(data), wrong, 0, 0, ctypes.byref(consumed), ctypes.byref(used), err, 256) == -1
