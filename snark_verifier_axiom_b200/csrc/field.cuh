@@ -201,7 +201,117 @@ struct Fe {
 #else
   HD friend Fe operator*(const Fe& a, const Fe& b) { return mul_inline(a, b); }
 #endif
-  HD Fe sqr() const { return (*this) * (*this); }
+  // ---- Montgomery squaring: 36 + 64 wide MACs instead of 128 ------------------------------------------------------
+  // (1) the 28 off-diagonal products a_i a_j (i < j) go to two 16-limb accumulators by column parity (E: pairs at even
+  //     columns, O: pairs at odd columns, O[k] = column k + 1), one carry chain per (row, parity); rows ascend, so the limb
+  //     that receives a chain's carry-out holds only earlier carry-outs at that moment (no ripple);
+  // (2) T = 2 (E + (O << 32)) + sum_i a_i^2 2^(64 i)   (one add chain, one funnel-shift pass, one 8-MAC chain);
+  // (3) U = (T_lo + M p) / 2^256 by eight pure reduction rows (the two-limb shift of the `of` accumulator is fused into the
+  //     m p MACs), result = U + T_hi < 1.19 p + 1, one conditional subtraction.
+  HD static void redc_row(u32* al, u32* of, bool first) {
+    if (first) {
+      u32 mi = al[0] * P::M0;
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        of[j] = ptx::mul_lo(P::mod(j + 1), mi);
+        of[j + 1] = ptx::mul_hi(P::mod(j + 1), mi);
+      }
+      cmad_row_mod(al, 0, mi);
+      of[7] = ptx::addc(of[7], 0);
+    } else {
+      u32 mi = (al[0] + of[1]) * P::M0;
+      al[0] = ptx::add_cc(al[0], of[1]);
+#pragma unroll
+      for (int j = 0; j < 6; j += 2) {
+        of[j] = ptx::madc_lo_cc(P::mod(j + 1), mi, of[j + 2]);
+        of[j + 1] = ptx::madc_hi_cc(P::mod(j + 1), mi, of[j + 3]);
+      }
+      of[6] = ptx::madc_lo_cc(P::mod(7), mi, 0);
+      of[7] = ptx::madc_hi(P::mod(7), mi, 0);
+      cmad_row_mod(al, 0, mi);
+      of[7] = ptx::addc(of[7], 0);
+    }
+  }
+  HD static Fe sqr_inline(const Fe& x) {
+    const u32* a = x.v;
+    u32 E[16], O[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) E[i] = O[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+      // odd columns: j = i+1, i+3, ...   ->  O[i+j-1], O[i+j]
+      {
+        int k = 2 * i;  // O index of column 2i+1
+        O[k] = ptx::mad_lo_cc(a[i], a[i + 1], O[k]);
+        O[k + 1] = ptx::madc_hi_cc(a[i], a[i + 1], O[k + 1]);
+#pragma unroll
+        for (int j = i + 3; j < 8; j += 2) {
+          O[i + j - 1] = ptx::madc_lo_cc(a[i], a[j], O[i + j - 1]);
+          O[i + j] = ptx::madc_hi_cc(a[i], a[j], O[i + j]);
+        }
+        int last = i + 1 + 2 * ((7 - (i + 1)) / 2);  // last j of the chain
+        O[i + last + 1] = ptx::addc(O[i + last + 1], 0);
+      }
+      // even columns: j = i+2, i+4, ...  ->  E[i+j], E[i+j+1]
+      if (i + 2 < 8) {
+        E[2 * i + 2] = ptx::mad_lo_cc(a[i], a[i + 2], E[2 * i + 2]);
+        E[2 * i + 3] = ptx::madc_hi_cc(a[i], a[i + 2], E[2 * i + 3]);
+#pragma unroll
+        for (int j = i + 4; j < 8; j += 2) {
+          E[i + j] = ptx::madc_lo_cc(a[i], a[j], E[i + j]);
+          E[i + j + 1] = ptx::madc_hi_cc(a[i], a[j], E[i + j + 1]);
+        }
+        int last = i + 2 + 2 * ((7 - (i + 2)) / 2);
+        E[i + last + 2] = ptx::addc(E[i + last + 2], 0);
+      }
+    }
+    // S = E + (O << 32); columns 0 and 15 of S are empty (a < 2^254: the off-diagonal sum is < 2^507)
+    u32 T[16];
+    T[0] = 0;
+    T[1] = O[0];
+    T[2] = ptx::add_cc(E[2], O[1]);
+#pragma unroll
+    for (int c = 3; c < 15; c++) T[c] = ptx::addc_cc(E[c], O[c - 1]);
+    T[15] = ptx::addc(E[15], O[14]);
+    // T = 2 S
+#pragma unroll
+    for (int c = 15; c >= 1; c--) T[c] = (T[c] << 1) | (T[c - 1] >> 31);
+    // T += diagonal
+    T[0] = ptx::mul_lo(a[0], a[0]);
+    T[1] = ptx::mad_hi_cc(a[0], a[0], T[1]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) {
+      T[2 * i] = ptx::madc_lo_cc(a[i], a[i], T[2 * i]);
+      T[2 * i + 1] = (i < 7) ? ptx::madc_hi_cc(a[i], a[i], T[2 * i + 1]) : ptx::madc_hi(a[i], a[i], T[2 * i + 1]);
+    }
+    // Montgomery-reduce the low half
+    u32 al[8], of[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) al[i] = T[i];
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      redc_row(al, of, i == 0);
+      redc_row(of, al, false);
+    }
+    Fe r;
+    r.v[0] = ptx::add_cc(al[0], of[1]);
+#pragma unroll
+    for (int j = 1; j < 7; j++) r.v[j] = ptx::addc_cc(al[j], of[j + 1]);
+    r.v[7] = ptx::addc(al[7], 0);
+    // + T_hi
+    r.v[0] = ptx::add_cc(r.v[0], T[8]);
+#pragma unroll
+    for (int j = 1; j < 7; j++) r.v[j] = ptx::addc_cc(r.v[j], T[8 + j]);
+    r.v[7] = ptx::addc(r.v[7], T[15]);
+    reduce_once(r.v);
+    return r;
+  }
+#if defined(__CUDA_ARCH__)
+  static __device__ __noinline__ Fe sqr_call(Fe a) { return sqr_inline(a); }
+  HD Fe sqr() const { return sqr_call(*this); }
+#else
+  HD Fe sqr() const { return sqr_inline(*this); }
+#endif
 
   // ---- fused Montgomery dot products ("lazy reduction"): sum_k a_k * b_k * R^-1 mod p with ONE reduction pass.
   // N products share the 8 reduction rows: 64 N + 72 wide MACs instead of 136 N, and the additions/subtractions a
@@ -309,14 +419,25 @@ struct Fe {
   }
 
   // a^e for a public 256-bit exponent (left-to-right binary; the exponent is uniform across a warp)
+  // 4-bit fixed windows: 252 squarings + <= 63 + 14 products (the table lives in the noinline frame)
   HDN Fe pow(const u32* e) const {
+    Fe tab[16];
+    tab[0] = one();
+    tab[1] = *this;
+#pragma unroll 1
+    for (int i = 2; i < 16; i += 2) {
+      tab[i] = tab[i >> 1].sqr();
+      tab[i + 1] = tab[i] * (*this);
+    }
     Fe r = one();
     bool started = false;
     for (int w = 7; w >= 0; w--) {
-      for (int b = 31; b >= 0; b--) {
-        if (started) r = r.sqr();
-        if ((e[w] >> b) & 1) {
-          r = started ? r * (*this) : *this;
+#pragma unroll 1
+      for (int b = 28; b >= 0; b -= 4) {
+        if (started) r = r.sqr().sqr().sqr().sqr();
+        u32 d = (e[w] >> b) & 15;
+        if (d) {
+          r = started ? r * tab[d] : tab[d];
           started = true;
         }
       }

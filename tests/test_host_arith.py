@@ -63,6 +63,10 @@ def test_field_ops(lib):
                 assert op(f, 0, a, b) == a * b * Ri % m
                 assert op(f, 1, a, b) == (a + b) % m and op(f, 2, a, b) == (a - b) % m
             assert op(f, 3, a) == (-a) % m and op(f, 6, a) == a * Rm % m and op(f, 7, a) == a * Ri % m
+            assert op(f, 8, a) == a * a * Ri % m  # dedicated Montgomery squaring
+        for a in [m - 1 - rng.randrange(1 << 40) for _ in range(100)] + [rng.randrange(m) for _ in range(2000)] + [
+                (1 << 254) - 1 - rng.randrange(1 << 33) for _ in range(50)] + [sum(0xFFFFFFFF << (32 * i) for i in rng.sample(range(8), 5)) % m for _ in range(100)]:
+            assert op(f, 8, a) == a * a * Ri % m
         for a in vals[:12]:
             assert op(f, 4, a * Rm % m) == (pow(a, -1, m) * Rm % m if a else 0)
         assert lib.host_is_canonical(f, limbs([m - 1])) == 1 and lib.host_is_canonical(f, limbs([m])) == 0
