@@ -173,6 +173,25 @@ int svk_msm_g1_dev(svk_ctx* ctx, size_t n, const void* d_scalars, const void* d_
 int svk_g1_mul_batch(svk_ctx* ctx, size_t n, const svk_fe* scalars, const svk_g1* points, size_t n_points, svk_g1* out);
 int svk_g1_mul_batch_dev(svk_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, size_t n_points, void* d_out);
 
+/* ---- MSM over a chosen curve, and the IPA accumulation decider -------------------------------
+ * The reference's `multi_scalar_multiplication` is generic over `CurveAffine` (util/msm.rs:238-317); its one in-tree caller on
+ * a verification path is `IpaAs::decide` over the Pasta curves (pcs/ipa/decider.rs:47-56; the reference test uses
+ * `pasta::pallas`, pcs/ipa.rs:407-446).  Points are 64-byte affine (x, y LE canonical in the curve's BASE field; identity = zeros),
+ * scalars 32-byte LE canonical in its SCALAR field. */
+enum { SVK_CURVE_BN254_G1 = 0, SVK_CURVE_PALLAS = 1, SVK_CURVE_VESTA = 2 };
+int svk_msm_curve(svk_ctx* ctx, int curve, size_t n, const svk_fe* scalars, const svk_g1* points, svk_g1* out, int32_t* out_status);
+int svk_msm_curve_dev(svk_ctx* ctx, int curve, size_t n, const void* d_scalars, const void* d_points, void* d_out, void* d_status);
+/* `<IpaAs<C, MOS> as AccumulationDecider<C, NativeLoader>>::decide` per accumulator (decider.rs:47-56; `decide_all`, :58-67, is
+ * "every status == 0"): g = `IpaDecidingKey::g` (2^k points, decider.rs:5-16); accumulator i = `IpaAccumulator { xi, u }`
+ * (pcs/ipa/accumulator.rs:5-25) = xi[i*k .. (i+1)*k], u[i].  out_status[i] = SVK_OK iff
+ * u == multi_scalar_multiplication(h_coeffs(xi, 1), g).to_affine(), else SVK_ASSERTION_FAILURE ("U == commit(G, h)").
+ * *out_invalid (may be NULL) = 1 if some input was not a value the reference's types can hold (xi >= the scalar modulus, a point of
+ * g off the curve or non-canonical); such accumulators fail.  n == 0 and k == 0 are argument faults (the reference asserts). */
+int svk_ipa_decide_batch(svk_ctx* ctx, int curve, uint32_t k, const svk_g1* g, size_t n, const svk_fe* xi, const svk_g1* u,
+                         int32_t* out_status, int32_t* out_invalid);
+int svk_ipa_decide_batch_dev(svk_ctx* ctx, int curve, uint32_t k, const void* d_g, size_t n, const void* d_xi, const void* d_u,
+                             void* d_out_status, void* d_invalid);
+
 /* Several batches per call: n_batches batches of batch_size proofs laid out back to back.  Every batch is folded
  * and decided on its own (same results as n_batches separate svk_plonk_verify_batch calls); the kernels of one call
  * serve all batches, so the serial tail of a batch (fold levels, the pairing) is shared.  Records, 256 B per batch:

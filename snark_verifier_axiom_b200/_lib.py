@@ -51,6 +51,10 @@ def _load():
     lib.svk_kzg_decide_records_dev.argtypes = [vp, i32, sz, vp]
     lib.svk_protocol_msm_terms.argtypes = [vp, i32, i32, vp, sz]
     lib.svk_plonk_msm_scalars_batch.argtypes = [vp, i32, sz, vp, ctypes.c_uint32, vp, sz, vp, vp, vp, vp]
+    lib.svk_msm_curve.argtypes = [vp, i32, sz, vp, vp, vp, vp]
+    lib.svk_msm_curve_dev.argtypes = [vp, i32, sz, vp, vp, vp, vp]
+    lib.svk_ipa_decide_batch.argtypes = [vp, i32, ctypes.c_uint32, vp, sz, vp, vp, vp, vp]
+    lib.svk_ipa_decide_batch_dev.argtypes = [vp, i32, ctypes.c_uint32, vp, sz, vp, vp, vp, vp]
     lib.svk_bench_modmul_peak.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     return lib
 

@@ -447,9 +447,9 @@ struct Fe {
   // Fermat inversion a^(p-2); 0 -> 0 (== the `unwrap_or_else(|| value.clone())` of loader.rs:247)
   HD Fe inv() const {
     u32 e[8];
+    e[0] = ptx::sub_cc(P::mod(0), 2);
 #pragma unroll
-    for (int i = 0; i < 8; i++) e[i] = P::mod(i);
-    e[0] -= 2;  // both moduli end in ...47 / ...01: no borrow
+    for (int i = 1; i < 8; i++) e[i] = ptx::subc_cc(P::mod(i), 0);
     return pow(e);
   }
   // sqrt for p = 3 mod 4 (Fq only): candidate a^((p+1)/4); caller checks y*y == a

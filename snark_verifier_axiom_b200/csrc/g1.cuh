@@ -13,44 +13,39 @@
 #pragma once
 #include "field.cuh"
 
-struct G1Affine {
-  Fq x, y;
+template <class F>
+struct AffT {
+  typedef AffT G1Affine;
+  F x, y;
   HD bool is_identity() const { return x.is_zero() && y.is_zero(); }
-  HD static G1Affine identity() { return {Fq::zero(), Fq::zero()}; }
+  HD static G1Affine identity() { return {F::zero(), F::zero()}; }
   HD G1Affine neg() const { return is_identity() ? *this : G1Affine{x, y.neg()}; }
 };
 
-HD Fq fq_b3() {  // curve constant b = 3 in Montgomery form
-  Fq one = Fq::one();
-  return one + one + one;
-}
-
-HD bool g1_on_curve(const G1Affine& p) {
-  if (p.is_identity()) return true;
-  return p.y.sqr() == p.x.sqr() * p.x + fq_b3();
-}
-
-struct G1Jac {
-  Fq X, Y, Z;
+template <class F>
+struct JacT {
+  typedef AffT<F> G1Affine;
+  typedef JacT G1Jac;
+  F X, Y, Z;
   HD bool is_identity() const { return Z.is_zero(); }
-  HD static G1Jac identity() { return {Fq::one(), Fq::one(), Fq::zero()}; }
+  HD static G1Jac identity() { return {F::one(), F::one(), F::zero()}; }
   HD static G1Jac from_affine(const G1Affine& p) {
     if (p.is_identity()) return identity();
-    return {p.x, p.y, Fq::one()};
+    return {p.x, p.y, F::one()};
   }
   // dbl-2009-l (a = 0): 2M + 5S
   HD G1Jac dbl() const {
     if (is_identity()) return *this;
-    Fq A = X.sqr();
-    Fq B = Y.sqr();
-    Fq C = B.sqr();
-    Fq t = (X + B).sqr() - A - C;
-    Fq D = t.dbl();
-    Fq E = A.dbl() + A;
-    Fq F = E.sqr();
+    F A = X.sqr();
+    F B = Y.sqr();
+    F C = B.sqr();
+    F t = (X + B).sqr() - A - C;
+    F D = t.dbl();
+    F E = A.dbl() + A;
+    F EE = E.sqr();
     G1Jac r;
-    r.X = F - D.dbl();
-    Fq C8 = C.dbl().dbl().dbl();
+    r.X = EE - D.dbl();
+    F C8 = C.dbl().dbl().dbl();
     r.Y = E * (D - r.X) - C8;
     r.Z = (Y * Z).dbl();
     return r;
@@ -59,19 +54,19 @@ struct G1Jac {
   HD G1Jac add_affine(const G1Affine& q) const {
     if (q.is_identity()) return *this;
     if (is_identity()) return from_affine(q);
-    Fq Z1Z1 = Z.sqr();
-    Fq U2 = q.x * Z1Z1;
-    Fq S2 = q.y * Z * Z1Z1;
+    F Z1Z1 = Z.sqr();
+    F U2 = q.x * Z1Z1;
+    F S2 = q.y * Z * Z1Z1;
     if (U2 == X) {
       if (S2 == Y) return dbl();
       return identity();
     }
-    Fq H = U2 - X;
-    Fq HH = H.sqr();
-    Fq I = HH.dbl().dbl();
-    Fq J = H * I;
-    Fq rr = (S2 - Y).dbl();
-    Fq V = X * I;
+    F H = U2 - X;
+    F HH = H.sqr();
+    F I = HH.dbl().dbl();
+    F J = H * I;
+    F rr = (S2 - Y).dbl();
+    F V = X * I;
     G1Jac r;
     r.X = rr.sqr() - J - V.dbl();
     r.Y = rr * (V - r.X) - (Y * J).dbl();
@@ -82,21 +77,21 @@ struct G1Jac {
   HD G1Jac add(const G1Jac& q) const {
     if (q.is_identity()) return *this;
     if (is_identity()) return q;
-    Fq Z1Z1 = Z.sqr();
-    Fq Z2Z2 = q.Z.sqr();
-    Fq U1 = X * Z2Z2;
-    Fq U2 = q.X * Z1Z1;
-    Fq S1 = Y * q.Z * Z2Z2;
-    Fq S2 = q.Y * Z * Z1Z1;
+    F Z1Z1 = Z.sqr();
+    F Z2Z2 = q.Z.sqr();
+    F U1 = X * Z2Z2;
+    F U2 = q.X * Z1Z1;
+    F S1 = Y * q.Z * Z2Z2;
+    F S2 = q.Y * Z * Z1Z1;
     if (U1 == U2) {
       if (S1 == S2) return dbl();
       return identity();
     }
-    Fq H = U2 - U1;
-    Fq I = H.dbl().sqr();
-    Fq J = H * I;
-    Fq rr = (S2 - S1).dbl();
-    Fq V = U1 * I;
+    F H = U2 - U1;
+    F I = H.dbl().sqr();
+    F J = H * I;
+    F rr = (S2 - S1).dbl();
+    F V = U1 * I;
     G1Jac r;
     r.X = rr.sqr() - J - V.dbl();
     r.Y = rr * (V - r.X) - (S1 * J).dbl();
@@ -105,31 +100,35 @@ struct G1Jac {
   }
   HD G1Jac neg() const { return {X, Y.neg(), Z}; }
   // to affine with a caller-supplied inverse of Z (batched inversion) or a Fermat inversion
-  HD G1Affine to_affine_with_zinv(const Fq& zinv) const {
+  HD G1Affine to_affine_with_zinv(const F& zinv) const {
     if (is_identity()) return G1Affine::identity();
-    Fq zi2 = zinv.sqr();
+    F zi2 = zinv.sqr();
     return {X * zi2, Y * zi2 * zinv};
   }
   HD G1Affine to_affine() const { return to_affine_with_zinv(Z.inv()); }
 };
 
-struct G1Xyzz {
-  Fq X, Y, ZZ, ZZZ;
+template <class F>
+struct XyzzT {
+  typedef AffT<F> G1Affine;
+  typedef JacT<F> G1Jac;
+  typedef XyzzT G1Xyzz;
+  F X, Y, ZZ, ZZZ;
   HD bool is_identity() const { return ZZ.is_zero(); }
-  HD static G1Xyzz identity() { return {Fq::zero(), Fq::zero(), Fq::zero(), Fq::zero()}; }
+  HD static G1Xyzz identity() { return {F::zero(), F::zero(), F::zero(), F::zero()}; }
   HD static G1Xyzz from_affine(const G1Affine& p) {
     if (p.is_identity()) return identity();
-    return {p.x, p.y, Fq::one(), Fq::one()};
+    return {p.x, p.y, F::one(), F::one()};
   }
   // dbl-2008-s-1 (a = 0): 6M + 4S... here 2M? -> U=2Y, V=U^2, W=U*V, S=X*V, M=3X^2, X3=M^2-2S, Y3=M(S-X3)-W*Y, ZZ3=V*ZZ, ZZZ3=W*ZZZ
   HD G1Xyzz dbl() const {
     if (is_identity()) return *this;
-    Fq U = Y.dbl();
-    Fq V = U.sqr();
-    Fq W = U * V;
-    Fq S = X * V;
-    Fq XX = X.sqr();
-    Fq M = XX.dbl() + XX;
+    F U = Y.dbl();
+    F V = U.sqr();
+    F W = U * V;
+    F S = X * V;
+    F XX = X.sqr();
+    F M = XX.dbl() + XX;
     G1Xyzz r;
     r.X = M.sqr() - S.dbl();
     r.Y = M * (S - r.X) - W * Y;
@@ -138,12 +137,12 @@ struct G1Xyzz {
     return r;
   }
   HD static G1Xyzz dbl_affine(const G1Affine& p) {
-    Fq U = p.y.dbl();
-    Fq V = U.sqr();
-    Fq W = U * V;
-    Fq S = p.x * V;
-    Fq XX = p.x.sqr();
-    Fq M = XX.dbl() + XX;
+    F U = p.y.dbl();
+    F V = U.sqr();
+    F W = U * V;
+    F S = p.x * V;
+    F XX = p.x.sqr();
+    F M = XX.dbl() + XX;
     G1Xyzz r;
     r.X = M.sqr() - S.dbl();
     r.Y = M * (S - r.X) - W * p.y;
@@ -155,17 +154,17 @@ struct G1Xyzz {
   HD G1Xyzz add_affine(const G1Affine& q) const {
     if (q.is_identity()) return *this;
     if (is_identity()) return from_affine(q);
-    Fq U2 = q.x * ZZ;
-    Fq S2 = q.y * ZZZ;
+    F U2 = q.x * ZZ;
+    F S2 = q.y * ZZZ;
     if (U2 == X) {
       if (S2 == Y) return dbl_affine(q);
       return identity();
     }
-    Fq Pp = U2 - X;
-    Fq Rr = S2 - Y;
-    Fq PP = Pp.sqr();
-    Fq PPP = Pp * PP;
-    Fq Q = X * PP;
+    F Pp = U2 - X;
+    F Rr = S2 - Y;
+    F PP = Pp.sqr();
+    F PPP = Pp * PP;
+    F Q = X * PP;
     G1Xyzz r;
     r.X = Rr.sqr() - PPP - Q.dbl();
     r.Y = Rr * (Q - r.X) - Y * PPP;
@@ -177,19 +176,19 @@ struct G1Xyzz {
   HD G1Xyzz add(const G1Xyzz& q) const {
     if (q.is_identity()) return *this;
     if (is_identity()) return q;
-    Fq U1 = X * q.ZZ;
-    Fq U2 = q.X * ZZ;
-    Fq S1 = Y * q.ZZZ;
-    Fq S2 = q.Y * ZZZ;
+    F U1 = X * q.ZZ;
+    F U2 = q.X * ZZ;
+    F S1 = Y * q.ZZZ;
+    F S2 = q.Y * ZZZ;
     if (U1 == U2) {
       if (S1 == S2) return dbl();
       return identity();
     }
-    Fq Pp = U2 - U1;
-    Fq Rr = S2 - S1;
-    Fq PP = Pp.sqr();
-    Fq PPP = Pp * PP;
-    Fq Q = U1 * PP;
+    F Pp = U2 - U1;
+    F Rr = S2 - S1;
+    F PP = Pp.sqr();
+    F PPP = Pp * PP;
+    F Q = U1 * PP;
     G1Xyzz r;
     r.X = Rr.sqr() - PPP - Q.dbl();
     r.Y = Rr * (Q - r.X) - S1 * PPP;
@@ -200,18 +199,33 @@ struct G1Xyzz {
   // x = X/ZZ, y = Y/ZZZ.  One inversion: (ZZ*ZZZ)^-1 -> 1/ZZ = inv*ZZZ, 1/ZZZ = inv*ZZ
   HD G1Affine to_affine() const {
     if (is_identity()) return G1Affine::identity();
-    Fq inv = (ZZ * ZZZ).inv();
+    F inv = (ZZ * ZZZ).inv();
     return {X * (inv * ZZZ), Y * (inv * ZZ)};
   }
   HD G1Jac to_jac() const {
     // (X, Y, ZZ, ZZZ) -> Jacobian with Z = ZZZ/ZZ is not polynomial; use Z' = ZZ*ZZZ... instead:
     // x = X/ZZ = X*ZZ*ZZZ^2/(ZZ*ZZZ)^2, y = Y/ZZZ = Y*ZZ^3*ZZZ^2/(ZZ*ZZZ)^3 with Z = ZZ*ZZZ
     if (is_identity()) return G1Jac::identity();
-    Fq Z = ZZ * ZZZ;
-    Fq ZZZ2 = ZZZ.sqr();
+    F Z = ZZ * ZZZ;
+    F ZZZ2 = ZZZ.sqr();
     return {X * ZZ * ZZZ2, Y * ZZ.sqr() * ZZ * ZZZ2, Z};
   }
 };
+
+// BN254 G1 instantiation (the KZG path); csrc/pasta.cuh instantiates the same templates over the Pasta base fields.
+typedef AffT<Fq> G1Affine;
+typedef JacT<Fq> G1Jac;
+typedef XyzzT<Fq> G1Xyzz;
+
+HD Fq fq_b3() {  // curve constant b = 3 in Montgomery form
+  Fq one = Fq::one();
+  return one + one + one;
+}
+
+HD bool g1_on_curve(const G1Affine& p) {
+  if (p.is_identity()) return true;
+  return p.y.sqr() == p.x.sqr() * p.x + fq_b3();
+}
 
 // 256-bit scalar (canonical, little-endian limbs) times affine point; MSB-first double-and-add.
 // Only the value is observable (SURVEY finding 1), the schedule is ours.

@@ -13,7 +13,7 @@
 //   k_msm_buckets   one bucket per thread: XYZZ mixed additions (8M+2S) over its sorted run
 //   k_msm_reduce    one block per window: sum_b b*B_b by chunked running sums + shared-memory tree
 //   k_msm_combine   Horner over the windows (c doublings each) + to_affine
-#include "g1.cuh"
+#include "pasta.cuh"
 #include "svk_ctx.h"
 
 struct MsmPlan {
@@ -43,8 +43,12 @@ __device__ __forceinline__ void load32(u32* v, const uint8_t* p) {
 }
 
 // keys[w * n + i] = bucket id (0 = skip) | sign << 31
-__global__ void __launch_bounds__(256) k_msm_prepare(size_t n, MsmPlan plan, const uint8_t* scalars, const uint8_t* points, G1Affine* pts_m,
-                                                     u32* keys, u32* hist, int* bad) {
+template <class C>
+__global__ void __launch_bounds__(256) k_msm_prepare(size_t n, MsmPlan plan, const uint8_t* scalars, const uint8_t* points,
+                                                     AffT<typename C::Base>* pts_m, u32* keys, u32* hist, int* bad) {
+  typedef typename C::Base Fq;
+  typedef typename C::Scalar Fr;
+  typedef AffT<Fq> G1Affine;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   G1Affine p;
@@ -53,7 +57,7 @@ __global__ void __launch_bounds__(256) k_msm_prepare(size_t n, MsmPlan plan, con
   bool canon = Fq::is_canonical(p.x.v) && Fq::is_canonical(p.y.v);
   bool ident = p.is_identity();
   if (!ident) { p.x = p.x.to_mont(); p.y = p.y.to_mont(); }
-  if (!canon || !g1_on_curve(p)) { *bad = 1; p = G1Affine::identity(); ident = true; }
+  if (!canon || !curve_on_curve<C>(p)) { *bad = 1; p = G1Affine::identity(); ident = true; }
   pts_m[i] = p;
   u32 k[9];
   load32(k, scalars + i * 32);
@@ -113,8 +117,11 @@ __global__ void __launch_bounds__(256) k_msm_scatter(size_t n, MsmPlan plan, con
 }
 
 // one bucket per thread; buckets[w][b-1] (XYZZ)
+template <class Fq>
 __global__ void __launch_bounds__(128) k_msm_buckets(size_t n, MsmPlan plan, const u32* hist, const u32* offs, const u32* sorted,
-                                                     const G1Affine* pts_m, G1Xyzz* buckets) {
+                                                     const AffT<Fq>* pts_m, XyzzT<Fq>* buckets) {
+  typedef AffT<Fq> G1Affine;
+  typedef XyzzT<Fq> G1Xyzz;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)plan.windows * plan.buckets;
   if (t >= total) return;
@@ -134,7 +141,9 @@ __global__ void __launch_bounds__(128) k_msm_buckets(size_t n, MsmPlan plan, con
 
 // S_w = sum_{b=1..B} b * bucket[w][b-1]; one block of REDUCE_T threads per window
 #define REDUCE_T 256
-__global__ void __launch_bounds__(REDUCE_T) k_msm_reduce(MsmPlan plan, const G1Xyzz* buckets, G1Xyzz* window_sums) {
+template <class Fq>
+__global__ void __launch_bounds__(REDUCE_T) k_msm_reduce(MsmPlan plan, const XyzzT<Fq>* buckets, XyzzT<Fq>* window_sums) {
+  typedef XyzzT<Fq> G1Xyzz;
   __shared__ G1Xyzz sm[REDUCE_T];
   u32 w = blockIdx.x, B = plan.buckets;
   const G1Xyzz* bk = buckets + (size_t)w * B;
@@ -163,7 +172,10 @@ __global__ void __launch_bounds__(REDUCE_T) k_msm_reduce(MsmPlan plan, const G1X
   if (threadIdx.x == 0) window_sums[w] = sm[0];
 }
 
-__global__ void k_msm_combine(MsmPlan plan, const G1Xyzz* window_sums, uint8_t* out, int add_to_out_jac, G1Jac* out_jac) {
+template <class Fq>
+__global__ void k_msm_combine(MsmPlan plan, const XyzzT<Fq>* window_sums, uint8_t* out) {
+  typedef AffT<Fq> G1Affine;
+  typedef XyzzT<Fq> G1Xyzz;
   G1Xyzz acc = G1Xyzz::identity();
   for (int w = (int)plan.windows - 1; w >= 0; w--) {
     for (u32 k = 0; k < plan.c; k++) acc = acc.dbl();
@@ -176,12 +188,13 @@ __global__ void k_msm_combine(MsmPlan plan, const G1Xyzz* window_sums, uint8_t* 
   o[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
   o[2] = make_uint4(y.v[0], y.v[1], y.v[2], y.v[3]);
   o[3] = make_uint4(y.v[4], y.v[5], y.v[6], y.v[7]);
-  (void)add_to_out_jac;
-  (void)out_jac;
 }
 
 // d_out: 64 B affine canonical; d_status: int (0 ok, 1 bad point, 2 bad scalar)
-int svk_msm_launch(svk_ctx* ctx, size_t n, const uint8_t* d_scalars, const uint8_t* d_points, uint8_t* d_out, int* d_status) {
+template <class C>
+static int msm_launch_t(svk_ctx* ctx, size_t n, const uint8_t* d_scalars, const uint8_t* d_points, uint8_t* d_out, int* d_status) {
+  typedef AffT<typename C::Base> G1Affine;
+  typedef XyzzT<typename C::Base> G1Xyzz;
   if (n == 0) {
     SVK_CUDA(ctx, cudaMemsetAsync(d_out, 0, 64, ctx->stream));
     SVK_CUDA(ctx, cudaMemsetAsync(d_status, 0, 4, ctx->stream));
@@ -205,15 +218,29 @@ int svk_msm_launch(svk_ctx* ctx, size_t n, const uint8_t* d_scalars, const uint8
   SVK_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)plan.windows * nb * 4, s));
   SVK_CUDA(ctx, cudaMemsetAsync(d_status, 0, 4, s));
   unsigned gb = (unsigned)((n + 255) / 256);
-  SVK_LAUNCH(ctx, "k_msm_prepare", k_msm_prepare<<<gb, 256, 0, s>>>(n, plan, d_scalars, d_points, pts_m, keys, hist, d_status));
+  SVK_LAUNCH(ctx, "k_msm_prepare", k_msm_prepare<C><<<gb, 256, 0, s>>>(n, plan, d_scalars, d_points, pts_m, keys, hist, d_status));
   SVK_LAUNCH(ctx, "k_msm_scan", k_msm_scan<<<plan.windows, 1024, 0, s>>>(plan, hist, offs, cursor));
   SVK_LAUNCH(ctx, "k_msm_scatter", k_msm_scatter<<<dim3(gb, plan.windows), 256, 0, s>>>(n, plan, keys, cursor, sorted));
   size_t total = (size_t)plan.windows * plan.buckets;
-  SVK_LAUNCH(ctx, "k_msm_buckets", k_msm_buckets<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(n, plan, hist, offs, sorted, pts_m, buckets));
-  SVK_LAUNCH(ctx, "k_msm_reduce", k_msm_reduce<<<plan.windows, REDUCE_T, 0, s>>>(plan, buckets, wsums));
-  SVK_LAUNCH(ctx, "k_msm_combine", k_msm_combine<<<1, 1, 0, s>>>(plan, wsums, d_out, 0, nullptr));
+  SVK_LAUNCH(ctx, "k_msm_buckets", k_msm_buckets<typename C::Base><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(n, plan, hist, offs, sorted, pts_m, buckets));
+  SVK_LAUNCH(ctx, "k_msm_reduce", k_msm_reduce<typename C::Base><<<plan.windows, REDUCE_T, 0, s>>>(plan, buckets, wsums));
+  SVK_LAUNCH(ctx, "k_msm_combine", k_msm_combine<typename C::Base><<<1, 1, 0, s>>>(plan, wsums, d_out));
   SVK_CUDA(ctx, cudaGetLastError());
   return 0;
+}
+
+int svk_msm_launch(svk_ctx* ctx, size_t n, const uint8_t* d_scalars, const uint8_t* d_points, uint8_t* d_out, int* d_status) {
+  return msm_launch_t<CurveBn254>(ctx, n, d_scalars, d_points, d_out, d_status);
+}
+
+// curve: SVK_CURVE_BN254_G1 (0), SVK_CURVE_PALLAS (1), SVK_CURVE_VESTA (2)
+int svk_msm_curve_launch(svk_ctx* ctx, int curve, size_t n, const uint8_t* d_scalars, const uint8_t* d_points, uint8_t* d_out, int* d_status) {
+  switch (curve) {
+    case 0: return msm_launch_t<CurveBn254>(ctx, n, d_scalars, d_points, d_out, d_status);
+    case 1: return msm_launch_t<CurvePallas>(ctx, n, d_scalars, d_points, d_out, d_status);
+    case 2: return msm_launch_t<CurveVesta>(ctx, n, d_scalars, d_points, d_out, d_status);
+    default: return svk_fail(ctx, "msm: unknown curve id");
+  }
 }
 
 // ---- batched scalar multiplication: out[i] = scalars[i] * points[i % n_points]  (`base * scalar`,

@@ -11,6 +11,9 @@ int svk_decide_launch(svk_ctx* ctx, int dk, size_t n, const void* d_accs, void* 
 int svk_modmul_peak_launch(svk_ctx* ctx, int iters, double* out_rate, double* out_ms);
 int svk_msm_launch(svk_ctx* ctx, size_t n, const uint8_t* d_scalars, const uint8_t* d_points, uint8_t* d_out, int* d_status);
 int svk_g1_mul_batch_launch(svk_ctx* ctx, size_t n, const uint8_t* d_scalars, const uint8_t* d_points, size_t n_points, uint8_t* d_out);
+int svk_msm_curve_launch(svk_ctx* ctx, int curve, size_t n, const uint8_t* d_scalars, const uint8_t* d_points, uint8_t* d_out, int* d_status);
+int svk_ipa_decide_launch(svk_ctx* ctx, int curve, u32 k, const uint8_t* d_g, size_t n, const uint8_t* d_xi, const uint8_t* d_u,
+                          int32_t* d_out_status, int32_t* d_invalid);
 int svk_fixed_tables_launch(svk_ctx* ctx, ProtocolDevice* pd);
 int svk_fold_launch(svk_ctx* ctx, size_t n, const uint8_t* d_accs, size_t group_size, uint8_t* d_out_acc, u32* d_out_r, int32_t* d_status);
 int svk_fold_launch_seg(svk_ctx* ctx, size_t n_seg, size_t n, const uint8_t* d_accs, size_t group_size, uint8_t* d_out, size_t out_stride);
@@ -579,6 +582,60 @@ int svk_msm_g1(svk_ctx* ctx, size_t n, const svk_fe* scalars, const svk_g1* poin
   SVK_CUDA(ctx, cudaMemcpyAsync(out, d + off_o, 64, cudaMemcpyDeviceToHost, s));
   SVK_CUDA(ctx, cudaMemcpyAsync(out_status, d + off_o + 64, 4, cudaMemcpyDeviceToHost, s));
   if (svk_wait(ctx)) return -1;
+  return 0;
+}
+
+// ---- MSM over a chosen curve + the IPA decider -------------------------------------------
+int svk_msm_curve_dev(svk_ctx* ctx, int curve, size_t n, const void* d_scalars, const void* d_points, void* d_out, void* d_status) {
+  SVK_CUDA(ctx, cudaSetDevice(ctx->device));
+  return svk_msm_curve_launch(ctx, curve, n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, (int*)d_status);
+}
+
+int svk_msm_curve(svk_ctx* ctx, int curve, size_t n, const svk_fe* scalars, const svk_g1* points, svk_g1* out, int32_t* out_status) {
+  SVK_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  uint8_t* d;
+  size_t off_p = (n * 32 + 255) / 256 * 256, off_o = off_p + (n * 64 + 255) / 256 * 256;
+  if (svk_scratch(ctx, 0, off_o + 256, (void**)&d)) return -1;
+  if (n) {
+    SVK_CUDA(ctx, cudaMemcpyAsync(d, scalars, n * 32, cudaMemcpyHostToDevice, s));
+    SVK_CUDA(ctx, cudaMemcpyAsync(d + off_p, points, n * 64, cudaMemcpyHostToDevice, s));
+  }
+  if (svk_msm_curve_launch(ctx, curve, n, d, d + off_p, d + off_o, (int*)(d + off_o + 64))) return -1;
+  SVK_CUDA(ctx, cudaMemcpyAsync(out, d + off_o, 64, cudaMemcpyDeviceToHost, s));
+  SVK_CUDA(ctx, cudaMemcpyAsync(out_status, d + off_o + 64, 4, cudaMemcpyDeviceToHost, s));
+  if (svk_wait(ctx)) return -1;
+  return 0;
+}
+
+int svk_ipa_decide_batch_dev(svk_ctx* ctx, int curve, uint32_t k, const void* d_g, size_t n, const void* d_xi, const void* d_u,
+                             void* d_out_status, void* d_invalid) {
+  SVK_CUDA(ctx, cudaSetDevice(ctx->device));
+  return svk_ipa_decide_launch(ctx, curve, k, (const uint8_t*)d_g, n, (const uint8_t*)d_xi, (const uint8_t*)d_u, (int32_t*)d_out_status,
+                               (int32_t*)d_invalid);
+}
+
+int svk_ipa_decide_batch(svk_ctx* ctx, int curve, uint32_t k, const svk_g1* g, size_t n, const svk_fe* xi, const svk_g1* u,
+                         int32_t* out_status, int32_t* out_invalid) {
+  SVK_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (k == 0 || k > 26) return svk_fail(ctx, "ipa_decide: k out of range");
+  if (n == 0) return svk_fail(ctx, "ipa_decide: no accumulators (the reference asserts !accumulators.is_empty(), pcs/ipa/decider.rs:61)");
+  cudaStream_t s = ctx->stream;
+  size_t m = (size_t)1 << k;
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+  size_t off_xi = al(m * 64), off_u = off_xi + al(n * (size_t)k * 32), off_st = off_u + al(n * 64), off_inv = off_st + al(n * 4);
+  uint8_t* d;
+  if (svk_scratch(ctx, 0, off_inv + 256, (void**)&d)) return -1;
+  SVK_CUDA(ctx, cudaMemcpyAsync(d, g, m * 64, cudaMemcpyHostToDevice, s));
+  SVK_CUDA(ctx, cudaMemcpyAsync(d + off_xi, xi, n * (size_t)k * 32, cudaMemcpyHostToDevice, s));
+  SVK_CUDA(ctx, cudaMemcpyAsync(d + off_u, u, n * 64, cudaMemcpyHostToDevice, s));
+  SVK_CUDA(ctx, cudaMemsetAsync(d + off_inv, 0, 4, s));
+  if (svk_ipa_decide_launch(ctx, curve, k, d, n, d + off_xi, d + off_u, (int32_t*)(d + off_st), (int32_t*)(d + off_inv))) return -1;
+  SVK_CUDA(ctx, cudaMemcpyAsync(out_status, d + off_st, n * 4, cudaMemcpyDeviceToHost, s));
+  int32_t inv = 0;
+  SVK_CUDA(ctx, cudaMemcpyAsync(&inv, d + off_inv, 4, cudaMemcpyDeviceToHost, s));
+  if (svk_wait(ctx)) return -1;
+  if (out_invalid) *out_invalid = inv;
   return 0;
 }
 

@@ -376,3 +376,67 @@ def g1_mul_batch(ctx: Context, scalars: Sequence[int], bases: Sequence[Optional[
     ctx._check(ctx._L.svk_g1_mul_batch(ctx._c, n, _ptr(sc), _ptr(pt), len(bases), _ptr(out)))
     b = out.tobytes()
     return [_g1_from(b[64 * i : 64 * i + 64]) for i in range(n)]
+
+
+# ---- the same MSM over a chosen curve, and the IPA decider ----------------------------------
+CURVE_BN254_G1, CURVE_PALLAS, CURVE_VESTA = 0, 1, 2  # include/svk.h SVK_CURVE_*
+
+
+def multi_scalar_multiplication_on(ctx: Context, curve: int, scalars: Sequence[int], bases: Sequence[Optional[Tuple[int, int]]]):
+    """`multi_scalar_multiplication` is generic over `CurveAffine` (util/msm.rs:238): the Pippenger kernels instantiated for `curve`."""
+    assert len(scalars) == len(bases)
+    n = len(scalars)
+    sc = np.frombuffer(b"".join(_fe(s) for s in scalars), dtype=np.uint8).copy() if n else np.zeros(0, np.uint8)
+    pt = np.frombuffer(b"".join(_g1_bytes(p) for p in bases), dtype=np.uint8).copy() if n else np.zeros(0, np.uint8)
+    out, st = np.zeros(64, np.uint8), np.zeros(1, np.int32)
+    ctx._check(ctx._L.svk_msm_curve(ctx._c, curve, n, _ptr(sc), _ptr(pt), _ptr(out), _ptr(st)))
+    if st[0] != 0:
+        raise ValueError(f"msm: invalid input (status {int(st[0])})")
+    return _g1_from(out.tobytes())
+
+
+@dataclass
+class IpaAccumulator:
+    """snark-verifier/src/pcs/ipa/accumulator.rs:5-25"""
+
+    xi: Sequence[int]
+    u: Optional[Tuple[int, int]]
+
+
+@dataclass
+class IpaDecidingKey:
+    """snark-verifier/src/pcs/ipa/decider.rs:5-16 (`svk` is not used by `decide`; `g` has 2^k points)."""
+
+    g: Sequence[Optional[Tuple[int, int]]]
+    curve: int = CURVE_PALLAS
+
+
+class IpaAs:
+    """`<IpaAs<C, MOS> as AccumulationDecider<C, NativeLoader>>` (snark-verifier/src/pcs/ipa/decider.rs:33-67)."""
+
+    @staticmethod
+    def decide_batch(ctx: Context, dk: IpaDecidingKey, accumulators: Sequence[IpaAccumulator]) -> np.ndarray:
+        """Per-accumulator status (0 ok, 3 AssertionFailure "U == commit(G, h)"), no fail-fast."""
+        assert len(accumulators) > 0  # decider.rs:61
+        k = len(accumulators[0].xi)
+        assert k > 0 and len(dk.g) == 1 << k and all(len(a.xi) == k for a in accumulators)  # pcs/ipa.rs:380
+        n = len(accumulators)
+        g = np.frombuffer(b"".join(_g1_bytes(p) for p in dk.g), dtype=np.uint8).copy()
+        xi = np.frombuffer(b"".join(_fe(x) for a in accumulators for x in a.xi), dtype=np.uint8).copy()
+        u = np.frombuffer(b"".join(_g1_bytes(a.u) for a in accumulators), dtype=np.uint8).copy()
+        st, inv = np.zeros(n, np.int32), np.zeros(1, np.int32)
+        ctx._check(ctx._L.svk_ipa_decide_batch(ctx._c, dk.curve, k, _ptr(g), n, _ptr(xi), _ptr(u), _ptr(st), _ptr(inv)))
+        return st
+
+    @staticmethod
+    def decide(ctx: Context, dk: IpaDecidingKey, accumulator: IpaAccumulator) -> None:
+        st = IpaAs.decide_batch(ctx, dk, [accumulator])
+        if st[0] != 0:
+            raise Error(st[0])
+
+    @staticmethod
+    def decide_all(ctx: Context, dk: IpaDecidingKey, accumulators: Sequence[IpaAccumulator]) -> None:
+        st = IpaAs.decide_batch(ctx, dk, accumulators)
+        bad = np.nonzero(st)[0]
+        if len(bad):
+            raise Error(st[bad[0]])

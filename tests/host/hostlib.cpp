@@ -246,3 +246,52 @@ void host_keccak256(const uint8_t* data, u32 n, uint8_t* out) {
   KeccakSponge k; keccak_reset(k); keccak_absorb(k, data, n); keccak_finish(k, out);
 }
 }
+
+// ---- Pasta: the same templates over the Pallas / Vesta base fields --------------------------
+#include "../../snark_verifier_axiom_b200/csrc/pasta.cuh"
+template <class F>
+static void fe_op_t(int op, const u32* a, const u32* b, u32* out) {
+  F x, y, r;
+  memcpy(x.v, a, 32); memcpy(y.v, b, 32);
+  switch (op) {
+    case 0: r = x * y; break; case 1: r = x + y; break; case 2: r = x - y; break; case 3: r = x.neg(); break;
+    case 4: r = x.inv(); break; case 6: r = x.to_mont(); break;
+    case 7: r = x.from_mont(); break; case 8: r = x.sqr(); break; default: r = x.dbl(); break;
+  }
+  memcpy(out, r.v, 32);
+}
+template <class C>
+static int muladd_t(const u32* p_xy, const u32* k, const u32* q_xy, u32* out_xy) {
+  typedef typename C::Base F;
+  AffT<F> p, q;
+  memcpy(p.x.v, p_xy, 32); memcpy(p.y.v, p_xy + 8, 32); memcpy(q.x.v, q_xy, 32); memcpy(q.y.v, q_xy + 8, 32);
+  if (!p.is_identity()) { p.x = p.x.to_mont(); p.y = p.y.to_mont(); }
+  if (!q.is_identity()) { q.x = q.x.to_mont(); q.y = q.y.to_mont(); }
+  if (!curve_on_curve<C>(p) || !curve_on_curve<C>(q)) return 1;
+  XyzzT<F> acc = XyzzT<F>::identity();
+  JacT<F> jac = JacT<F>::identity();
+  for (int w = 7; w >= 0; w--) for (int b = 31; b >= 0; b--) {
+    acc = acc.dbl(); jac = jac.dbl();
+    if ((k[w] >> b) & 1) { acc = acc.add_affine(p); jac = jac.add_affine(p); }
+  }
+  XyzzT<F> r = acc.add(XyzzT<F>::from_affine(q));
+  JacT<F> rj = jac.add(JacT<F>::from_affine(q));
+  AffT<F> a1 = r.to_affine(), a2 = rj.to_affine();
+  if (!(a1.x == a2.x) || !(a1.y == a2.y)) return 2;
+  if (!curve_on_curve<C>(a1)) return 3;
+  F x = a1.x.from_mont(), y = a1.y.from_mont();
+  memcpy(out_xy, x.v, 32); memcpy(out_xy + 8, y.v, 32);
+  return 0;
+}
+extern "C" {
+// field: 2 Pallas base (= Vesta scalar), 3 Vesta base (= Pallas scalar)
+void host_pasta_fe_op(int field, int op, const u32* a, const u32* b, u32* out) {
+  if (field == 2) fe_op_t<PallasFp>(op, a, b, out); else fe_op_t<VestaFp>(op, a, b, out);
+}
+// out = k*P + Q on curve 0 BN254 G1 / 1 Pallas / 2 Vesta through BOTH the XYZZ and the Jacobian formulas (must agree)
+int host_curve_muladd(int curve, const u32* p_xy, const u32* k, const u32* q_xy, u32* out_xy) {
+  if (curve == 0) return muladd_t<CurveBn254>(p_xy, k, q_xy, out_xy);
+  if (curve == 1) return muladd_t<CurvePallas>(p_xy, k, q_xy, out_xy);
+  return muladd_t<CurveVesta>(p_xy, k, q_xy, out_xy);
+}
+}

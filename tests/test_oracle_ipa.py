@@ -1,0 +1,110 @@
+"""IPA decider on CPU: the Pasta oracle's self-checks, the restatement of `h_coeffs` / `decide` against an honest
+prover's base folding (pcs/ipa.rs:78-118), and the DEVICE field / point templates built for the host over the Pasta fields."""
+import ctypes
+import os
+import random
+import subprocess
+
+import pytest
+
+from oracle import ipa, pasta
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "host", "_hostlib.so")
+SRC = os.path.join(HERE, "host", "hostlib.cpp")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", SO, SRC], check=True, timeout=600)
+    return ctypes.CDLL(SO)
+
+
+def limbs(vals):
+    out = []
+    for v in vals:
+        out += [(v >> (32 * i)) & 0xFFFFFFFF for i in range(8)]
+    return (ctypes.c_uint32 * len(out))(*out)
+
+
+def rd(a, n):
+    return [sum(int(a[8 * j + i]) << (32 * i) for i in range(8)) for j in range(n)]
+
+
+def test_pasta_curves_exact_algebra():
+    for C in (pasta.PALLAS, pasta.VESTA):
+        assert C.is_on_curve(C.gen)
+        assert C.mul(C.gen, C.n) is None and C.mul(C.gen, C.n - 1) == C.neg(C.gen)  # prime group order = the other field
+        a, b = 0x1234567 << 200, 0xABCDEF << 100
+        assert C.add(C.mul(C.gen, a), C.mul(C.gen, b)) == C.mul(C.gen, a + b)
+    assert pasta.PALLAS.p == pasta.VESTA.n and pasta.VESTA.p == pasta.PALLAS.n
+    bn = pasta.bn254_g1()
+    assert bn.mul(bn.gen, bn.n) is None
+
+
+@pytest.mark.parametrize("C", [pasta.PALLAS, pasta.VESTA], ids=["pallas", "vesta"])
+def test_h_coeffs_decide_vs_honest_folding(C):
+    rng = random.Random(11 + C.id)
+    for k in (1, 3, 5):
+        g = [C.mul(C.gen, rng.randrange(1, C.n)) for _ in range(1 << k)]
+        xi = [rng.randrange(1, C.n) for _ in range(k)]
+        u = ipa.fold_bases(C, g, xi)  # what Ipa::create_proof leaves in bases[0]
+        h = ipa.h_coeffs(xi, 1, C.n)
+        assert C.msm_naive(h, g) == u == C.msm_pippenger(h, g)
+        z = rng.randrange(C.n)
+        assert ipa.h_eval(xi, z, C.n) == sum(c * pow(z, i, C.n) for i, c in enumerate(h)) % C.n
+        assert ipa.decide(C, g, ipa.IpaAccumulator(xi, u)) == 0
+        assert ipa.decide(C, g, ipa.IpaAccumulator(xi, C.add(u, C.gen))) == 3
+        if k > 1:
+            assert ipa.decide(C, g, ipa.IpaAccumulator(xi[::-1], u)) == 3
+        assert ipa.decide_all(C, g, [ipa.IpaAccumulator(xi, u)] * 2) == 0
+        assert ipa.decide_all(C, g, [ipa.IpaAccumulator(xi, u), ipa.IpaAccumulator(xi, None)]) == 3
+
+
+def test_device_field_templates_over_pasta_fields(lib):
+    rng = random.Random(2)
+
+    def op(f, o, a, b=0):
+        out = (ctypes.c_uint32 * 8)()
+        lib.host_pasta_fe_op(f, o, limbs([a]), limbs([b]), out)
+        return rd(out, 1)[0]
+
+    for f, m in ((2, pasta.PALLAS_P), (3, pasta.VESTA_P)):
+        Rm = (1 << 256) % m
+        Ri = pow(Rm, -1, m)
+        edge = [0, 1, 2, m - 1, m - 2, Rm, (1 << 254) % m, m >> 1, (1 << 254) - 1, (1 << 254), m - (1 << 32), (1 << 224) - 1]
+        vals = edge + [rng.randrange(m) for _ in range(80)]
+        for a in vals:
+            for b in rng.sample(vals, 6) + edge:
+                assert op(f, 0, a, b) == a * b * Ri % m
+                assert op(f, 1, a, b) == (a + b) % m and op(f, 2, a, b) == (a - b) % m
+            assert op(f, 3, a) == (-a) % m and op(f, 6, a) == a * Rm % m and op(f, 7, a) == a * Ri % m
+            assert op(f, 8, a) == a * a * Ri % m
+        for a in [rng.randrange(m) for _ in range(1500)] + [m - 1 - rng.randrange(1 << 40) for _ in range(200)]:
+            assert op(f, 8, a) == a * a * Ri % m
+            b = rng.choice(vals)
+            assert op(f, 0, a, b) == a * b * Ri % m
+        for a in vals[:14]:
+            assert op(f, 4, a * Rm % m) == (pow(a, -1, m) * Rm % m if a else 0)  # p - 2 needs a borrow across limb 0 here
+
+
+def test_device_point_templates_over_pasta_curves(lib):
+    rng = random.Random(3)
+    for C in (pasta.bn254_g1(), pasta.PALLAS, pasta.VESTA):
+        for trial in range(8):
+            P = C.mul(C.gen, rng.randrange(1, C.n))
+            Q = C.mul(C.gen, rng.randrange(1, C.n)) if trial != 1 else None
+            k = rng.randrange(C.n) if trial not in (2, 3) else (0 if trial == 2 else C.n - 1)
+            if trial == 4:
+                Q = C.neg(C.mul(P, k))  # k P + Q = identity
+            if trial == 5:
+                Q = C.mul(P, k)  # doubling inside add
+            out = (ctypes.c_uint32 * 16)()
+            rc = lib.host_curve_muladd(C.id, limbs(P), limbs([k]), limbs(Q if Q else (0, 0)), out)
+            assert rc == 0
+            x, y = rd(out, 2)
+            got = None if x == 0 and y == 0 else (x, y)
+            assert got == C.add(C.mul(P, k), Q), (C.name, trial)
+        # off-curve input is rejected
+        bad = (C.gen[0], (C.gen[1] + 1) % C.p)
+        assert lib.host_curve_muladd(C.id, limbs(bad), limbs([5]), limbs((0, 0)), (ctypes.c_uint32 * 16)()) == 1
