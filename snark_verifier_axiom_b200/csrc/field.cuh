@@ -342,7 +342,9 @@ struct Fe {
   }
   template <int N>
   HD static Fe dot_inline(const Fe* a, const Fe* b) {
-    static_assert(N >= 1 && N <= 4, "bound of the single final subtraction");
+    // result before the final subtraction < (N p / 2^256 + 1) p: < 2p for N <= 4 with the 254-bit BN254 moduli (p / 2^256 = 0.19),
+    // for N <= 3 with the 255-bit Pasta moduli (0.25)
+    static_assert(N >= 1 && N <= (P::mod(7) < 0x40000000u ? 4 : 3), "bound of the single final subtraction");
     u32 al[8], of[8];
 #pragma unroll
     for (int i = 0; i < 8; i += 2) {

@@ -11,7 +11,7 @@
 //   k_fold_sponge : one group per thread: Poseidon sponge -> r, then the scalars r^j (canonical)
 //   k_group_var / k_group_sum : the group MSMs (see below)
 //                   block's threads, shared-memory tree reduction of the partial sums, to_affine
-#include "g1.cuh"
+#include "straus.cuh"
 #include "poseidon.cuh"
 #include "svk_ctx.h"
 
@@ -84,8 +84,8 @@ __device__ __noinline__ G1Jac fold_mul_window4(const G1Affine& p, const u32* k) 
 
 // Group MSM, split like the per-proof MSM (verify.cu):
 //   k_group_var  `vpl` threads per (group, side); a thread owns terms j = 1 + lane, 1 + lane + vpl, ... of its group
-//                and runs them as ONE interleaved (Straus) multiplication: 252 shared doublings + per term a
-//                15-entry Jacobian table and 64 table additions.  vpl = 1 where groups are plentiful (minimal work:
+//                and runs them as ONE interleaved (Straus) multiplication (straus.cuh): 255 shared doublings + per term a
+//                16-entry Jacobian table and <= 52 signed-window additions.  vpl = 1 where groups are plentiful (minimal work:
 //                1778 + 7 x 1185 M for a group of 8 instead of 7 x 2977), vpl = m - 1 on the upper, narrow levels
 //                (minimal latency).  The first version ran one block of 32 threads per (group, side) with 7 active
 //                lanes and was the largest consumer of issue slots of the whole step (profiles/r1_notes.md).
@@ -120,40 +120,10 @@ __global__ void __launch_bounds__(64) k_group_var(size_t n_seg, size_t n, size_t
       atomicMax(status + seg * status_stride_words, SVK_TRANSCRIPT | (SVK_T_POINT_INVALID << 8));
       base = G1Affine::identity();
     }
-    G1Jac* tb = tables + ((size_t)nt * 16) * n_threads + gid;  // entry d at tb[d * n_threads]
-    G1Jac e = G1Jac::from_affine(base);
-    tb[1 * n_threads] = e;
-    G1Jac cur = e.dbl();
-    tb[2 * n_threads] = cur;
-    for (u32 d = 3; d < 16; d++) {
-      cur = cur.add_affine(base);
-      tb[d * n_threads] = cur;
-    }
+    straus_recode(k[nt]);
+    straus_build_table(tables + ((size_t)nt * STRAUS_TABLE) * n_threads + gid, n_threads, base);
   }
-  // Table entries are fetched one step ahead of their use (the address depends on the scalar only): the tables of a
-  // launch are hundreds of MB, every read misses L2 (ncu: 2.6 GB of DRAM reads, long-scoreboard stall 0.65 per issue
-  // before prefetching), and a table addition (16 M) is long enough to cover a DRAM round trip.
-  G1Jac acc = G1Jac::identity();
-  G1Jac nxt = G1Jac::identity();
-  u32 dn = nt ? ((k[0][7] >> 28) & 0xf) : 0;
-  if (dn) nxt = tables[((size_t)0 * 16 + dn) * n_threads + gid];
-  for (int w = 63; w >= 0; w--) {
-    if (w != 63) acc = acc.dbl().dbl().dbl().dbl();
-    for (u32 t = 0; t < nt; t++) {
-      G1Jac cur = nxt;
-      u32 d = dn;
-      // next (term, window)
-      u32 t2 = t + 1;
-      int w2 = w;
-      if (t2 == nt) { t2 = 0; w2 = w - 1; }
-      dn = 0;
-      if (w2 >= 0) {
-        dn = (k[t2][w2 >> 3] >> ((w2 & 7) * 4)) & 0xf;
-        if (dn) nxt = tables[((size_t)t2 * 16 + dn) * n_threads + gid];
-      }
-      if (d) acc = acc.add(cur);
-    }
-  }
+  G1Jac acc = straus_run(&k[0][0], nt, tables + gid, n_threads);
   partials[gid] = acc;
 }
 

@@ -69,7 +69,7 @@ struct JacT {
     F V = X * I;
     G1Jac r;
     r.X = rr.sqr() - J - V.dbl();
-    r.Y = rr * (V - r.X) - (Y * J).dbl();
+    r.Y = F::dot2(rr, V - r.X, Y.dbl().neg_lazy(), J);  // rr (V - X3) - 2 Y J, one shared reduction
     r.Z = (Z + H).sqr() - Z1Z1 - HH;
     return r;
   }
@@ -94,7 +94,7 @@ struct JacT {
     F V = U1 * I;
     G1Jac r;
     r.X = rr.sqr() - J - V.dbl();
-    r.Y = rr * (V - r.X) - (S1 * J).dbl();
+    r.Y = F::dot2(rr, V - r.X, S1.dbl().neg_lazy(), J);  // rr (V - X3) - 2 S1 J
     r.Z = ((Z + q.Z).sqr() - Z1Z1 - Z2Z2) * H;
     return r;
   }
@@ -131,7 +131,7 @@ struct XyzzT {
     F M = XX.dbl() + XX;
     G1Xyzz r;
     r.X = M.sqr() - S.dbl();
-    r.Y = M * (S - r.X) - W * Y;
+    r.Y = F::dot2(M, S - r.X, W.neg_lazy(), Y);
     r.ZZ = V * ZZ;
     r.ZZZ = W * ZZZ;
     return r;
@@ -145,7 +145,7 @@ struct XyzzT {
     F M = XX.dbl() + XX;
     G1Xyzz r;
     r.X = M.sqr() - S.dbl();
-    r.Y = M * (S - r.X) - W * p.y;
+    r.Y = F::dot2(M, S - r.X, W.neg_lazy(), p.y);
     r.ZZ = V;
     r.ZZZ = W;
     return r;
@@ -167,7 +167,7 @@ struct XyzzT {
     F Q = X * PP;
     G1Xyzz r;
     r.X = Rr.sqr() - PPP - Q.dbl();
-    r.Y = Rr * (Q - r.X) - Y * PPP;
+    r.Y = F::dot2(Rr, Q - r.X, Y.neg_lazy(), PPP);
     r.ZZ = ZZ * PP;
     r.ZZZ = ZZZ * PPP;
     return r;
@@ -191,7 +191,7 @@ struct XyzzT {
     F Q = U1 * PP;
     G1Xyzz r;
     r.X = Rr.sqr() - PPP - Q.dbl();
-    r.Y = Rr * (Q - r.X) - S1 * PPP;
+    r.Y = F::dot2(Rr, Q - r.X, S1.neg_lazy(), PPP);
     r.ZZ = ZZ * q.ZZ * PP;
     r.ZZZ = ZZZ * q.ZZZ * PPP;
     return r;

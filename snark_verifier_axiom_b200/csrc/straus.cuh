@@ -1,0 +1,82 @@
+// Interleaved (Straus) multi-scalar multiplication with signed 5-bit fixed windows, shared by the per-proof MSM
+// (k_msm_var, verify.cu) and the fold group MSM (k_group_var, fold.cu) -- both stand for the reference's
+// `Σ base * scalar` of NativeLoader::multi_scalar_multiplication (snark-verifier/src/loader/native.rs:61-71); only the
+// resulting group element is observable, the schedule is ours.
+//
+// Recoding without a carry chain at read time: k' = k + C with C = Σ_{i<51} 16 * 32^i (fits 256 bits for any k < 2^255), then
+//   digit_i = ((k' >> 5 i) & 31) - 16  in [-16, 15]   (i < 51),      digit_51 = k' >> 255  in {0, 1}
+// and Σ digit_i 32^i = k.  Per term: a 16-entry Jacobian table {1..16} P (1 + 7 doublings, 7 mixed additions) and
+// <= 52 table additions (a digit is zero with probability 1/32); per thread 255 shared doublings.  Against the unsigned
+// 4-bit windows of the first version (15-entry table, 64 additions, 252 doublings): ~10 additions fewer per term.
+#pragma once
+#include "g1.cuh"
+
+#define STRAUS_WINDOWS 52
+#define STRAUS_TABLE 16
+
+// k (8 limbs, canonical scalar) += C
+HD void straus_recode(u32* k) {
+  const u32 C[8] = {0x21084210u, 0x08421084u, 0x42108421u, 0x10842108u, 0x84210842u, 0x21084210u, 0x08421084u, 0x42108421u};
+  k[0] = ptx::add_cc(k[0], C[0]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) k[i] = ptx::addc_cc(k[i], C[i]);
+  k[7] = ptx::addc(k[7], C[7]);
+}
+
+// magnitude (0..16) and sign of digit w of a recoded scalar
+HD u32 straus_digit(const u32* k, int w, u32& neg) {
+  u32 bit = 5u * (u32)w, word = bit >> 5, sh = bit & 31;
+  u32 lo = k[word], hi = word < 7 ? k[word + 1] : 0;
+  u32 v = (u32)((((u64)hi << 32) | lo) >> sh) & 31;
+  neg = 0;
+  if (w == STRAUS_WINDOWS - 1) return v;
+  int s = (int)v - 16;
+  neg = s < 0;
+  return (u32)(s < 0 ? -s : s);
+}
+
+// tb[(d - 1) * stride] = d * base for d = 1..16
+template <class F>
+HD void straus_build_table(JacT<F>* tb, size_t stride, const AffT<F>& base) {
+  JacT<F> cur = JacT<F>::from_affine(base);
+  tb[0] = cur;
+  for (u32 d = 2; d <= STRAUS_TABLE; d++) {
+    if (d & 1) cur = cur.add_affine(base);
+    else cur = tb[(size_t)(d / 2 - 1) * stride].dbl();
+    tb[(size_t)(d - 1) * stride] = cur;
+  }
+}
+
+// acc = Σ_t k[t] * base_t over `nt` recoded scalars k[t] (8 limbs each, row stride 8) whose tables start at
+// tables[(t * 16) * stride]; entries are fetched one step ahead of their use (the tables of a launch are hundreds of MB and
+// every read misses L2; a table addition is long enough to cover a DRAM round trip).
+template <class F>
+HD JacT<F> straus_run(const u32* k, u32 nt, const JacT<F>* tables, size_t stride) {
+  typedef JacT<F> J;
+  J acc = J::identity();
+  if (nt == 0) return acc;
+  J nxt = J::identity();
+  u32 nn = 0;
+  u32 dn = straus_digit(k, STRAUS_WINDOWS - 1, nn);
+  if (dn) nxt = tables[(size_t)(dn - 1) * stride];
+  for (int w = STRAUS_WINDOWS - 1; w >= 0; w--) {
+    if (w != STRAUS_WINDOWS - 1) acc = acc.dbl().dbl().dbl().dbl().dbl();
+    for (u32 t = 0; t < nt; t++) {
+      J cur = nxt;
+      u32 d = dn, ng = nn;
+      u32 t2 = t + 1;
+      int w2 = w;
+      if (t2 == nt) { t2 = 0; w2 = w - 1; }
+      dn = 0;
+      if (w2 >= 0) {
+        dn = straus_digit(k + 8 * t2, w2, nn);
+        if (dn) nxt = tables[((size_t)t2 * STRAUS_TABLE + (dn - 1)) * stride];
+      }
+      if (d) {
+        if (ng) cur.Y = cur.Y.neg();
+        acc = acc.add(cur);
+      }
+    }
+  }
+  return acc;
+}

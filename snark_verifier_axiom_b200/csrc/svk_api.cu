@@ -377,7 +377,7 @@ int svk_protocol_info(svk_ctx* ctx, int proto, uint32_t* out) {
   ProtocolDevice* pd = ctx->protocols[proto];
   out[0] = pd->proof_len; out[1] = pd->n_instances; out[2] = pd->n_challenges; out[3] = pd->n_regs; out[4] = pd->n_ops;
   out[5] = (u32)pd->n_perm; out[6] = pd->verify_valid ? 1 : 0; out[7] = (u32)pd->n_fr_mul; out[8] = pd->n_lhs; out[9] = pd->n_rhs;
-  out[10] = (u32)pd->points.size(); out[11] = pd->n_scalar_slots; out[12] = (u32)pd->msm_work_modmul; out[13] = (u32)(pd->n_var * (161 + 64 * 16) + pd->var_lanes_total * 252 * 7); out[14] = pd->n_var; out[15] = pd->var_lanes_total;
+  out[10] = (u32)pd->points.size(); out[11] = pd->n_scalar_slots; out[12] = (u32)pd->msm_work_modmul; out[13] = (u32)(pd->n_var * (133 + 50 * 16) + pd->var_lanes_total * 255 * 7);  /* straus.cuh: table 8 dbl + 7 madd, ~50 additions, 255 doublings */ out[14] = pd->n_var; out[15] = pd->var_lanes_total;
   out[16] = pd->n_old; out[17] = pd->acc_limbs; out[18] = pd->acc_bits; out[19] = (u32)pd->transcript_kind;
   return 0;
 }

@@ -8,7 +8,7 @@
 //                    (util/msm.rs:70-77 -> NativeLoader::multi_scalar_multiplication, loader/native.rs:61-71)
 //   k_status       : per-proof `Result` -> status word (include/svk.h)
 #include "compiler.h"
-#include "g1.cuh"
+#include "straus.cuh"
 #include "svk_ctx.h"
 #include "svk_protocol.h"
 
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(32) k_fixed_tables(u32 n_fixed, const G1Affine
 //                additions only), plus the partials and the scalar == 1 bases; shuffle reduction -> sums[side][proof]
 //   k_to_affine  one (proof, side) per thread: Fermat inversion, canonical accumulator bytes
 // Straus / interleaved windows: one thread owns up to SVK_VAR_TERMS_MAX variable-base terms of ONE proof and
-// shares the 252 doublings between them (per term: a 15-entry Jacobian table + 64 table additions).  With
+// shares the 255 doublings between them (per term: a 16-entry Jacobian table + <= 52 signed-window additions, straus.cuh).  With
 // `vpl` threads ("var lanes") per proof, each with its own host-scheduled item list (lanes never mix the lhs and
 // rhs sides): fewer lanes minimise total work
 // (1778 + 11 x 1185 M per StandardPlonk proof instead of 11 x 2977), larger vpl shortens the latency.
@@ -180,42 +180,11 @@ __global__ void __launch_bounds__(64) k_msm_var(size_t n_items, const MsmWork* v
     const uint4* sp = reinterpret_cast<const uint4*>(scalars + ((size_t)wk.slot * n_items + it) * 8);
     uint4 lo = sp[0], hi = sp[1];
     k[nt][0] = lo.x; k[nt][1] = lo.y; k[nt][2] = lo.z; k[nt][3] = lo.w; k[nt][4] = hi.x; k[nt][5] = hi.y; k[nt][6] = hi.z; k[nt][7] = hi.w;
+    straus_recode(k[nt]);
     G1Affine base = pts[(size_t)wk.base * n_items + it];
-    G1Jac* tb = tables + ((size_t)nt * 16) * n_threads + gid;  // entry d at tb[d * n_threads]
-    G1Jac e = G1Jac::from_affine(base);
-    tb[1 * n_threads] = e;
-    G1Jac d2 = e.dbl();
-    tb[2 * n_threads] = d2;
-    G1Jac cur = d2;
-    for (u32 d = 3; d < 16; d++) {
-      cur = cur.add_affine(base);
-      tb[d * n_threads] = cur;
-    }
+    straus_build_table(tables + ((size_t)nt * STRAUS_TABLE) * n_threads + gid, n_threads, base);
   }
-  // Table entries are fetched one step ahead of their use (the address depends on the scalar only): the tables of a
-  // launch are hundreds of MB, every read misses L2 (ncu: 2.6 GB of DRAM reads, long-scoreboard stall 0.65 per issue
-  // before prefetching), and a table addition (16 M) is long enough to cover a DRAM round trip.
-  G1Jac acc = G1Jac::identity();
-  G1Jac nxt = G1Jac::identity();
-  u32 dn = nt ? ((k[0][7] >> 28) & 0xf) : 0;
-  if (dn) nxt = tables[((size_t)0 * 16 + dn) * n_threads + gid];
-  for (int w = 63; w >= 0; w--) {
-    if (w != 63) acc = acc.dbl().dbl().dbl().dbl();
-    for (u32 t = 0; t < nt; t++) {
-      G1Jac cur = nxt;
-      u32 d = dn;
-      // next (term, window)
-      u32 t2 = t + 1;
-      int w2 = w;
-      if (t2 == nt) { t2 = 0; w2 = w - 1; }
-      dn = 0;
-      if (w2 >= 0) {
-        dn = (k[t2][w2 >> 3] >> ((w2 & 7) * 4)) & 0xf;
-        if (dn) nxt = tables[((size_t)t2 * 16 + dn) * n_threads + gid];
-      }
-      if (d) acc = acc.add(cur);
-    }
-  }
+  G1Jac acc = straus_run(&k[0][0], nt, tables + gid, n_threads);
   partials[gid] = acc;
 }
 

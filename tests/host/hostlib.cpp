@@ -295,3 +295,29 @@ int host_curve_muladd(int curve, const u32* p_xy, const u32* k, const u32* q_xy,
   return muladd_t<CurveVesta>(p_xy, k, q_xy, out_xy);
 }
 }
+template <class F>
+static void fe_dot_t(int n, int neg_mask, const u32* a, const u32* b, u32* out) {
+  F x[3], y[3];
+  for (int k = 0; k < n; k++) { memcpy(x[k].v, a + 8 * k, 32); memcpy(y[k].v, b + 8 * k, 32); if (neg_mask >> k & 1) x[k] = x[k].neg_lazy(); }
+  F r = n == 2 ? F::dot2(x[0], y[0], x[1], y[1]) : F::dot3(x[0], y[0], x[1], y[1], x[2], y[2]);
+  memcpy(out, r.v, 32);
+}
+extern "C" void host_pasta_fe_dot(int field, int n, int neg_mask, const u32* a, const u32* b, u32* out) {
+  if (field == 2) fe_dot_t<PallasFp>(n, neg_mask, a, b, out); else fe_dot_t<VestaFp>(n, neg_mask, a, b, out);
+}
+
+// ---- Straus (signed 5-bit windows) over the BN254 G1 templates: out = sum_t k_t * P_t --------------------
+#include "../../snark_verifier_axiom_b200/csrc/straus.cuh"
+extern "C" int host_straus(int nt, const u32* pts_xy, const u32* ks, u32* out_xy) {
+  if (nt > 16) return 1;
+  static G1Jac tables[16 * STRAUS_TABLE];
+  u32 k[16][8];
+  for (int t = 0; t < nt; t++) {
+    memcpy(k[t], ks + 8 * t, 32);
+    straus_recode(k[t]);
+    straus_build_table(tables + (size_t)t * STRAUS_TABLE, 1, load_aff(pts_xy + 16 * t));
+  }
+  G1Jac acc = straus_run(&k[0][0], (u32)nt, tables, 1);
+  store_aff(out_xy, acc.to_affine());
+  return 0;
+}

@@ -117,6 +117,32 @@ def test_g1_ops(lib):
         assert (rc == 0) == ok and (not ok or rd_g1(out) == pt)
 
 
+def test_straus_signed_windows(lib):
+    """csrc/straus.cuh (k_msm_var / k_group_var core): recoding k + C, 16-entry tables, signed digits -- vs the naive MSM."""
+    rng = random.Random(21)
+    for trial in range(10):
+        nt = [1, 2, 5, 11, 16, 3, 7, 1, 4, 2][trial]
+        pts = [bn254.g1_mul(bn254.G1_GEN, rng.randrange(1, R)) for _ in range(nt)]
+        ks = [rng.randrange(R) for _ in range(nt)]
+        if trial == 1:
+            ks = [0, R - 1]
+        if trial == 2:
+            ks[:5] = [1, 16, 17, (1 << 253) + 16, sum(16 << (5 * i) for i in range(50))]  # digits at the -16 / +16 extremes
+            pts[1] = None
+        if trial == 5:
+            pts[1] = pts[0]
+            pts[2] = bn254.g1_neg(pts[0])
+            ks[2] = (ks[0] + ks[1]) % R  # total = identity
+        if trial == 7:
+            ks = [sum(15 << (5 * i) for i in range(51)) % R]
+        out = (ctypes.c_uint32 * 16)()
+        flat = []
+        for p_ in pts:
+            flat += list(p_ if p_ else (0, 0))
+        assert lib.host_straus(nt, limbs(flat), limbs(ks), out) == 0
+        assert rd_g1(out) == bn254.g1_msm_naive(list(zip(ks, pts))), trial
+
+
 def test_pairing_exact(lib):
     rng = random.Random(3)
     s, d = rng.randrange(1, R), rng.randrange(1, R)

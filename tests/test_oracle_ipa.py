@@ -88,6 +88,24 @@ def test_device_field_templates_over_pasta_fields(lib):
             assert op(f, 4, a * Rm % m) == (pow(a, -1, m) * Rm % m if a else 0)  # p - 2 needs a borrow across limb 0 here
 
 
+def test_fused_dot_products_over_pasta_fields(lib):
+    """The point formulas use dot2 (Y3 = r (V - X3) - 2 Y J with one reduction); its bound for 255-bit moduli: N <= 3."""
+    rng = random.Random(8)
+    for f, m in ((2, pasta.PALLAS_P), (3, pasta.VESTA_P)):
+        Ri = pow(1 << 256, -1, m)
+        edge = [0, 1, m - 1, m, m - 2, (1 << 254) + 5, (1 << 254) - 1]
+        for n in (2, 3):
+            for trial in range(400):
+                src = edge if trial < 80 else None
+                a = [rng.choice(src) if src else rng.randrange(m) for _ in range(n)]
+                b = [rng.choice(src) if src else rng.randrange(m) for _ in range(n)]
+                neg = rng.randrange(1 << n)
+                out = (ctypes.c_uint32 * 8)()
+                lib.host_pasta_fe_dot(f, n, neg, limbs(a), limbs(b), out)
+                want = sum((-x if neg >> k & 1 else x) * y for k, (x, y) in enumerate(zip(a, b))) * Ri % m
+                assert rd(out, 1)[0] == want, (f, n, a, b, neg)
+
+
 def test_device_point_templates_over_pasta_curves(lib):
     rng = random.Random(3)
     for C in (pasta.bn254_g1(), pasta.PALLAS, pasta.VESTA):
