@@ -36,7 +36,8 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=128)
     ap.add_argument("--inflight", type=int, default=16, help="launches in flight (one libsvk context + stream each)")
-    ap.add_argument("--batches-per-launch", type=int, default=8, help="4096-proof batches verified by one call (each folded + decided on its own)")
+    ap.add_argument("--batches-per-launch", type=int, default=0, help="4096-proof batches verified by one call (each folded + decided on its own); "
+                    "0 = auto: 8 when --steps gives every in-flight slot a full launch, fewer for short runs so that the K timed steps still fill the slots")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4096, help="proofs per GPU per step")
     ap.add_argument("--group-size", type=int, default=8, help="KzgAs fold group size (0 = the reference's flat fold)")
@@ -193,12 +194,18 @@ def run_ours(args):
     from snark_verifier_axiom_b200 import verifier as V
     from snark_verifier_axiom_b200.distributed import ShardedBatchVerifier
 
-    B = max(1, args.batches_per_launch)
+    S = max(1, args.inflight)
+    # K timed steps = K batches.  A launch carries B batches; with few steps, smaller launches keep all S slots busy.
+    # Auto: the largest B <= 8 that divides K (exactly K steps are timed) and still gives every slot a launch.
+    B = args.batches_per_launch
+    if B <= 0:
+        B = max(1, min(8, args.steps // S))
+        while args.steps % B:
+            B -= 1
     g, reps, np = make_workload(args.batch * B, args.scheme)
     mos = V.SHPLONK if args.scheme == "bdfg21" else V.GWC
     nb1 = args.batch           # proofs per batch (= per step)
     n = args.batch * B         # proofs per launch
-    S = max(1, args.inflight)
     steps = -(-args.steps // B) * B  # whole launches
     slots = [Slot(torch, V, ShardedBatchVerifier, g, local, dev, world, rank, args.group_size, B, mos) for _ in range(S)]
     pv = slots[0].pv
@@ -384,15 +391,26 @@ def run_ours(args):
         name = max((k for k in prof if k in work), key=lambda k: prof[k]["ms"])
         ms_launch = prof[name]["ms"] / prof[name]["count"]
         ach = work[name] / (ms_launch * 1e-3)
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/r1_traffic.json), per proof x proofs per launch
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")))
+            if name in tr:
+                traffic = tr[name]["dram_bytes_per_launch"] / tr[name]["proofs_per_launch"] * n
+                traffic_src = tr[name].get("source")
+        except (OSError, ValueError, KeyError):
+            pass
         total_work = (sum(work.values()) + work_other) / B  # per 4096-proof batch (fold and pairing not counted: < 8 %)
         roofline = {
             "bound": "imad", "kernel": name, "achieved": ach / 1e9, "peak": peak / 1e9,
             "unit": "Gmodmul/s (1 modmul = one 8x32-bit-limb Montgomery multiplication = 139 IMAD + 37 IADD3, cuobjdump)",
-            "frac": ach / peak, "traffic": None,
+            "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes of DRAM traffic per launch of this kernel (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
+            "scaled by proofs per launch)", "traffic_source": traffic_src,
             "peak_source": "measured in this run: svk_bench_modmul_peak (independent Montgomery-mul chains, 8 warps/SMSP on all SMs)",
             "kernel_ms_per_launch": ms_launch, "batches_per_launch": B, "kernels_one_launch_in_flight": kernels,
             "whole_step_frac": (total_work * world / (ms_per_step * 1e-3)) / peak,
             "hbm_gbs_algorithmic": (h2d + d2h) / (ms_per_step * 1e-3) / 1e9,
+            "hbm_gbs_dominant_kernel": (traffic / (ms_launch * 1e-3) / 1e9) if traffic else None,
         }
         base = None if args.no_cpu_baseline else cpu_baseline(g, args.cpu_sample, args.group_size, args.scheme)
         out = {

@@ -327,7 +327,8 @@ static int protocol_upload(svk_ctx* ctx, svk_host::CompiledProtocol& cp, int mos
   std::vector<u32> ol, orr;
   // k_msm_var lanes: `var_lanes` threads per proof for the lhs terms, and one more for the rhs side when it has
   // scaled variable bases of its own (GWC: rhs = sum u^i W_i; SHPLONK's rhs is W' itself).
-  pd->var_lanes = 2;  // measured on B200 (profiles/r1_notes.md): 1 and 2 give the same throughput, 2 halves the kernel's latency
+  pd->var_lanes = 1;  // measured on B200 (profiles/r1_notes.md) with the signed-window Straus core: 1 lane = 1.37 M proofs/s, 2 lanes = 1.33 M
+                      // (one more 255-doubling chain per proof); 2 halves this kernel's latency for a lone small batch (SVK_VAR_LANES=2)
   if (const char* e = getenv("SVK_VAR_LANES")) pd->var_lanes = (u32)std::max(1, std::min(8, atoi(e)));
   bool rhs_var = false;
   for (auto& t : rhs) rhs_var = rhs_var || (t.slot >= 0 && !t.fixed);
