@@ -11,8 +11,8 @@
 //   k_msm_scan      one block per window: exclusive scan of the histogram -> bucket offsets
 //   k_msm_scatter   counting sort of (point index | sign) by bucket id, per window
 //   k_msm_buckets   one bucket per thread: XYZZ mixed additions (8M+2S) over its sorted run
-//   k_msm_reduce    one block per window: sum_b b*B_b by chunked running sums + shared-memory tree
-//   k_msm_combine   Horner over the windows (c doublings each) + to_affine
+//   k_msm_reduce    up to 8 blocks per window: sum_b b*B_b over a bucket range by chunked running sums + shared-memory tree
+//   k_msm_combine   one warp: per-window sum of the block partials, then Horner over the windows (c doublings each) + to_affine
 #include "pasta.cuh"
 #include "svk_ctx.h"
 
@@ -139,25 +139,30 @@ __global__ void __launch_bounds__(128) k_msm_buckets(size_t n, MsmPlan plan, con
   buckets[t] = acc;
 }
 
-// S_w = sum_{b=1..B} b * bucket[w][b-1]; one block of REDUCE_T threads per window
+// S_w = sum_{b=1..B} b * bucket[w][b-1], in two stages: `rb` blocks of REDUCE_T threads per window each reduce a contiguous range of
+// buckets to one partial (chunked running sums per thread, + lo * (plain sum) for the chunk's offset, shared-memory tree), then
+// k_msm_combine adds the partials of a window.  (The first version used ONE block per window: 128 buckets per thread at c = 16 made
+// this serial tail 2.8 ms -- a third of a 2^20-point MSM.)
 #define REDUCE_T 256
 template <class Fq>
-__global__ void __launch_bounds__(REDUCE_T) k_msm_reduce(MsmPlan plan, const XyzzT<Fq>* buckets, XyzzT<Fq>* window_sums) {
+__global__ void __launch_bounds__(REDUCE_T) k_msm_reduce(MsmPlan plan, u32 rb, const XyzzT<Fq>* buckets, XyzzT<Fq>* partials) {
   typedef XyzzT<Fq> G1Xyzz;
   __shared__ G1Xyzz sm[REDUCE_T];
-  u32 w = blockIdx.x, B = plan.buckets;
+  u32 w = blockIdx.y, B = plan.buckets;
   const G1Xyzz* bk = buckets + (size_t)w * B;
-  u32 per = (B + REDUCE_T - 1) / REDUCE_T;
-  u32 lo = threadIdx.x * per, hi = min(lo + per, B);  // bucket ids lo+1 .. hi
+  u32 chunk = (B + rb - 1) / rb;
+  u32 c_lo = blockIdx.x * chunk, c_hi = min(c_lo + chunk, B);
+  u32 per = (chunk + REDUCE_T - 1) / REDUCE_T;
+  u32 lo = min(c_lo + threadIdx.x * per, c_hi), hi = min(lo + per, c_hi);  // bucket ids lo+1 .. hi
   G1Xyzz run = G1Xyzz::identity(), acc = G1Xyzz::identity();
   for (u32 b = hi; b > lo; b--) {
     run = run.add(bk[b - 1]);
     acc = acc.add(run);  // acc = sum (id - lo) * B_id
   }
-  // + lo * run  (run = plain sum of the chunk): double-and-add on the small integer lo
+  // + lo * run  (run = plain sum of the chunk): double-and-add on the small integer lo < 2^(c-1)
   if (lo && !run.is_identity()) {
-    G1Xyzz m = G1Xyzz::identity();
-    for (int bit = 31; bit >= 0; bit--) {
+    G1Xyzz m = run;
+    for (int bit = 30 - __clz(lo); bit >= 0; bit--) {
       m = m.dbl();
       if ((lo >> bit) & 1) m = m.add(run);
     }
@@ -169,17 +174,27 @@ __global__ void __launch_bounds__(REDUCE_T) k_msm_reduce(MsmPlan plan, const Xyz
     if (threadIdx.x < s) sm[threadIdx.x] = sm[threadIdx.x].add(sm[threadIdx.x + s]);
     __syncthreads();
   }
-  if (threadIdx.x == 0) window_sums[w] = sm[0];
+  if (threadIdx.x == 0) partials[(size_t)w * rb + blockIdx.x] = sm[0];
 }
 
+// one warp: lane w adds the rb partials of window w; lane 0 then runs Horner over the windows (c doublings each) + to_affine
 template <class Fq>
-__global__ void k_msm_combine(MsmPlan plan, const XyzzT<Fq>* window_sums, uint8_t* out) {
+__global__ void __launch_bounds__(32) k_msm_combine(MsmPlan plan, u32 rb, const XyzzT<Fq>* partials, uint8_t* out) {
   typedef AffT<Fq> G1Affine;
   typedef XyzzT<Fq> G1Xyzz;
+  __shared__ G1Xyzz wsum[32];
+  u32 lane = threadIdx.x;
+  if (lane < plan.windows) {
+    G1Xyzz sacc = partials[(size_t)lane * rb];
+    for (u32 i = 1; i < rb; i++) sacc = sacc.add(partials[(size_t)lane * rb + i]);
+    wsum[lane] = sacc;
+  }
+  __syncthreads();
+  if (lane != 0) return;
   G1Xyzz acc = G1Xyzz::identity();
   for (int w = (int)plan.windows - 1; w >= 0; w--) {
     for (u32 k = 0; k < plan.c; k++) acc = acc.dbl();
-    acc = acc.add(window_sums[w]);
+    acc = acc.add(wsum[w]);
   }
   G1Affine a = acc.to_affine();
   Fq x = a.x.from_mont(), y = a.y.from_mont();
@@ -211,7 +226,8 @@ static int msm_launch_t(svk_ctx* ctx, size_t n, const uint8_t* d_scalars, const 
   if (svk_scratch(ctx, 11, (size_t)plan.windows * n * 4, (void**)&keys)) return -1;
   if (svk_scratch(ctx, 12, (size_t)plan.windows * n * 4, (void**)&sorted)) return -1;
   if (svk_scratch(ctx, 13, (size_t)plan.windows * nb * 4 * 3, (void**)&hist)) return -1;
-  if (svk_scratch(ctx, 14, ((size_t)plan.windows * plan.buckets + plan.windows) * sizeof(G1Xyzz), (void**)&buckets)) return -1;
+  u32 rb = plan.buckets >= 4096 ? 8 : (plan.buckets >= 1024 ? 4 : 1);  // reduce blocks per window: <= 16 buckets per thread
+  if (svk_scratch(ctx, 14, ((size_t)plan.windows * plan.buckets + (size_t)plan.windows * rb) * sizeof(G1Xyzz), (void**)&buckets)) return -1;
   u32* offs = hist + (size_t)plan.windows * nb;
   u32* cursor = offs + (size_t)plan.windows * nb;
   G1Xyzz* wsums = buckets + (size_t)plan.windows * plan.buckets;
@@ -223,8 +239,8 @@ static int msm_launch_t(svk_ctx* ctx, size_t n, const uint8_t* d_scalars, const 
   SVK_LAUNCH(ctx, "k_msm_scatter", k_msm_scatter<<<dim3(gb, plan.windows), 256, 0, s>>>(n, plan, keys, cursor, sorted));
   size_t total = (size_t)plan.windows * plan.buckets;
   SVK_LAUNCH(ctx, "k_msm_buckets", k_msm_buckets<typename C::Base><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(n, plan, hist, offs, sorted, pts_m, buckets));
-  SVK_LAUNCH(ctx, "k_msm_reduce", k_msm_reduce<typename C::Base><<<plan.windows, REDUCE_T, 0, s>>>(plan, buckets, wsums));
-  SVK_LAUNCH(ctx, "k_msm_combine", k_msm_combine<typename C::Base><<<1, 1, 0, s>>>(plan, wsums, d_out));
+  SVK_LAUNCH(ctx, "k_msm_reduce", k_msm_reduce<typename C::Base><<<dim3(rb, plan.windows), REDUCE_T, 0, s>>>(plan, rb, buckets, wsums));
+  SVK_LAUNCH(ctx, "k_msm_combine", k_msm_combine<typename C::Base><<<1, 32, 0, s>>>(plan, rb, wsums, d_out));
   SVK_CUDA(ctx, cudaGetLastError());
   return 0;
 }

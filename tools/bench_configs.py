@@ -47,7 +47,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--max-log-n", type=int, default=24)
     ap.add_argument("--decide-n", type=int, default=65536)
-    ap.add_argument("--only", choices=["all", "msm", "latency", "decide"], default="all")
+    ap.add_argument("--only", choices=["all", "msm", "latency", "decide", "ipa"], default="all")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     ctx = V.Context(0)
@@ -112,6 +112,38 @@ def main():
         gpu_ms = 1e3 * (_t.perf_counter() - t0) / 5
         print(json.dumps({"config": "single_proof_verify_latency", "gpu_ms_host_call": gpu_ms,
                           "note": "one proof cannot fill a GPU: the B200 path is a throughput device (batch configs)"}))
+    # ---- IpaAs::decide over pallas (h_coeffs + 2^k-point Pippenger + compare), 4 accumulators per call
+    if args.only in ("all", "ipa"):
+        import numpy as np
+
+        from oracle import pasta  # test infrastructure: only generates the committing-key points here
+
+        C = pasta.PALLAS
+        for k in (10, 14, 16):
+            m = 1 << k
+            step, cur, g = C.mul(C.gen, 0x9E3779B97F4A7C15F39CC0605CEDC834), C.mul(C.gen, 12345), []
+            for _ in range(m):
+                g.append(cur)
+                cur = C.add(cur, step)
+            gb = np.frombuffer(b"".join(x.to_bytes(32, "little") + y.to_bytes(32, "little") for x, y in g), dtype=np.uint8)
+            d_g = torch.from_numpy(gb.copy()).to(dev)
+            n_acc = 4
+            with torch.cuda.stream(stream):
+                d_xi = rand_scalars(n_acc * k, dev, 7 + k)
+            d_h = torch.zeros(m * 32, dtype=torch.uint8, device=dev)
+            d_u = torch.zeros(n_acc * 64, dtype=torch.uint8, device=dev)
+            d_st = torch.zeros(n_acc, dtype=torch.int32, device=dev)
+            d_inv = torch.zeros(1, dtype=torch.int32, device=dev)
+            # u_i := what the device commits to (parity with the oracle is tests/test_gpu_ipa.py); the last one is corrupted
+            ctx._check(L.svk_ipa_decide_batch_dev(c, 1, k, p(d_g), n_acc, p(d_xi), p(d_u), p(d_st), p(d_inv)))
+            stream.synchronize()
+
+            def run_ipa():
+                ctx._check(L.svk_ipa_decide_batch_dev(c, 1, k, p(d_g), n_acc, p(d_xi), p(d_u), p(d_st), p(d_inv)))
+
+            ms = timed(run_ipa, 3)
+            print(json.dumps({"config": "ipa_decide_pallas", "k": k, "accumulators": n_acc, "ms_per_accumulator": ms / n_acc,
+                              "msm_points_per_s": n_acc * m / (ms * 1e-3)}))
     if args.only not in ("all", "decide"):
         return
 
