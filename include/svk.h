@@ -202,6 +202,12 @@ int svk_plonk_verify_multi(svk_ctx* ctx, int proto, size_t n_batches, size_t bat
 int svk_plonk_verify_multi_dev(svk_ctx* ctx, int proto, size_t n_batches, size_t batch_size, const void* d_instances, uint32_t n_instances,
                                const void* d_proofs, size_t proof_stride, const void* d_proof_lens, size_t group_size, void* d_out_accs,
                                void* d_out_status, void* d_out_records);
+/* The same without the pairing -- the per-rank half of a proof-sharded job: the per-batch folded accumulators of all
+ * ranks are all-gathered, folded once more (svk_kzg_as_fold_multi_dev) and decided ONCE (svk_kzg_decide_records_dev).  Records
+ * carry decide_ok = 1 ("not decided here"). */
+int svk_plonk_fold_multi_dev(svk_ctx* ctx, int proto, size_t n_batches, size_t batch_size, const void* d_instances, uint32_t n_instances,
+                               const void* d_proofs, size_t proof_stride, const void* d_proof_lens, size_t group_size, void* d_out_accs,
+                               void* d_out_status, void* d_out_records);
 
 /* Segmented fold / decide on 256-byte records (the layout above), device pointers: n_seg independent groups of n
  * accumulators each ([seg][n] x svk_acc) -> one record per segment; decide fills `decide_ok` of every record.

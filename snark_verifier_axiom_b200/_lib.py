@@ -47,6 +47,7 @@ def _load():
     lib.svk_g1_mul_batch_dev.argtypes = [vp, sz, vp, vp, sz, vp]
     lib.svk_plonk_verify_multi.argtypes = [vp, i32, sz, sz, vp, ctypes.c_uint32, vp, sz, vp, sz, i32, vp, vp]
     lib.svk_plonk_verify_multi_dev.argtypes = [vp, i32, sz, sz, vp, ctypes.c_uint32, vp, sz, vp, sz, vp, vp, vp]
+    lib.svk_plonk_fold_multi_dev.argtypes = [vp, i32, sz, sz, vp, ctypes.c_uint32, vp, sz, vp, sz, vp, vp, vp]
     lib.svk_kzg_as_fold_multi_dev.argtypes = [vp, sz, sz, vp, sz, vp]
     lib.svk_kzg_decide_records_dev.argtypes = [vp, i32, sz, vp]
     lib.svk_protocol_msm_terms.argtypes = [vp, i32, i32, vp, sz]

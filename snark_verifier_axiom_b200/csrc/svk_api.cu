@@ -501,6 +501,26 @@ int svk_plonk_verify_multi_dev(svk_ctx* ctx, int proto, size_t n_batches, size_t
   return svk_batch_verdict_launch(ctx, n_batches, batch_size, (const int32_t*)d_out_status, rec, 256);
 }
 
+// The same without the pairing: what a RANK of a proof-sharded job runs -- its per-batch folded accumulators are
+// all-gathered, folded across ranks and decided ONCE (snark_verifier_axiom_b200/distributed.py).  Records carry decide_ok = 1
+// ("not decided here"), so `ok` = every proof read and verified succinctly and the fold found only curve points.
+int svk_plonk_fold_multi_dev(svk_ctx* ctx, int proto, size_t n_batches, size_t batch_size, const void* d_instances, uint32_t n_instances,
+                             const void* d_proofs, size_t proof_stride, const void* d_proof_lens, size_t group_size, void* d_out_accs,
+                             void* d_out_status, void* d_out_records) {
+  SVK_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
+  if (n_batches == 0 || batch_size == 0) return svk_fail(ctx, "empty batch");
+  ProtocolDevice* pd = ctx->protocols[proto];
+  size_t n = n_batches * batch_size;
+  uint8_t* rec = (uint8_t*)d_out_records;
+  if (svk_succinct_verify_launch(ctx, pd, n, (const uint8_t*)d_instances, n_instances, (const uint8_t*)d_proofs, proof_stride,
+                                 (const u32*)d_proof_lens, (uint8_t*)d_out_accs, nullptr, (int32_t*)d_out_status))
+    return -1;
+  if (svk_fold_launch_seg(ctx, n_batches, batch_size * pd->accs_per_proof(), (const uint8_t*)d_out_accs, group_size, rec, 256)) return -1;
+  SVK_CUDA(ctx, cudaMemset2DAsync(rec + 164, 256, 1, 1, n_batches, ctx->stream));
+  return svk_batch_verdict_launch(ctx, n_batches, batch_size, (const int32_t*)d_out_status, rec, 256);
+}
+
 int svk_plonk_verify_batch_dev(svk_ctx* ctx, int proto, size_t n, const void* d_instances, uint32_t n_instances, const void* d_proofs,
                                size_t proof_stride, const void* d_proof_lens, size_t group_size, void* d_out_accs, void* d_out_status,
                                void* d_out_folded) {

@@ -39,9 +39,11 @@ class LibsvkOps:
     def _p(t):
         return ctypes.c_void_p(t.data_ptr())
 
-    def local_verify(self, d_inst, n_inst, d_proofs, n_batches, batch, group_size, d_accs, d_status, d_records, d_lens=None):
-        """n_batches batches of `batch` proofs: succinct verify + fold + decide + verdict, one record per batch"""
-        rc = self.L.svk_plonk_verify_multi_dev(self.c, self.pv.pid, n_batches, batch, self._p(d_inst), n_inst, self._p(d_proofs), d_proofs.shape[1],
+    def local_verify(self, d_inst, n_inst, d_proofs, n_batches, batch, group_size, d_accs, d_status, d_records, d_lens=None, decide=True):
+        """n_batches batches of `batch` proofs: succinct verify + fold (+ decide) + verdict, one record per batch.  decide=False
+        is the per-rank half of a sharded job: the single pairing runs after the cross-rank fold."""
+        fn = self.L.svk_plonk_verify_multi_dev if decide else self.L.svk_plonk_fold_multi_dev
+        rc = fn(self.c, self.pv.pid, n_batches, batch, self._p(d_inst), n_inst, self._p(d_proofs), d_proofs.shape[1],
                                                self._p(d_lens) if d_lens is not None else None, group_size, self._p(d_accs), self._p(d_status),
                                                self._p(d_records))
         self.ctx._check(rc)
@@ -93,7 +95,8 @@ class ShardedBatchVerifier:
         self._ensure(n)
         self.nb = n_batches
         nb = n_batches
-        self.ops.local_verify(d_inst, n_inst, d_proofs, nb, n // nb, self.group_size, self.d_accs, self.d_status, self.d_records, d_lens)
+        self.ops.local_verify(d_inst, n_inst, d_proofs, nb, n // nb, self.group_size, self.d_accs, self.d_status, self.d_records, d_lens,
+                              decide=self.world == 1)
         if self.world > 1:
             with self._on_stream():
                 dist.all_gather_into_tensor(self.d_gather[: self.world * nb * RECORD], self.d_records[: nb * RECORD])

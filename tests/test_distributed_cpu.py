@@ -25,8 +25,9 @@ class OracleOps:
         self.S = forge.Setup(0)
         self.trace = cref.Trace(self.S, "bdfg21")
 
-    def local_verify(self, d_inst, n_inst, d_proofs, n_batches, n, group_size, d_accs, d_status, d_record, d_lens=None):
+    def local_verify(self, d_inst, n_inst, d_proofs, n_batches, n, group_size, d_accs, d_status, d_record, d_lens=None, decide=True):
         assert n_batches == 1
+        self.local_decides = getattr(self, "local_decides", 0) + (1 if decide else 0)
         buf = d_proofs.numpy()
         lens = np.full(n, buf.shape[1], dtype=np.int32)
         inp = np.ascontiguousarray(d_inst.numpy()).view(np.uint64).reshape(n, -1)
@@ -36,7 +37,7 @@ class OracleOps:
         acc, r, fst = self.cref.fold(accs, group_size)
         rec = np.zeros(256, dtype=np.uint8)
         rec[:128] = acc
-        ok = self.cref.decide(acc, self.S.dk)
+        ok = self.cref.decide(acc, self.S.dk) if decide else True  # a rank of a sharded job does not run the pairing
         rec[164] = 1 if ok else 0
         rec[165] = 1 if (ok and (st == 0).all() and fst == 0) else 0
         d_record[:] = torch.from_numpy(rec)
@@ -66,6 +67,7 @@ def _worker(rank, world, port, q):
     inst = torch.from_numpy(np.frombuffer(b"".join(int(x).to_bytes(32, "little") for s in mine for col in s.instances for x in col), dtype=np.uint8).copy())
     sv = ShardedBatchVerifier(None, world, rank, torch.device("cpu"), None, group_size=GROUP, ops=OracleOps())
     sv.verify_dev(inst, 1, proofs, len(mine))
+    assert sv.ops.local_decides == 0  # world > 1: the single pairing runs after the cross-rank fold
     q.put((rank, lo, hi, sv.last_ok(), sv.final_accumulator()))
     dist.barrier()
     dist.destroy_process_group()
