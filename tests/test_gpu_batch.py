@@ -99,3 +99,60 @@ def test_verify_batches_equals_separate_calls(env):
                 assert (res.folded.lhs, res.folded.rhs) == (single.folded.lhs, single.folded.rhs)
         assert [r.ok for r in multi] == [True, False, True]
         assert [int(x) for x in multi[1].status] == [0, 0, 3, 0, 0]
+
+
+def test_sharded_fold_then_single_pairing(env):
+    """SURVEY 8e on one GPU: two 'ranks' fold their shards WITHOUT deciding (svk_plonk_fold_multi_dev), the per-rank accumulators
+    are folded once more and decided once (svk_kzg_as_fold_multi_dev + svk_kzg_decide_records_dev) -- equals the oracle's
+    fold-of-folds and its decision; a corrupted proof in one shard fails the verdict of that shard and the final pairing."""
+    import numpy as np
+    import torch
+
+    from snark_verifier_axiom_b200.distributed import OFF_DECIDE_OK, OFF_FOLD_STATUS, OFF_OK, RECORD, LibsvkOps
+
+    V, S, ctx, AS, pv = env
+    dev = torch.device("cuda", 0)
+    n, world, m = 12, 2, 2
+    insts, proofs = forge.forge_batch(S, "bdfg21", n, seed0=1300)
+    for corrupt in (False, True):
+        pr = list(proofs)
+        if corrupt:
+            bad = bytearray(pr[8])
+            bad[9 * 32 + 5] ^= 4  # an evaluation: the proof still reads, its accumulator is wrong
+            pr[8] = bytes(bad)
+        snarks = [V.Snark(i, p) for i, p in zip(insts, pr)]
+        ops = LibsvkOps(pv[0])
+        recs = []
+        for r in range(world):
+            mine = snarks[r * n // world : (r + 1) * n // world]
+            inst, n_inst, pb, lens = pv[0].pack(mine)
+            d_inst, d_pb = torch.from_numpy(inst).to(dev), torch.from_numpy(pb).to(dev)
+            d_accs = torch.zeros(len(mine) * 128, dtype=torch.uint8, device=dev)
+            d_st = torch.zeros(len(mine), dtype=torch.int32, device=dev)
+            d_rec = torch.zeros(RECORD, dtype=torch.uint8, device=dev)
+            ops.local_verify(d_inst, n_inst, d_pb, 1, len(mine), m, d_accs, d_st, d_rec, decide=False)
+            ctx.sync()
+            rec = d_rec.cpu().numpy()
+            assert rec[OFF_DECIDE_OK] == 1 and (d_st.cpu().numpy() == 0).all()  # not decided here
+            assert rec[OFF_OK] == 1
+            recs.append(rec)
+        gathered = torch.from_numpy(np.stack([r[:128] for r in recs]).reshape(-1).copy()).to(dev)
+        d_final = torch.zeros(RECORD, dtype=torch.uint8, device=dev)
+        ops.fold(1, world, gathered, d_final)
+        ops.decide(1, d_final)
+        ctx.sync()
+        f = d_final.cpu().numpy()
+        assert int(np.frombuffer(f[OFF_FOLD_STATUS : OFF_FOLD_STATUS + 4].tobytes(), np.int32)[0]) == 0
+        # oracle: fold each shard (groups of m), then fold the two results flat, then decide
+        pairs = []
+        for i, p in zip(insts, pr):
+            a = api.succinct_verify(S.dk.svk, S.protocol, i, p, "bdfg21")[0]
+            pairs.append((a.lhs.pt, a.rhs.pt))
+        shard_accs = [api.fold(pairs[r * n // world : (r + 1) * n // world], m)[0] for r in range(world)]
+        for r in range(world):
+            got = V.KzgAccumulator.from_bytes(recs[r][:128].tobytes())
+            assert (got.lhs, got.rhs) == shard_accs[r]
+        final = api.fold(shard_accs, 0)[0]
+        got = V.KzgAccumulator.from_bytes(f[:128].tobytes())
+        assert (got.lhs, got.rhs) == final
+        assert bool(f[OFF_DECIDE_OK]) == api.decide(S.dk, final) == (not corrupt)
