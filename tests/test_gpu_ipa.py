@@ -156,3 +156,38 @@ def test_ipa_decide_unrepresentable_inputs_fail(ctx):
     assert V.IpaAs.decide_batch(c, V.IpaDecidingKey(g_bad, C.id), [V.IpaAccumulator(xi, u)]).tolist() == [3]
     # the same key/accumulator under the wrong curve id
     assert V.IpaAs.decide_batch(c, V.IpaDecidingKey(g, pasta.VESTA.id), [V.IpaAccumulator(xi, u)]).tolist() == [3]
+
+
+@pytest.mark.parametrize("zk", [False, True])
+def test_ipa_and_ipa_as_like_the_reference_tests(ctx, zk):
+    """`test_ipa` (pcs/ipa.rs:407-446) and `test_ipa_as` (pcs/ipa/accumulation.rs:212-280) with the NativeLoader pieces on the GPU:
+    commit / the two `Msm::evaluate`s of `succinct_verify` through svk_msm_curve, `IpaAs::decide` through svk_ipa_decide_batch;
+    proving and the transcript stay in the oracle (prover-side code is out of scope)."""
+    V, c = ctx
+    C = pasta.PALLAS
+    rng = random.Random(2024 + zk)
+    k = 4
+    pk = ipa.IpaProvingKey.rand(C, k, zk, rng)
+    gpu_msm = lambda scalars, points: V.multi_scalar_multiplication_on(c, C.id, [s % C.n for s in scalars], points)  # noqa: E731
+    dk = V.IpaDecidingKey(pk.g, C.id)
+    accs = []
+    for _ in range(3):
+        p = [rng.randrange(C.n) for _ in range(1 << k)]
+        omega = rng.randrange(C.n) if zk else None
+        com = pk.commit(p, omega, msm=gpu_msm)
+        assert com == pk.commit(p, omega)
+        z = rng.randrange(C.n)
+        v = ipa.poly_eval(p, z, C.n)
+        tw = ipa.HashTranscript(C)
+        ipa.ipa_create_proof(pk, p, z, omega, tw, rng)
+        proof = ipa.IpaProof.read(zk, k, ipa.HashTranscript(C, tw.finalize()))
+        acc = ipa.ipa_succinct_verify(pk, [(1, com)], z, v, proof, msm=gpu_msm)  # asserts C_k == c[U] + v'[H'] on device results
+        V.IpaAs.decide(c, dk, V.IpaAccumulator(acc.xi, acc.u))  # assert!(IpaAs::decide(&dk, accumulator).is_ok())
+        accs.append(acc)
+    tw = ipa.HashTranscript(C)
+    ipa.ipa_as_create_proof(pk, accs, tw, rng)
+    folded = ipa.ipa_as_verify(pk, accs, ipa.HashTranscript(C, tw.finalize()), msm=gpu_msm)
+    V.IpaAs.decide(c, dk, V.IpaAccumulator(folded.xi, folded.u))
+    V.IpaAs.decide_all(c, dk, [V.IpaAccumulator(a.xi, a.u) for a in accs + [folded]])
+    with pytest.raises(V.Error):
+        V.IpaAs.decide(c, dk, V.IpaAccumulator(folded.xi, C.add(folded.u, C.gen)))

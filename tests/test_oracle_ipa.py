@@ -126,3 +126,43 @@ def test_device_point_templates_over_pasta_curves(lib):
         # off-curve input is rejected
         bad = (C.gen[0], (C.gen[1] + 1) % C.p)
         assert lib.host_curve_muladd(C.id, limbs(bad), limbs([5]), limbs((0, 0)), (ctypes.c_uint32 * 16)()) == 1
+
+
+@pytest.mark.parametrize("zk", [False, True])
+def test_ipa_prove_verify_decide_like_the_reference(zk):
+    """The reference's `test_ipa` (pcs/ipa.rs:407-446) and `test_ipa_as` (pcs/ipa/accumulation.rs:212-280) over the oracle:
+    random polynomial -> create_proof -> read_proof -> succinct_verify -> (accumulate) -> decide."""
+    C = pasta.PALLAS
+    rng = random.Random(99 + zk)
+    k = 3
+    pk = ipa.IpaProvingKey.rand(C, k, zk, rng)
+    accs = []
+    for _ in range(3):
+        p = [rng.randrange(C.n) for _ in range(1 << k)]
+        omega = rng.randrange(C.n) if zk else None
+        c = pk.commit(p, omega)
+        z = rng.randrange(C.n)
+        v = ipa.poly_eval(p, z, C.n)
+        tw = ipa.HashTranscript(C)
+        made = ipa.ipa_create_proof(pk, p, z, omega, tw, rng)
+        tr = ipa.HashTranscript(C, tw.finalize())
+        proof = ipa.IpaProof.read(zk, k, tr)
+        acc = ipa.ipa_succinct_verify(pk, [(1, c)], z, v, proof)
+        assert (acc.xi, acc.u) == (made.xi, made.u)
+        assert ipa.decide(C, pk.g, acc) == 0
+        with pytest.raises(AssertionError):
+            ipa.ipa_succinct_verify(pk, [(1, c)], z, (v + 1) % C.n, proof)
+        accs.append(acc)
+    tw = ipa.HashTranscript(C)
+    ipa.ipa_as_create_proof(pk, accs, tw, rng)
+    folded = ipa.ipa_as_verify(pk, accs, ipa.HashTranscript(C, tw.finalize()))
+    assert ipa.decide(C, pk.g, folded) == 0
+    # a wrong accumulator among the inputs: the honest prover's L/R no longer match the verifier's commitment, so the succinct
+    # check fails (NativeLoader's `ec_point_assert_eq` panics there, loader/native.rs:81-85) -- before `decide` is ever reached
+    bad = [accs[0], ipa.IpaAccumulator(accs[1].xi, C.add(accs[1].u, C.gen)), accs[2]]
+    tw = ipa.HashTranscript(C)
+    ipa.ipa_as_create_proof(pk, bad, tw, rng)
+    with pytest.raises(AssertionError):
+        ipa.ipa_as_verify(pk, bad, ipa.HashTranscript(C, tw.finalize()))
+    # `decide` is what catches a folded accumulator whose U is not commit(G, h)
+    assert ipa.decide(C, pk.g, ipa.IpaAccumulator(folded.xi, C.add(folded.u, C.gen))) == 3
