@@ -61,13 +61,13 @@ static size_t schedule_msm(const std::vector<MsmTermDev>& terms, std::vector<std
     else {
       var_lanes_items[var_lane_base + (n_var % var_lanes)].push_back({0, 0, t.base, t.slot, 0, 0});
       n_var++;
-      total += 161 + 64 * 16;
+      total += 133 + 50 * 16;
     }
   }
   u32 used = std::min(n_var, var_lanes);
   for (u32 l = 0; l < used; l++) {  // this side's k_msm_var partial sums
     lanes[rr++ % L].push_back({3, 0, (int32_t)(var_lane_base + l), -1, 0, 0});
-    total += 252 * 7 + 16;
+    total += 255 * 7 + 16;
   }
   // fixed-base table additions: a flat list of (term, window) pairs dealt evenly, `per` per lane, padded with no-ops
   size_t fixed_windows = fixed_terms.size() * SVK_FIXED_WINDOWS;
@@ -332,6 +332,10 @@ static int protocol_upload(svk_ctx* ctx, svk_host::CompiledProtocol& cp, int mos
   if (const char* e = getenv("SVK_VAR_LANES")) pd->var_lanes = (u32)std::max(1, std::min(8, atoi(e)));
   bool rhs_var = false;
   for (auto& t : rhs) rhs_var = rhs_var || (t.slot >= 0 && !t.fixed);
+  // a thread carries at most SVK_VAR_TERMS_MAX (16) terms: protocols with more variable bases (lookups, several proofs) get more lanes
+  u32 lhs_var = 0;
+  for (auto& t : lhs) lhs_var += (t.slot >= 0 && !t.fixed) ? 1 : 0;
+  pd->var_lanes = std::max<u32>(pd->var_lanes, (lhs_var + 15) / 16);
   std::vector<std::vector<MsmWork>> vlanes(pd->var_lanes + (rhs_var ? 1 : 0));
   std::vector<FixedSlot> fl, fr;
   pd->msm_work_modmul = schedule_msm(lhs, vlanes, 0, pd->var_lanes, wl, ol, fl, pd->fixed_per_lhs) +

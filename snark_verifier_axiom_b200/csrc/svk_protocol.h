@@ -33,7 +33,7 @@ struct FixedSlot {
   int32_t w;     // 8-bit window index
   int32_t slot;  // scalar slot
 };
-#define SVK_MSM_LANES 16
+#define SVK_MSM_LANES 1
 #define SVK_FIXED_WINDOWS 32   // 8-bit windows of a 256-bit scalar
 #define SVK_FIXED_DIGITS 256   // table entries per window
 
