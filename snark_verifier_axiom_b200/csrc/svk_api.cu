@@ -48,8 +48,9 @@ static int upload(svk_ctx* ctx, T** d, const std::vector<T>& v) {
 // `var_lane_base`: index of this side's first k_msm_var lane; `var_lanes`: how many lanes this side may use.
 static size_t schedule_msm(const std::vector<MsmTermDev>& terms, std::vector<std::vector<MsmWork>>& var_lanes_items, u32 var_lane_base,
                            u32 var_lanes, std::vector<MsmWork>& work, std::vector<u32>& lane_off, std::vector<FixedSlot>& fixed_sched,
-                           u32& fixed_per) {
+                           u32& fixed_per, u32 fixed_bits) {
   const int L = SVK_MSM_LANES;
+  const size_t FW = 256 / fixed_bits;  // table windows per fixed base
   std::vector<std::vector<MsmWork>> lanes(L);
   size_t total = 0;
   int rr = 0;
@@ -70,14 +71,14 @@ static size_t schedule_msm(const std::vector<MsmTermDev>& terms, std::vector<std
     total += 255 * 7 + 16;
   }
   // fixed-base table additions: a flat list of (term, window) pairs dealt evenly, `per` per lane, padded with no-ops
-  size_t fixed_windows = fixed_terms.size() * SVK_FIXED_WINDOWS;
+  size_t fixed_windows = fixed_terms.size() * FW;
   size_t per = (fixed_windows + L - 1) / L;
   fixed_per = (u32)per;
   fixed_sched.assign(per * L, FixedSlot{-1, 0, 0});
   for (size_t i = 0; i < fixed_windows; i++) {
-    const MsmTermDev& ft = fixed_terms[i / SVK_FIXED_WINDOWS];
+    const MsmTermDev& ft = fixed_terms[i / FW];
     size_t lane = i / per, j = i % per;
-    fixed_sched[lane * per + j] = FixedSlot{ft.base, (int32_t)(i % SVK_FIXED_WINDOWS), ft.slot};
+    fixed_sched[lane * per + j] = FixedSlot{ft.base, (int32_t)(i % FW), ft.slot};
     total += 11;
   }
   work.clear(); lane_off.assign(L + 1, 0);
@@ -338,8 +339,11 @@ static int protocol_upload(svk_ctx* ctx, svk_host::CompiledProtocol& cp, int mos
   pd->var_lanes = std::max<u32>(pd->var_lanes, (lhs_var + 15) / 16);
   std::vector<std::vector<MsmWork>> vlanes(pd->var_lanes + (rhs_var ? 1 : 0));
   std::vector<FixedSlot> fl, fr;
-  pd->msm_work_modmul = schedule_msm(lhs, vlanes, 0, pd->var_lanes, wl, ol, fl, pd->fixed_per_lhs) +
-                        schedule_msm(rhs, vlanes, pd->var_lanes, 1, wr, orr, fr, pd->fixed_per_rhs);
+  // 16-bit windows halve the table additions of k_msm_sum; their tables (67 MB per base) are used while they stay under ~3 GB
+  pd->fixed_bits = fixed.size() <= 48 ? SVK_FIXED_BITS_LARGE : SVK_FIXED_BITS_SMALL;
+  if (const char* e = getenv("SVK_FIXED_BITS")) pd->fixed_bits = atoi(e) == 16 ? 16 : 8;
+  pd->msm_work_modmul = schedule_msm(lhs, vlanes, 0, pd->var_lanes, wl, ol, fl, pd->fixed_per_lhs, pd->fixed_bits) +
+                        schedule_msm(rhs, vlanes, pd->var_lanes, 1, wr, orr, fr, pd->fixed_per_rhs, pd->fixed_bits);
   if (upload(ctx, &pd->d_fixed_lhs, fl) || upload(ctx, &pd->d_fixed_rhs, fr)) { delete pd; return -1; }
   std::vector<u32> vloff;
   for (auto& l : vlanes) {
@@ -354,13 +358,13 @@ static int protocol_upload(svk_ctx* ctx, svk_host::CompiledProtocol& cp, int mos
   if (upload(ctx, &pd->d_var_lane_off, vloff)) { delete pd; return -1; }
   if (upload(ctx, &pd->d_var_items, var_items) || upload(ctx, &pd->d_work_lhs, wl) || upload(ctx, &pd->d_lane_off_lhs, ol) || upload(ctx, &pd->d_work_rhs, wr) ||
       upload(ctx, &pd->d_lane_off_rhs, orr)) { delete pd; return -1; }
-  pd->table_key = std::to_string(ctx->device) + ":" + std::string((const char*)fixed.data(), fixed.size() * sizeof(G1Affine));
+  pd->table_key = std::to_string(ctx->device) + ":" + std::to_string(pd->fixed_bits) + ":" + std::string((const char*)fixed.data(), fixed.size() * sizeof(G1Affine));
   bool need_tables = false;
   {
     std::lock_guard<std::mutex> lk(g_table_mu);
     SharedTable& st = g_tables[pd->table_key];
     if (!st.d) {
-      if (cudaMalloc(&st.d, fixed.size() * SVK_FIXED_WINDOWS * SVK_FIXED_DIGITS * sizeof(G1Affine)) != cudaSuccess) { g_tables.erase(pd->table_key); delete pd; return svk_fail(ctx, "fixed table alloc"); }
+      if (cudaMalloc(&st.d, fixed.size() * (256 / pd->fixed_bits) * ((size_t)1 << pd->fixed_bits) * sizeof(G1Affine)) != cudaSuccess) { g_tables.erase(pd->table_key); delete pd; return svk_fail(ctx, "fixed table alloc"); }
       need_tables = true;
     }
     st.refs++;

@@ -34,8 +34,9 @@ struct FixedSlot {
   int32_t slot;  // scalar slot
 };
 #define SVK_MSM_LANES 1
-#define SVK_FIXED_WINDOWS 32   // 8-bit windows of a 256-bit scalar
-#define SVK_FIXED_DIGITS 256   // table entries per window
+// Fixed-base tables use `fixed_bits`-wide windows (8 or 16, chosen per protocol): 256 / bits windows of 2^bits entries per base.
+#define SVK_FIXED_BITS_SMALL 8    // 524 KB per base
+#define SVK_FIXED_BITS_LARGE 16   // 67 MB per base, half the table additions; used while the tables stay under ~3 GB
 
 struct ProtocolDevice {
   int mos = 0;
@@ -59,7 +60,8 @@ struct ProtocolDevice {
   u32 *d_lane_off_lhs = nullptr, *d_lane_off_rhs = nullptr;
   FixedSlot *d_fixed_lhs = nullptr, *d_fixed_rhs = nullptr;  // [lane][per] table additions
   u32 fixed_per_lhs = 0, fixed_per_rhs = 0;
-  G1Affine* d_fixed_tables = nullptr;  // [n_pre + 1][32 windows][256 digits]: d * 2^(8w) * B, affine Montgomery (4.7 MB for 9 bases)
+  u32 fixed_bits = SVK_FIXED_BITS_SMALL;
+  G1Affine* d_fixed_tables = nullptr;  // [n_pre + 1][256 / bits windows][2^bits digits]: d * 2^(bits w) * B, affine Montgomery
   MsmWork* d_var_items = nullptr;      // variable-base terms of both sides; partial index = position here
   u32 n_var = 0;
   std::string table_key;               // key of the shared fixed-base table (svk_api.cu: g_tables)

@@ -132,21 +132,24 @@ __device__ __noinline__ G1Jac g1_mul_window4(const G1Affine& p, const u32* k) {
   return acc;
 }
 
-// Fixed-base window tables: tables[(b * 32 + w) * 256 + d] = d * 2^(8w) * fixed_bases[b]  (d = 0: identity).
-// One (base, window) per thread; run once per compiled protocol (255 additions + affine conversions each).
-__global__ void __launch_bounds__(32) k_fixed_tables(u32 n_fixed, const G1Affine* fixed_bases, G1Affine* tables) {
-  u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_fixed * SVK_FIXED_WINDOWS) return;
-  u32 b = t / SVK_FIXED_WINDOWS, w = t % SVK_FIXED_WINDOWS;
+// Fixed-base window tables: tables[((b * W + w) << bits) + d] = d * 2^(bits w) * fixed_bases[b]  (d = 0: identity), W = 256 / bits.
+// One (base, window, chunk of 256 digits) per thread; run once per compiled protocol and key (shared process-wide).
+__global__ void __launch_bounds__(64) k_fixed_tables(u32 n_fixed, u32 bits, const G1Affine* fixed_bases, G1Affine* tables) {
+  u32 W = 256 / bits, chunks = (1u << bits) / 256;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)n_fixed * W * chunks) return;
+  u32 ch = (u32)(t % chunks);
+  u32 bw = (u32)(t / chunks);
+  u32 b = bw / W, w = bw % W;
   G1Jac pw = G1Jac::from_affine(fixed_bases[b]);
-  for (u32 k = 0; k < 8 * w; k++) pw = pw.dbl();
+  for (u32 k = 0; k < bits * w; k++) pw = pw.dbl();
   G1Affine base = pw.to_affine();
-  G1Affine* out = tables + (size_t)t * SVK_FIXED_DIGITS;
-  out[0] = G1Affine::identity();
-  G1Jac acc = G1Jac::identity();
-  for (u32 d = 1; d < SVK_FIXED_DIGITS; d++) {
+  u32 k0[8] = {ch * 256, 0, 0, 0, 0, 0, 0, 0};
+  G1Jac acc = g1_scalar_mul(base, k0);
+  G1Affine* out = tables + ((size_t)bw << bits) + (size_t)ch * 256;
+  for (u32 d = 0; d < 256; d++) {
+    out[d] = acc.to_affine();  // identity -> (0, 0)
     acc = acc.add_affine(base);
-    out[d] = acc.to_affine();
   }
 }
 
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(64) k_msm_var(size_t n_items, const MsmWork* v
 // work: per side, per lane a list of items of kind 1 (fixed-base window slice), 2 (add base), 3 (add partial #base)
 __global__ void __launch_bounds__(128) k_msm_sum(size_t n_items, const MsmWork* work_lhs, const u32* off_lhs, const MsmWork* work_rhs,
                                                  const u32* off_rhs, const FixedSlot* fixed_lhs, u32 per_lhs, const FixedSlot* fixed_rhs,
-                                                 u32 per_rhs, const G1Affine* fixed_bases, const G1Affine* tables,
+                                                 u32 per_rhs, u32 fixed_bits, const G1Affine* fixed_bases, const G1Affine* tables,
                                                  const G1Affine* pts, const u32* scalars, const G1Jac* partials, G1Jac* sums) {
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t item = gid / MSM_LANES;
@@ -204,12 +207,25 @@ __global__ void __launch_bounds__(128) k_msm_sum(size_t n_items, const MsmWork* 
   // fixed-base table additions: the same trip count on every lane
   const FixedSlot* fsched = (blockIdx.y ? fixed_rhs : fixed_lhs);
   u32 per = blockIdx.y ? per_rhs : per_lhs;
-  for (u32 j = 0; j < per; j++) {
+  // table entries are fetched one step ahead of their use (the address depends on the scalar only): the 16-bit tables are
+  // HBM-resident (67 MB per base) and an L2 / DRAM round trip is shorter than the mixed addition that covers it
+  const u32 FW = 256 / fixed_bits, dmask = (1u << fixed_bits) - 1;
+  auto fetch = [&](u32 j, G1Affine& e) -> bool {
     FixedSlot fs = fsched[lane * per + j];
-    if (fs.base < 0) continue;
-    u32 word = scalars[((size_t)fs.slot * n_items + it) * 8 + (fs.w >> 2)];
-    u32 d = (word >> ((fs.w & 3) * 8)) & 0xff;
-    acc = acc.add_affine(tables[((size_t)fs.base * SVK_FIXED_WINDOWS + fs.w) * SVK_FIXED_DIGITS + d]);
+    if (fs.base < 0) return false;
+    u32 bit = (u32)fs.w * fixed_bits;
+    u32 d = (scalars[((size_t)fs.slot * n_items + it) * 8 + (bit >> 5)] >> (bit & 31)) & dmask;
+    if (d == 0) return false;
+    e = tables[(((size_t)fs.base * FW + fs.w) << fixed_bits) + d];
+    return true;
+  };
+  G1Affine nxt = G1Affine::identity();
+  bool have = per ? fetch(0, nxt) : false;
+  for (u32 j = 0; j < per; j++) {
+    G1Affine cur = nxt;
+    bool use = have;
+    if (j + 1 < per) have = fetch(j + 1, nxt);
+    if (use) acc = acc.add_affine(cur);
   }
   for (u32 wi = off[lane]; wi < off[lane + 1]; wi++) {
     MsmWork wk = work[wi];
@@ -218,10 +234,11 @@ __global__ void __launch_bounds__(128) k_msm_sum(size_t n_items, const MsmWork* 
       const uint4* sp = reinterpret_cast<const uint4*>(scalars + ((size_t)wk.slot * n_items + it) * 8);
       uint4 lo = sp[0], hi = sp[1];
       k[0] = lo.x; k[1] = lo.y; k[2] = lo.z; k[3] = lo.w; k[4] = hi.x; k[5] = hi.y; k[6] = hi.z; k[7] = hi.w;
-      const G1Affine* tb = tables + (size_t)wk.base * SVK_FIXED_WINDOWS * SVK_FIXED_DIGITS;
+      const G1Affine* tb = tables + (((size_t)wk.base * FW) << fixed_bits);
       for (int w = wk.w0; w < wk.w1; w++) {
-        u32 d = (k[w >> 2] >> ((w & 3) * 8)) & 0xff;
-        acc = acc.add_affine(tb[w * SVK_FIXED_DIGITS + d]);
+        u32 bit = (u32)w * fixed_bits;
+        u32 d = (k[bit >> 5] >> (bit & 31)) & dmask;
+        acc = acc.add_affine(tb[((size_t)w << fixed_bits) + d]);
       }
     } else if (wk.kind == 2) {
       acc = acc.add_affine(wk.fixed ? fixed_bases[wk.base] : pts[(size_t)wk.base * n_items + it]);
@@ -332,8 +349,9 @@ __global__ void __launch_bounds__(64) k_old_accumulators(size_t n_items, u32 n_o
 
 int svk_fixed_tables_launch(svk_ctx* ctx, ProtocolDevice* pd) {
   u32 n_fixed = pd->n_pre + 1;
-  u32 total = n_fixed * SVK_FIXED_WINDOWS;
-  SVK_LAUNCH(ctx, "k_fixed_tables", k_fixed_tables<<<(total + 31) / 32, 32, 0, ctx->stream>>>(n_fixed, pd->d_fixed, pd->d_fixed_tables));
+  size_t total = (size_t)n_fixed * (256 / pd->fixed_bits) * ((1u << pd->fixed_bits) / 256);
+  SVK_LAUNCH(ctx, "k_fixed_tables",
+             k_fixed_tables<<<(unsigned)((total + 63) / 64), 64, 0, ctx->stream>>>(n_fixed, pd->fixed_bits, pd->d_fixed, pd->d_fixed_tables));
   SVK_CUDA(ctx, cudaGetLastError());
   SVK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -425,7 +443,7 @@ int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const
     dim3 grid((unsigned)((n * MSM_LANES + 127) / 128), 2);
     SVK_LAUNCH(ctx, "k_msm_sum",
                k_msm_sum<<<grid, 128, 0, s>>>(n, pd->d_work_lhs, pd->d_lane_off_lhs, pd->d_work_rhs, pd->d_lane_off_rhs, pd->d_fixed_lhs,
-                                              pd->fixed_per_lhs, pd->d_fixed_rhs, pd->fixed_per_rhs, pd->d_fixed,
+                                              pd->fixed_per_lhs, pd->d_fixed_rhs, pd->fixed_per_rhs, pd->fixed_bits, pd->d_fixed,
                                               pd->d_fixed_tables, d_pts, d_scalars, d_partials, d_sums));
     SVK_LAUNCH(ctx, "k_to_affine", k_to_affine<<<(unsigned)((2 * n + 127) / 128), 128, 0, s>>>(n, d_sums, d_err, d_out_acc, acc_stride));
   } else {
