@@ -99,8 +99,9 @@ __device__ __forceinline__ bool load_acc_point(G1Affine& b, const uint8_t* p) {
   return canon && g1_on_curve(b);
 }
 
+template <bool AFFINE>
 __global__ void __launch_bounds__(64) k_group_var(size_t n_seg, size_t n, size_t m, u32 vpl, const uint8_t* accs, const u32* scalars,
-                                                  G1Jac* tables, G1Jac* partials, int32_t* status, size_t status_stride_words) {
+                                                  G1Jac* tables, Fq* prefix, G1Jac* partials, int32_t* status, size_t status_stride_words) {
   size_t n_groups = (n + m - 1) / m;
   size_t n_threads = n_seg * n_groups * 2 * vpl;
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -123,7 +124,8 @@ __global__ void __launch_bounds__(64) k_group_var(size_t n_seg, size_t n, size_t
     straus_recode(k[nt]);
     straus_build_table(tables + ((size_t)nt * STRAUS_TABLE) * n_threads + gid, n_threads, base);
   }
-  G1Jac acc = straus_run(&k[0][0], nt, tables + gid, n_threads);
+  if (AFFINE) straus_normalize(tables + gid, prefix + gid, n_threads, nt * STRAUS_TABLE);
+  G1Jac acc = straus_run<AFFINE>(&k[0][0], nt, tables + gid, n_threads);
   partials[gid] = acc;
 }
 
@@ -191,9 +193,18 @@ int svk_fold_launch_seg(svk_ctx* ctx, size_t n_seg, size_t n, const uint8_t* d_a
     G1Jac *d_tables, *d_partials;
     if (svk_scratch(ctx, 17, (terms_per_thread * 16 * var_threads + 1) * sizeof(G1Jac), (void**)&d_tables)) return -1;
     if (svk_scratch(ctx, 18, (var_threads + 1) * sizeof(G1Jac), (void**)&d_partials)) return -1;
-    SVK_LAUNCH(ctx, "k_group_var",
-               k_group_var<<<(unsigned)((var_threads + 63) / 64), 64, 0, s>>>(n_seg, cnt, m, vpl, cur, d_scal, d_tables, d_partials, d_status,
-                                                                              out_stride / 4));
+    // threads that own >= 3 terms normalise their tables to affine (one inversion per thread) and use mixed additions
+    if (terms_per_thread >= 3) {
+      Fq* d_prefix;
+      if (svk_scratch(ctx, 22, (terms_per_thread * 16 * var_threads + 1) * sizeof(Fq), (void**)&d_prefix)) return -1;
+      SVK_LAUNCH(ctx, "k_group_var",
+                 k_group_var<true><<<(unsigned)((var_threads + 63) / 64), 64, 0, s>>>(n_seg, cnt, m, vpl, cur, d_scal, d_tables, d_prefix, d_partials,
+                                                                                      d_status, out_stride / 4));
+    } else {
+      SVK_LAUNCH(ctx, "k_group_var",
+                 k_group_var<false><<<(unsigned)((var_threads + 63) / 64), 64, 0, s>>>(n_seg, cnt, m, vpl, cur, d_scal, d_tables, nullptr, d_partials,
+                                                                                       d_status, out_stride / 4));
+    }
     SVK_LAUNCH(ctx, "k_group_sum",
                k_group_sum<<<(unsigned)((total_groups * 2 + 127) / 128), 128, 0, s>>>(n_seg, cnt, m, vpl, cur, d_partials, dst,
                                                                                       last ? out_stride : 128, d_status, out_stride / 4));

@@ -5,8 +5,9 @@
 //
 // Recoding without a carry chain at read time: k' = k + C with C = Σ_{i<51} 16 * 32^i (fits 256 bits for any k < 2^255), then
 //   digit_i = ((k' >> 5 i) & 31) - 16  in [-16, 15]   (i < 51),      digit_51 = k' >> 255  in {0, 1}
-// and Σ digit_i 32^i = k.  Per term: a 16-entry Jacobian table {1..16} P (1 + 7 doublings, 7 mixed additions) and
-// <= 52 table additions (a digit is zero with probability 1/32); per thread 255 shared doublings.  Against the unsigned
+// and Σ digit_i 32^i = k.  Per term: a 16-entry table {1..16} P (1 + 7 doublings, 7 mixed additions, then normalised to affine
+// together with all other tables of the thread) and <= 52 MIXED table additions (a digit is zero with probability 1/32); per
+// thread 255 shared doublings and one inversion.  Against the unsigned
 // 4-bit windows of the first version (15-entry table, 64 additions, 252 doublings): ~10 additions fewer per term.
 #pragma once
 #include "g1.cuh"
@@ -47,10 +48,40 @@ HD void straus_build_table(JacT<F>* tb, size_t stride, const AffT<F>& base) {
   }
 }
 
-// acc = Σ_t k[t] * base_t over `nt` recoded scalars k[t] (8 limbs each, row stride 8) whose tables start at
+// Batch normalisation of a thread's tables to affine (Montgomery's trick over all its entries: one Fermat inversion per thread):
+// X, Y of every entry are overwritten by the affine coordinates ((0, 0) for an identity entry), so that the main loop uses mixed
+// additions (9.9 instead of 14.8 product-equivalents each).  `prefix` holds the running products of the Z's (n_entries x stride).
+// Per entry 1 + 5 products and a squaring: pays off from ~3 terms per thread on (11 terms: -11 % of the kernel).
+template <class F>
+HD void straus_normalize(JacT<F>* tables, F* prefix, size_t stride, u32 n_entries) {
+  F run = F::one();
+  for (u32 i = 0; i < n_entries; i++) {
+    F z = tables[(size_t)i * stride].Z;
+    if (!z.is_zero()) run = run * z;
+    prefix[(size_t)i * stride] = run;
+  }
+  F inv = run.inv();
+  for (u32 i = n_entries; i-- > 0;) {
+    JacT<F>* e = tables + (size_t)i * stride;
+    F z = e->Z;
+    if (z.is_zero()) {
+      e->X = F::zero();
+      e->Y = F::zero();
+      continue;
+    }
+    F zi = i ? inv * prefix[(size_t)(i - 1) * stride] : inv;
+    inv = inv * z;
+    F zi2 = zi.sqr();
+    e->X = e->X * zi2;
+    e->Y = e->Y * (zi2 * zi);
+  }
+}
+
+// acc = Σ_t k[t] * base_t over `nt` recoded scalars k[t] (8 limbs each, row stride 8) whose NORMALISED tables start at
 // tables[(t * 16) * stride]; entries are fetched one step ahead of their use (the tables of a launch are hundreds of MB and
 // every read misses L2; a table addition is long enough to cover a DRAM round trip).
-template <class F>
+// AFFINE = false: the tables are still Jacobian (threads with one or two terms, where the inversion would not pay): full additions.
+template <bool AFFINE, class F>
 HD JacT<F> straus_run(const u32* k, u32 nt, const JacT<F>* tables, size_t stride) {
   typedef JacT<F> J;
   J acc = J::identity();
@@ -58,7 +89,12 @@ HD JacT<F> straus_run(const u32* k, u32 nt, const JacT<F>* tables, size_t stride
   J nxt = J::identity();
   u32 nn = 0;
   u32 dn = straus_digit(k, STRAUS_WINDOWS - 1, nn);
-  if (dn) nxt = tables[(size_t)(dn - 1) * stride];
+  if (dn) {
+    const J* e = tables + (size_t)(dn - 1) * stride;
+    nxt.X = e->X;
+    nxt.Y = e->Y;
+    if (!AFFINE) nxt.Z = e->Z;
+  }
   for (int w = STRAUS_WINDOWS - 1; w >= 0; w--) {
     if (w != STRAUS_WINDOWS - 1) acc = acc.dbl().dbl().dbl().dbl().dbl();
     for (u32 t = 0; t < nt; t++) {
@@ -70,11 +106,17 @@ HD JacT<F> straus_run(const u32* k, u32 nt, const JacT<F>* tables, size_t stride
       dn = 0;
       if (w2 >= 0) {
         dn = straus_digit(k + 8 * t2, w2, nn);
-        if (dn) nxt = tables[((size_t)t2 * STRAUS_TABLE + (dn - 1)) * stride];
+        if (dn) {
+          const J* e = tables + ((size_t)t2 * STRAUS_TABLE + (dn - 1)) * stride;
+          nxt.X = e->X;
+          nxt.Y = e->Y;
+          if (!AFFINE) nxt.Z = e->Z;
+        }
       }
       if (d) {
         if (ng) cur.Y = cur.Y.neg();
-        acc = acc.add(cur);
+        if (AFFINE) acc = acc.add_affine(AffT<F>{cur.X, cur.Y});
+        else acc = acc.add(cur);
       }
     }
   }

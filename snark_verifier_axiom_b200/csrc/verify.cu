@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(64) k_fixed_tables(u32 n_fixed, u32 bits, cons
 // partials[(lane * n_items) + proof]  (Jacobian)
 #define SVK_VAR_TERMS_MAX 16
 __global__ void __launch_bounds__(64) k_msm_var(size_t n_items, const MsmWork* var_items, const u32* var_lane_off, u32 vpl, const G1Affine* pts,
-                                                const u32* scalars, G1Jac* tables, G1Jac* partials) {
+                                                const u32* scalars, G1Jac* tables, Fq* prefix, G1Jac* partials) {
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= n_items * vpl) return;
   size_t it = gid % n_items;
@@ -187,7 +187,8 @@ __global__ void __launch_bounds__(64) k_msm_var(size_t n_items, const MsmWork* v
     G1Affine base = pts[(size_t)wk.base * n_items + it];
     straus_build_table(tables + ((size_t)nt * STRAUS_TABLE) * n_threads + gid, n_threads, base);
   }
-  G1Jac acc = straus_run(&k[0][0], nt, tables + gid, n_threads);
+  straus_normalize(tables + gid, prefix + gid, n_threads, nt * STRAUS_TABLE);
+  G1Jac acc = straus_run<true>(&k[0][0], nt, tables + gid, n_threads);
   partials[gid] = acc;
 }
 
@@ -262,19 +263,25 @@ __global__ void __launch_bounds__(128) k_msm_sum(size_t n_items, const MsmWork* 
   if (active && lane == 0) sums[(size_t)blockIdx.y * n_items + item] = acc;
 }
 
+// One proof per thread: both sides share ONE Fermat inversion (Montgomery's trick on Z_lhs * Z_rhs; an identity side takes Z := 1).
 __global__ void __launch_bounds__(128) k_to_affine(size_t n_items, const G1Jac* sums, const u32* err, uint8_t* out_acc, size_t acc_stride) {
-  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= 2 * n_items) return;
-  size_t item = gid % n_items;
-  u32 side = (u32)(gid / n_items);
+  size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= n_items) return;
   bool bad = err[item] != SVK_NO_ERR;
-  G1Affine a = bad ? G1Affine::identity() : sums[gid].to_affine();
-  Fq x = a.x.from_mont(), y = a.y.from_mont();
-  uint4* o = reinterpret_cast<uint4*>(out_acc + item * acc_stride + (side ? 64 : 0));
-  o[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
-  o[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
-  o[2] = make_uint4(y.v[0], y.v[1], y.v[2], y.v[3]);
-  o[3] = make_uint4(y.v[4], y.v[5], y.v[6], y.v[7]);
+  G1Jac l = sums[item], r = sums[n_items + item];
+  Fq zl = l.is_identity() ? Fq::one() : l.Z, zr = r.is_identity() ? Fq::one() : r.Z;
+  Fq inv = (zl * zr).inv();
+  G1Affine a[2] = {l.to_affine_with_zinv(inv * zr), r.to_affine_with_zinv(inv * zl)};
+#pragma unroll
+  for (int side = 0; side < 2; side++) {
+    G1Affine p = bad ? G1Affine::identity() : a[side];
+    Fq x = p.x.from_mont(), y = p.y.from_mont();
+    uint4* o = reinterpret_cast<uint4*>(out_acc + item * acc_stride + (side ? 64 : 0));
+    o[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+    o[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+    o[2] = make_uint4(y.v[0], y.v[1], y.v[2], y.v[3]);
+    o[3] = make_uint4(y.v[4], y.v[5], y.v[6], y.v[7]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -436,16 +443,18 @@ int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const
     if (svk_scratch(ctx, 15, 2 * n * sizeof(G1Jac), (void**)&d_sums)) return -1;
     if (pd->n_var) {
       size_t total = n * vpl;
+      Fq* d_prefix;
       if (svk_scratch(ctx, 6, (size_t)terms_per_thread * 16 * total * sizeof(G1Jac), (void**)&d_tables)) return -1;
+      if (svk_scratch(ctx, 21, (size_t)terms_per_thread * 16 * total * sizeof(Fq), (void**)&d_prefix)) return -1;
       SVK_LAUNCH(ctx, "k_msm_var",
-                 k_msm_var<<<(unsigned)((total + 63) / 64), 64, 0, s>>>(n, pd->d_var_items, pd->d_var_lane_off, vpl, d_pts, d_scalars, d_tables, d_partials));
+                 k_msm_var<<<(unsigned)((total + 63) / 64), 64, 0, s>>>(n, pd->d_var_items, pd->d_var_lane_off, vpl, d_pts, d_scalars, d_tables, d_prefix, d_partials));
     }
     dim3 grid((unsigned)((n * MSM_LANES + 127) / 128), 2);
     SVK_LAUNCH(ctx, "k_msm_sum",
                k_msm_sum<<<grid, 128, 0, s>>>(n, pd->d_work_lhs, pd->d_lane_off_lhs, pd->d_work_rhs, pd->d_lane_off_rhs, pd->d_fixed_lhs,
                                               pd->fixed_per_lhs, pd->d_fixed_rhs, pd->fixed_per_rhs, pd->fixed_bits, pd->d_fixed,
                                               pd->d_fixed_tables, d_pts, d_scalars, d_partials, d_sums));
-    SVK_LAUNCH(ctx, "k_to_affine", k_to_affine<<<(unsigned)((2 * n + 127) / 128), 128, 0, s>>>(n, d_sums, d_err, d_out_acc, acc_stride));
+    SVK_LAUNCH(ctx, "k_to_affine", k_to_affine<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(n, d_sums, d_err, d_out_acc, acc_stride));
   } else {
     SVK_CUDA(ctx, cudaMemsetAsync(d_out_acc, 0, n * acc_stride, s));
   }

@@ -317,7 +317,12 @@ extern "C" int host_straus(int nt, const u32* pts_xy, const u32* ks, u32* out_xy
     straus_recode(k[t]);
     straus_build_table(tables + (size_t)t * STRAUS_TABLE, 1, load_aff(pts_xy + 16 * t));
   }
-  G1Jac acc = straus_run(&k[0][0], (u32)nt, tables, 1);
-  store_aff(out_xy, acc.to_affine());
+  G1Jac acc = straus_run<false>(&k[0][0], (u32)nt, tables, 1);
+  static Fq prefix[16 * STRAUS_TABLE];
+  straus_normalize(tables, prefix, 1, (u32)nt * STRAUS_TABLE);
+  G1Jac acc2 = straus_run<true>(&k[0][0], (u32)nt, tables, 1);
+  G1Affine a1 = acc.to_affine(), a2 = acc2.to_affine();
+  if (!(a1.x == a2.x) || !(a1.y == a2.y)) return 2;  // Jacobian-table and normalised-table runs must agree
+  store_aff(out_xy, a1);
   return 0;
 }
