@@ -398,7 +398,8 @@ def run_ours(args):
         tape_other = info["n_fr_mul"] - 600 * n_perm                                    # scalar algebra incl. 3 Fermat chains at 380
         dbl_e, madd_e, add_e = 2 + 5 * S_, 5 + 4 * S_ + D2, 9 + 5 * S_ + D2             # Jacobian dbl / mixed add / add with dot2
         var_canon = info["msm_var_modmul_per_proof"]
-        var_exec = info["n_var_terms"] * (8 * dbl_e + 7 * madd_e + 50 * add_e) + info["var_lanes"] * 255 * dbl_e
+        norm_e = 6 + S_                                                                # per table entry: prefix product, z^-1, z^-2, x, y
+        var_exec = info["n_var_terms"] * (8 * dbl_e + 7 * madd_e + 50 * madd_e + 16 * norm_e) + info["var_lanes"] * (255 * dbl_e + chain_exec)
         work = {
             "k_tape": n * info["n_fr_mul"],
             "k_decompress": n * info["n_points"] * 372,

@@ -62,13 +62,13 @@ static size_t schedule_msm(const std::vector<MsmTermDev>& terms, std::vector<std
     else {
       var_lanes_items[var_lane_base + (n_var % var_lanes)].push_back({0, 0, t.base, t.slot, 0, 0});
       n_var++;
-      total += 133 + 50 * 16;
+      total += 133 + 50 * 11 + 16 * 7;
     }
   }
   u32 used = std::min(n_var, var_lanes);
   for (u32 l = 0; l < used; l++) {  // this side's k_msm_var partial sums
     lanes[rr++ % L].push_back({3, 0, (int32_t)(var_lane_base + l), -1, 0, 0});
-    total += 255 * 7 + 16;
+    total += 255 * 7 + 380 + 16;
   }
   // fixed-base table additions: a flat list of (term, window) pairs dealt evenly, `per` per lane, padded with no-ops
   size_t fixed_windows = fixed_terms.size() * FW;
@@ -386,7 +386,7 @@ int svk_protocol_info(svk_ctx* ctx, int proto, uint32_t* out) {
   ProtocolDevice* pd = ctx->protocols[proto];
   out[0] = pd->proof_len; out[1] = pd->n_instances; out[2] = pd->n_challenges; out[3] = pd->n_regs; out[4] = pd->n_ops;
   out[5] = (u32)pd->n_perm; out[6] = pd->verify_valid ? 1 : 0; out[7] = (u32)pd->n_fr_mul; out[8] = pd->n_lhs; out[9] = pd->n_rhs;
-  out[10] = (u32)pd->points.size(); out[11] = pd->n_scalar_slots; out[12] = (u32)pd->msm_work_modmul; out[13] = (u32)(pd->n_var * (133 + 50 * 16) + pd->var_lanes_total * 255 * 7);  /* straus.cuh: table 8 dbl + 7 madd, ~50 additions, 255 doublings */ out[14] = pd->n_var; out[15] = pd->var_lanes_total;
+  out[10] = (u32)pd->points.size(); out[11] = pd->n_scalar_slots; out[12] = (u32)pd->msm_work_modmul; out[13] = (u32)(pd->n_var * (133 + 50 * 11 + 16 * 7) + pd->var_lanes_total * (255 * 7 + 380));  /* straus.cuh: table 8 dbl + 7 madd + normalisation, ~50 mixed additions; 255 doublings + one inversion per lane */ out[14] = pd->n_var; out[15] = pd->var_lanes_total;
   out[16] = pd->n_old; out[17] = pd->acc_limbs; out[18] = pd->acc_bits; out[19] = (u32)pd->transcript_kind;
   return 0;
 }
