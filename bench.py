@@ -393,20 +393,21 @@ def run_ours(args):
         #               cuobjdump / tools/sqr_probe.cu.  roofline.frac uses EXECUTED work, so it is a utilisation (<= 1).
         S_, D2, D3 = 117 / 136, 200 / 136, 264 / 136
         perm_exec = 8 * (3 * (2 * S_ + 1) + 3 * D3) + 57 * ((2 * S_ + 1) + D3 + 2)      # optimised Poseidon, T = 3: 491
-        chain_exec = 252 * S_ + 77                                                      # 4-bit-window Fermat / sqrt chain: 294
+        chain_exec = 252 * S_ + 77                                                      # 4-bit-window square-root chain: 294
+        inv_exec = 80                                                                   # binary-Euclid inversion: ALU work; ~55 IMAD.MOV/IMAD.X per step on the multiply pipe
         n_perm = info["n_poseidon_perms"]
         tape_other = info["n_fr_mul"] - 600 * n_perm                                    # scalar algebra incl. 3 Fermat chains at 380
         dbl_e, madd_e, add_e = 2 + 5 * S_, 5 + 4 * S_ + D2, 9 + 5 * S_ + D2             # Jacobian dbl / mixed add / add with dot2
         var_canon = info["msm_var_modmul_per_proof"]
         norm_e = 6 + S_                                                                # per table entry: prefix product, z^-1, z^-2, x, y
-        var_exec = info["n_var_terms"] * (8 * dbl_e + 7 * madd_e + 50 * madd_e + 16 * norm_e) + info["var_lanes"] * (255 * dbl_e + chain_exec)
+        var_exec = info["n_var_terms"] * (8 * dbl_e + 7 * madd_e + 50 * madd_e + 16 * norm_e) + info["var_lanes"] * (255 * dbl_e + inv_exec)
         work = {
             "k_tape": n * info["n_fr_mul"],
             "k_decompress": n * info["n_points"] * 372,
             "k_msm_var": n * var_canon,
         }
         work_exec = {
-            "k_tape": n * (n_perm * perm_exec + tape_other - 3 * (380 - chain_exec)),
+            "k_tape": n * (n_perm * perm_exec + tape_other - 3 * (380 - inv_exec)),
             "k_decompress": n * info["n_points"] * (chain_exec + 12),
             "k_msm_var": n * var_exec,
         }

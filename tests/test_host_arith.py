@@ -67,8 +67,11 @@ def test_field_ops(lib):
         for a in [m - 1 - rng.randrange(1 << 40) for _ in range(100)] + [rng.randrange(m) for _ in range(2000)] + [
                 (1 << 254) - 1 - rng.randrange(1 << 33) for _ in range(50)] + [sum(0xFFFFFFFF << (32 * i) for i in rng.sample(range(8), 5)) % m for _ in range(100)]:
             assert op(f, 8, a) == a * a * Ri % m
+        for a in vals[:12] + [rng.randrange(m) for _ in range(300)] + [m - 1, m - 2, 3, (m + 1) // 2, 1 << 253]:
+            want = pow(a, -1, m) * Rm % m if a else 0
+            assert op(f, 4, a * Rm % m) == want  # binary extended Euclid
         for a in vals[:12]:
-            assert op(f, 4, a * Rm % m) == (pow(a, -1, m) * Rm % m if a else 0)
+            assert op(f, 11, a * Rm % m) == (pow(a, -1, m) * Rm % m if a else 0)  # Fermat chain
         assert lib.host_is_canonical(f, limbs([m - 1])) == 1 and lib.host_is_canonical(f, limbs([m])) == 0
         # to_mont_wide: any 256-bit input (the Keccak challenge, evm.rs:172-182 `u256_to_fe`), worst cases included
         wide = [(1 << 256) - 1, (1 << 256) - 2, 0xFFFFFFFF << 224, m, 2 * m, 5 * m + 3, (1 << 255) + 12345]

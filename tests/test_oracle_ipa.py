@@ -84,8 +84,10 @@ def test_device_field_templates_over_pasta_fields(lib):
             assert op(f, 8, a) == a * a * Ri % m
             b = rng.choice(vals)
             assert op(f, 0, a, b) == a * b * Ri % m
+        for a in vals[:14] + [rng.randrange(m) for _ in range(200)]:
+            assert op(f, 4, a * Rm % m) == (pow(a, -1, m) * Rm % m if a else 0)  # binary extended Euclid over a 255-bit modulus
         for a in vals[:14]:
-            assert op(f, 4, a * Rm % m) == (pow(a, -1, m) * Rm % m if a else 0)  # p - 2 needs a borrow across limb 0 here
+            assert op(f, 11, a * Rm % m) == (pow(a, -1, m) * Rm % m if a else 0)  # Fermat: p - 2 needs a borrow across limb 0 here
 
 
 def test_fused_dot_products_over_pasta_fields(lib):

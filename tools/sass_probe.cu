@@ -4,3 +4,4 @@
 __global__ void k_probe_mul(Fq* a) { a[0] = a[1] * a[2]; }
 __global__ void k_probe_sqr(Fq* a) { a[0] = a[1].sqr(); }
 __global__ void k_probe_dot2(Fq* a) { a[0] = Fq::dot2(a[1], a[2], a[3], a[4]); }
+__global__ void k_probe_inv(Fq* a) { a[threadIdx.x] = a[threadIdx.x + 64].inv(); }
