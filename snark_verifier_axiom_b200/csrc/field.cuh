@@ -218,7 +218,7 @@ struct Fe {
       }
       cmad_row_mod(al, 0, mi);
       of[7] = ptx::addc(of[7], 0);
-    } else {
+      } else {
       u32 mi = (al[0] + of[1]) * P::M0;
       al[0] = ptx::add_cc(al[0], of[1]);
 #pragma unroll
@@ -230,8 +230,33 @@ struct Fe {
       of[7] = ptx::madc_hi(P::mod(7), mi, 0);
       cmad_row_mod(al, 0, mi);
       of[7] = ptx::addc(of[7], 0);
-    }
+      }
   }
+  // T (16 limbs, < 2^510) -> T * 2^-256 mod p: U = (T_lo + M p) / 2^256 by eight pure reduction rows, result = U + T_hi < 2p,
+  // one conditional subtraction.
+  HD static Fe redc_wide(const u32* T) {
+    u32 al[8], of[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) al[i] = T[i];
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      redc_row(al, of, i == 0);
+      redc_row(of, al, false);
+    }
+    Fe r;
+    r.v[0] = ptx::add_cc(al[0], of[1]);
+#pragma unroll
+    for (int j = 1; j < 7; j++) r.v[j] = ptx::addc_cc(al[j], of[j + 1]);
+    r.v[7] = ptx::addc(al[7], 0);
+    // + T_hi
+    r.v[0] = ptx::add_cc(r.v[0], T[8]);
+#pragma unroll
+    for (int j = 1; j < 7; j++) r.v[j] = ptx::addc_cc(r.v[j], T[8 + j]);
+    r.v[7] = ptx::addc(r.v[7], T[15]);
+    reduce_once(r.v);
+    return r;
+  }
+
   HD static Fe sqr_inline(const Fe& x) {
     const u32* a = x.v;
     u32 E[16], O[16];
@@ -284,27 +309,7 @@ struct Fe {
       T[2 * i] = ptx::madc_lo_cc(a[i], a[i], T[2 * i]);
       T[2 * i + 1] = (i < 7) ? ptx::madc_hi_cc(a[i], a[i], T[2 * i + 1]) : ptx::madc_hi(a[i], a[i], T[2 * i + 1]);
     }
-    // Montgomery-reduce the low half
-    u32 al[8], of[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) al[i] = T[i];
-#pragma unroll
-    for (int i = 0; i < 8; i += 2) {
-      redc_row(al, of, i == 0);
-      redc_row(of, al, false);
-    }
-    Fe r;
-    r.v[0] = ptx::add_cc(al[0], of[1]);
-#pragma unroll
-    for (int j = 1; j < 7; j++) r.v[j] = ptx::addc_cc(al[j], of[j + 1]);
-    r.v[7] = ptx::addc(al[7], 0);
-    // + T_hi
-    r.v[0] = ptx::add_cc(r.v[0], T[8]);
-#pragma unroll
-    for (int j = 1; j < 7; j++) r.v[j] = ptx::addc_cc(r.v[j], T[8 + j]);
-    r.v[7] = ptx::addc(r.v[7], T[15]);
-    reduce_once(r.v);
-    return r;
+    return redc_wide(T);
   }
 #if defined(__CUDA_ARCH__)
   static __device__ __noinline__ Fe sqr_call(Fe a) { return sqr_inline(a); }

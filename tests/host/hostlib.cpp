@@ -14,7 +14,7 @@ void host_fe_op(int field, int op, const u32* a, const u32* b, u32* out) {
     switch (op) {
       case 0: r = x * y; break; case 1: r = x + y; break; case 2: r = x - y; break; case 3: r = x.neg(); break;
       case 4: r = x.inv(); break; case 5: r = x.sqrt_candidate(); break; case 6: r = x.to_mont(); break;
-      case 7: r = x.from_mont(); break; case 8: r = x.sqr(); break; case 10: r = x.to_mont_wide(); break; case 11: r = x.inv_fermat(); break; default: r = x.dbl(); break;
+      case 7: r = x.from_mont(); break; case 8: r = x.sqr(); break; case 10: r = x.to_mont_wide(); break; case 11: r = x.inv_fermat(); break; case 13: r = decltype(x)::mul_inline(x, y); break; default: r = x.dbl(); break;
     }
     memcpy(out, r.v, 32);
   } else {
@@ -23,7 +23,7 @@ void host_fe_op(int field, int op, const u32* a, const u32* b, u32* out) {
     switch (op) {
       case 0: r = x * y; break; case 1: r = x + y; break; case 2: r = x - y; break; case 3: r = x.neg(); break;
       case 4: r = x.inv(); break; case 5: r = x.sqrt_candidate(); break; case 6: r = x.to_mont(); break;
-      case 7: r = x.from_mont(); break; case 8: r = x.sqr(); break; case 10: r = x.to_mont_wide(); break; case 11: r = x.inv_fermat(); break; default: r = x.dbl(); break;
+      case 7: r = x.from_mont(); break; case 8: r = x.sqr(); break; case 10: r = x.to_mont_wide(); break; case 11: r = x.inv_fermat(); break; case 13: r = decltype(x)::mul_inline(x, y); break; default: r = x.dbl(); break;
     }
     memcpy(out, r.v, 32);
   }
@@ -256,7 +256,7 @@ static void fe_op_t(int op, const u32* a, const u32* b, u32* out) {
   switch (op) {
     case 0: r = x * y; break; case 1: r = x + y; break; case 2: r = x - y; break; case 3: r = x.neg(); break;
     case 4: r = x.inv(); break; case 6: r = x.to_mont(); break;
-    case 7: r = x.from_mont(); break; case 8: r = x.sqr(); break; case 11: r = x.inv_fermat(); break; default: r = x.dbl(); break;
+    case 7: r = x.from_mont(); break; case 8: r = x.sqr(); break; case 11: r = x.inv_fermat(); break; case 13: r = decltype(x)::mul_inline(x, y); break; default: r = x.dbl(); break;
   }
   memcpy(out, r.v, 32);
 }
