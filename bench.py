@@ -427,6 +427,11 @@ def run_ours(args):
                 traffic_src = tr[name].get("source")
         except (OSError, ValueError, KeyError):
             pass
+        hbm_peak = None  # driver-measured copy bandwidth (MEASURED_PEAKS.json); this path is not bound by it
+        try:
+            hbm_peak = float(json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except (OSError, ValueError, KeyError):
+            pass
         total_work = (sum(work.values()) + work_other) / B  # per 4096-proof batch (fold and pairing not counted: < 8 %)
         total_work_exec = (sum(work_exec.values()) + work_other_exec) / B
         roofline = {
@@ -444,6 +449,7 @@ def run_ours(args):
             "whole_step_frac_canonical": (total_work * world / (ms_per_step * 1e-3)) / peak,
             "hbm_gbs_algorithmic": (h2d + d2h) / (ms_per_step * 1e-3) / 1e9,
             "hbm_gbs_dominant_kernel": (traffic / (ms_launch * 1e-3) / 1e9) if traffic else None,
+            "hbm_peak_gbs": hbm_peak, "hbm_frac_dominant_kernel": (traffic / (ms_launch * 1e-3) / 1e9 / hbm_peak) if (traffic and hbm_peak) else None,
         }
         base = None if args.no_cpu_baseline else cpu_baseline(g, args.cpu_sample, args.group_size, args.scheme)
         out = {
