@@ -191,3 +191,16 @@ def test_ipa_and_ipa_as_like_the_reference_tests(ctx, zk):
     V.IpaAs.decide_all(c, dk, [V.IpaAccumulator(a.xi, a.u) for a in accs + [folded]])
     with pytest.raises(V.Error):
         V.IpaAs.decide(c, dk, V.IpaAccumulator(folded.xi, C.add(folded.u, C.gen)))
+
+
+def test_ipa_decide_against_committed_golden(ctx):
+    """Device vs tests/golden/ipa_golden.json: decide statuses and the commitment MSM for every fixture accumulator."""
+    from .test_oracle_ipa import _load_ipa_golden
+
+    V, c = ctx
+    for C, k, g, accs in _load_ipa_golden():
+        dk = V.IpaDecidingKey(g, C.id)
+        st = V.IpaAs.decide_batch(c, dk, [V.IpaAccumulator(xi, u) for xi, u, _, _ in accs])
+        assert st.tolist() == [s for _, _, _, s in accs]
+        for xi, _, commit, _ in accs[:2]:
+            assert V.multi_scalar_multiplication_on(c, C.id, ipa.h_coeffs(xi, 1, C.n), g) == commit

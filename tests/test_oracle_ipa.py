@@ -168,3 +168,29 @@ def test_ipa_prove_verify_decide_like_the_reference(zk):
         ipa.ipa_as_verify(pk, bad, ipa.HashTranscript(C, tw.finalize()))
     # `decide` is what catches a folded accumulator whose U is not commit(G, h)
     assert ipa.decide(C, pk.g, ipa.IpaAccumulator(folded.xi, C.add(folded.u, C.gen))) == 3
+
+
+def _load_ipa_golden():
+    import json
+
+    with open(os.path.join(HERE, "golden", "ipa_golden.json")) as f:
+        gold = json.load(f)
+    iv = lambda s: int(s, 16)  # noqa: E731
+    pt = lambda p: None if p is None else (iv(p[0]), iv(p[1]))  # noqa: E731
+    for case in gold["cases"]:
+        C = {"pallas": pasta.PALLAS, "vesta": pasta.VESTA}[case["curve"]]
+        g = [pt(p) for p in case["g"]]
+        accs = [([iv(x) for x in a["xi"]], pt(a["u"]), pt(a["commit"]), a["status"]) for a in case["accumulators"]]
+        yield C, case["k"], g, accs
+
+
+def test_oracle_against_committed_ipa_golden():
+    """tests/golden/ipa_golden.json (made by tests/golden/make_ipa_golden.py) pins the oracle's h_coeffs / MSM / decide."""
+    n = 0
+    for C, k, g, accs in _load_ipa_golden():
+        assert len(g) == 1 << k and all(C.is_on_curve(p) for p in g)
+        for xi, u, commit, status in accs:
+            assert C.msm_pippenger(ipa.h_coeffs(xi, 1, C.n), g) == commit
+            assert ipa.decide(C, g, ipa.IpaAccumulator(xi, u)) == status == (0 if u == commit else 3)
+            n += 1
+    assert n == 30
