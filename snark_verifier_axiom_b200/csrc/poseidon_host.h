@@ -173,6 +173,17 @@ inline bool make_poseidon_consts(PoseidonConsts& k, int secure_mds = 0) {
   Mat pre = mat_transpose(accm);
   for (int i = 0; i < T; i++)
     for (int j = 0; j < T; j++) { k.mds[i][j] = mds[i][j]; k.pre_sparse_mds[i][j] = pre[i][j]; }
+  for (int p = 0; p < SVK_POSEIDON_RP / 2; p++) {  // two partial rounds at a time (poseidon.cuh)
+    const int a = 2 * p, b = 2 * p + 1;
+    k.pair[p][0] = k.sparse_row[b][0];
+    k.pair[p][1] = k.sparse_row[b][1] * k.sparse_col_hat[a][0] + k.sparse_row[b][2] * k.sparse_col_hat[a][1];
+    k.pair[p][2] = k.sparse_row[b][1];
+    k.pair[p][3] = k.sparse_row[b][2];
+    k.pair[p][4] = k.sparse_col_hat[b][0];
+    k.pair[p][5] = k.sparse_col_hat[a][0];
+    k.pair[p][6] = k.sparse_col_hat[b][1];
+    k.pair[p][7] = k.sparse_col_hat[a][1];
+  }
   Fr cap = Fr::zero();
   cap.v[2] = 1;  // 2^64
   k.capacity = cap.to_mont();
