@@ -86,10 +86,10 @@ __device__ __noinline__ G1Jac fold_mul_window4(const G1Affine& p, const u32* k) 
 //   k_group_var  `vpl` threads per (group, side); a thread owns terms j = 1 + lane, 1 + lane + vpl, ... of its group
 //                and runs them as ONE interleaved (Straus) multiplication (straus.cuh): 255 shared doublings + per term a
 //                16-entry Jacobian table and <= 52 signed-window additions.  vpl = 1 where groups are plentiful (minimal work:
-//                1778 + 7 x 1185 M for a group of 8 instead of 7 x 2977), vpl = m - 1 on the upper, narrow levels
+//                1785 + 7 x ~800 M for a group of 8 instead of 7 full multiplications), vpl = m - 1 on the upper, narrow levels
 //                (minimal latency).  The first version ran one block of 32 threads per (group, side) with 7 active
 //                lanes and was the largest consumer of issue slots of the whole step (profiles/r1_notes.md).
-//   k_group_sum  one (group, side) per thread: base_0 (scalar r^0 = 1) + partial sums, Fermat to_affine.
+//   k_group_sum  one (group, side) per thread: base_0 (scalar r^0 = 1) + partial sums, to_affine.
 #define FOLD_TERMS_MAX 16
 __device__ __forceinline__ bool load_acc_point(G1Affine& b, const uint8_t* p) {
   load_canon32(b.x.v, p);

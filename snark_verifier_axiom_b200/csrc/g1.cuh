@@ -99,7 +99,7 @@ struct JacT {
     return r;
   }
   HD G1Jac neg() const { return {X, Y.neg(), Z}; }
-  // to affine with a caller-supplied inverse of Z (batched inversion) or a Fermat inversion
+  // to affine with a caller-supplied inverse of Z (batched inversion) or its own inversion
   HD G1Affine to_affine_with_zinv(const F& zinv) const {
     if (is_identity()) return G1Affine::identity();
     F zi2 = zinv.sqr();

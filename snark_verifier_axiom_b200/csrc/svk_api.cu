@@ -41,10 +41,10 @@ static int upload(svk_ctx* ctx, T** d, const std::vector<T>& v) {
   return 0;
 }
 
-// Schedule of the per-proof MSM (verify.cu: k_msm_var + k_msm_sum).  Variable-base terms become k_msm_var items
-// (one full windowed scalar multiplication each, ~2977 M); in k_msm_sum every one of the 16 lanes of a proof
-// gets an EQUAL number of fixed-base table windows (11 M each; vk commitments and g), and the partial sums /
-// scalar == 1 bases are dealt round-robin.  Returns the algorithmic Fq mults per proof for this side.
+// Schedule of the per-proof MSM (verify.cu: k_msm_var + k_msm_sum).  Variable-base terms become k_msm_var items (Straus,
+// straus.cuh); in k_msm_sum every one of the SVK_MSM_LANES lanes of a (proof, side) gets an EQUAL number of fixed-base table
+// windows (one mixed addition each; vk commitments and g), and the partial sums / scalar == 1 bases are dealt round-robin.
+// Returns the algorithmic Fq mults per proof for this side (SURVEY 8d counting).
 // `var_lane_base`: index of this side's first k_msm_var lane; `var_lanes`: how many lanes this side may use.
 static size_t schedule_msm(const std::vector<MsmTermDev>& terms, std::vector<std::vector<MsmWork>>& var_lanes_items, u32 var_lane_base,
                            u32 var_lanes, std::vector<MsmWork>& work, std::vector<u32>& lane_off, std::vector<FixedSlot>& fixed_sched,
@@ -84,7 +84,7 @@ static size_t schedule_msm(const std::vector<MsmTermDev>& terms, std::vector<std
   work.clear(); lane_off.assign(L + 1, 0);
   for (int l = 0; l < L; l++) { lane_off[l] = (u32)work.size(); work.insert(work.end(), lanes[l].begin(), lanes[l].end()); }
   lane_off[L] = (u32)work.size();
-  return total + (L - 1) * 16 + 385;  // + shuffle-tree additions + to_affine
+  return total + (L - 1) * 16 + 385;  // + lane-tree additions (none for one lane) + to_affine
 }
 
 extern "C" {

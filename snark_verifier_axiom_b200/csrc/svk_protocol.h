@@ -19,7 +19,7 @@ struct MsmTermDev {
 
 // One unit of per-proof MSM work, executed by one lane of the proof's lane group (k_proof_msm).
 struct MsmWork {
-  int32_t kind;   // 0: variable base, full 4-bit-window scalar mul (k_msm_var); 1: fixed base, table windows [w0, w1);
+  int32_t kind;   // 0: variable base, Straus item (k_msm_var); 1: fixed base, table windows [w0, w1);
                   // 2: add the base (scalar == 1); 3: add partial number `base` produced by k_msm_var
   int32_t fixed;  // base lives in fixed_bases[] (1) or in the proof-point file (0)
   int32_t base;

@@ -155,18 +155,16 @@ __global__ void __launch_bounds__(64) k_fixed_tables(u32 n_fixed, u32 bits, cons
 
 // ---- Per-proof MSM, split by uniformity of work (ncu on the first version -- one fused kernel, 16 lanes per
 // proof -- showed 10.5 of 32 lanes active per instruction: variable-base and fixed-base lanes serialised, and
-// the final Fermat inversion ran on 2 lanes; profiles/r1_ncu_notes.md):
-//   k_msm_var    one (variable-base term, proof) per thread, all lanes do the same 4-bit-window scalar
-//                multiplication; Jacobian partial -> partials[side][term][proof]
-//   k_msm_sum    16 lanes per (proof, side): an equal slice of the fixed-base table windows per lane (mixed
-//                additions only), plus the partials and the scalar == 1 bases; shuffle reduction -> sums[side][proof]
-//   k_to_affine  one (proof, side) per thread: Fermat inversion, canonical accumulator bytes
-// Straus / interleaved windows: one thread owns up to SVK_VAR_TERMS_MAX variable-base terms of ONE proof and
-// shares the 255 doublings between them (per term: a 16-entry Jacobian table + <= 52 signed-window additions, straus.cuh).  With
-// `vpl` threads ("var lanes") per proof, each with its own host-scheduled item list (lanes never mix the lhs and
-// rhs sides): fewer lanes minimise total work
-// (1778 + 11 x 1185 M per StandardPlonk proof instead of 11 x 2977), larger vpl shortens the latency.
-// partials[(lane * n_items) + proof]  (Jacobian)
+// the final inversion ran on 2 lanes; profiles/r1_notes.md):
+//   k_msm_var    `vpl` threads per proof; a thread owns up to SVK_VAR_TERMS_MAX variable-base terms of ONE proof and runs
+//                them as one interleaved (Straus) multiplication (straus.cuh): per term a 16-entry table normalised to affine
+//                together with all other tables of the thread, <= 52 signed 5-bit-window mixed additions; 255 shared
+//                doublings and one inversion per thread.  Each thread has its own host-scheduled item list (lanes never mix the
+//                lhs and rhs sides); fewer lanes minimise total work, more lanes shorten the latency.
+//                Jacobian partial -> partials[(lane * n_items) + proof]
+//   k_msm_sum    one thread per (proof, side) (SVK_MSM_LANES = 1): the fixed-base table windows (mixed additions only,
+//                entries prefetched), then the partials and the scalar == 1 bases -> sums[side][proof]
+//   k_to_affine  one proof per thread: one inversion for both sides, canonical accumulator bytes
 #define SVK_VAR_TERMS_MAX 16
 __global__ void __launch_bounds__(64) k_msm_var(size_t n_items, const MsmWork* var_items, const u32* var_lane_off, u32 vpl, const G1Affine* pts,
                                                 const u32* scalars, G1Jac* tables, Fq* prefix, G1Jac* partials) {
@@ -263,7 +261,7 @@ __global__ void __launch_bounds__(128) k_msm_sum(size_t n_items, const MsmWork* 
   if (active && lane == 0) sums[(size_t)blockIdx.y * n_items + item] = acc;
 }
 
-// One proof per thread: both sides share ONE Fermat inversion (Montgomery's trick on Z_lhs * Z_rhs; an identity side takes Z := 1).
+// One proof per thread: both sides share ONE inversion (Montgomery's trick on Z_lhs * Z_rhs; an identity side takes Z := 1).
 __global__ void __launch_bounds__(128) k_to_affine(size_t n_items, const G1Jac* sums, const u32* err, uint8_t* out_acc, size_t acc_stride) {
   size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= n_items) return;
