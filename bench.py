@@ -398,7 +398,7 @@ def run_ours(args):
         D4 = 328 / 136
         perm_exec = (8 * (3 * (2 * S_ + 1) + 3 * D3) + 28 * (2 * (2 * S_ + 1) + D3 + D4 + 2 * D2)  # optimised Poseidon, T = 3, partial
                      + ((2 * S_ + 1) + D3 + 2))                                                   # rounds two at a time: 475
-        chain_exec = 252 * S_ + 77                                                      # 4-bit-window square-root chain: 294
+        chain_exec = 253 * S_ + 58                                                      # sliding-window square-root chain: 276
         inv_exec = 80                                                                   # binary-Euclid inversion: ALU work; ~55 IMAD.MOV/IMAD.X per step on the multiply pipe
         n_perm = info["n_poseidon_perms"]
         tape_other = info["n_fr_mul"] - 600 * n_perm                                    # scalar algebra incl. 3 Fermat chains at 380

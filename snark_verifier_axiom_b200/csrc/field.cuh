@@ -426,28 +426,35 @@ struct Fe {
   }
 
   // a^e for a public 256-bit exponent (left-to-right binary; the exponent is uniform across a warp)
-  // 4-bit fixed windows: 252 squarings + <= 63 + 14 products (the table lives in the noinline frame)
+  // a^e for a public 256-bit exponent (uniform across a warp): sliding windows of up to 5 bits over a table of the odd powers
+  // a, a^3, .., a^31 (1 squaring + 15 products; the table lives in the noinline frame): ~253 squarings + ~42 + 16 products for a
+  // 254-bit exponent (fixed 4-bit windows: 252 + 77).
   HDN Fe pow(const u32* e) const {
     Fe tab[16];
-    tab[0] = one();
-    tab[1] = *this;
+    tab[0] = *this;
+    Fe a2 = sqr();
 #pragma unroll 1
-    for (int i = 2; i < 16; i += 2) {
-      tab[i] = tab[i >> 1].sqr();
-      tab[i + 1] = tab[i] * (*this);
-    }
+    for (int i = 1; i < 16; i++) tab[i] = tab[i - 1] * a2;
     Fe r = one();
     bool started = false;
-    for (int w = 7; w >= 0; w--) {
-#pragma unroll 1
-      for (int b = 28; b >= 0; b -= 4) {
-        if (started) r = r.sqr().sqr().sqr().sqr();
-        u32 d = (e[w] >> b) & 15;
-        if (d) {
-          r = started ? r * tab[d] : tab[d];
-          started = true;
-        }
+    int i = 255;
+    while (i >= 0) {
+      if (!((e[i >> 5] >> (i & 31)) & 1)) {
+        if (started) r = r.sqr();
+        i--;
+        continue;
       }
+      // window [j, i] with bit j set, at most 5 bits
+      int j = i - 4 < 0 ? 0 : i - 4;
+      while (!((e[j >> 5] >> (j & 31)) & 1)) j++;
+      u32 val = 0;
+      for (int t = i; t >= j; t--) {
+        val = (val << 1) | ((e[t >> 5] >> (t & 31)) & 1);
+        if (started) r = r.sqr();
+      }
+      r = started ? r * tab[val >> 1] : tab[val >> 1];
+      started = true;
+      i = j - 1;
     }
     return r;
   }

@@ -54,10 +54,11 @@ HD void straus_build_table(JacT<F>* tb, size_t stride, const AffT<F>& base) {
 // Per entry 1 + 5 products and a squaring: pays off from ~3 terms per thread on (11 terms: -11 % of the kernel).
 template <class F>
 HD void straus_normalize(JacT<F>* tables, F* prefix, size_t stride, u32 n_entries) {
+  // the first entry of every table is the base itself (Z = 1, or Z = 0 for an identity base): nothing to multiply
   F run = F::one();
   for (u32 i = 0; i < n_entries; i++) {
     F z = tables[(size_t)i * stride].Z;
-    if (!z.is_zero()) run = run * z;
+    if ((i % STRAUS_TABLE) != 0 && !z.is_zero()) run = run * z;
     prefix[(size_t)i * stride] = run;
   }
   F inv = run.inv();
@@ -69,6 +70,7 @@ HD void straus_normalize(JacT<F>* tables, F* prefix, size_t stride, u32 n_entrie
       e->Y = F::zero();
       continue;
     }
+    if ((i % STRAUS_TABLE) == 0) continue;  // already affine
     F zi = i ? inv * prefix[(size_t)(i - 1) * stride] : inv;
     inv = inv * z;
     F zi2 = zi.sqr();
