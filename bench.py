@@ -184,6 +184,17 @@ class Slot:
         self.sv = ShardedBatchVerifier(self.pv, world, rank, dev, self.stream, group_size=group_size, max_batches=max_batches)
 
 
+def choose_batches_per_launch(steps, slots, requested=0, cap=32):
+    """Batches carried by one call.  Auto (requested <= 0): the largest B <= cap that divides `steps` (so exactly `steps` batches
+    are timed) and still leaves every in-flight slot at least one launch."""
+    if requested > 0:
+        return requested
+    b = max(1, min(cap, steps // max(1, slots)))
+    while steps % b:
+        b -= 1
+    return b
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -205,12 +216,7 @@ def run_ours(args):
 
     S = max(1, args.inflight)
     # K timed steps = K batches.  A launch carries B batches; with few steps, smaller launches keep all S slots busy.
-    # Auto: the largest B <= 32 that divides K (exactly K steps are timed) and still gives every slot a launch.
-    B = args.batches_per_launch
-    if B <= 0:
-        B = max(1, min(32, args.steps // S))
-        while args.steps % B:
-            B -= 1
+    B = choose_batches_per_launch(args.steps, S, args.batches_per_launch)
     g, reps, np = make_workload(args.batch * B, args.scheme)
     mos = V.SHPLONK if args.scheme == "bdfg21" else V.GWC
     nb1 = args.batch           # proofs per batch (= per step)
