@@ -34,6 +34,42 @@ __global__ void __launch_bounds__(64, SVK_DECIDE_MINBLOCKS) k_decide(size_t n, c
   out_ok[i * ok_stride] = acc ? 1 : 0;
 }
 
+// Latency form (coop_pairing.cuh): one accumulator per block of COOP_THREADS threads.  Used when there are too few
+// accumulators to fill the machine with one thread each (the single pairing that ends a batch, the per-rank or per-batch
+// pairings of a sharded / multi-batch call).
+#define COOP_THREADS 64
+struct DevExec {
+  template <class F>
+  __device__ __forceinline__ void par(int n_tasks, F f) {
+    for (int i = threadIdx.x; i < n_tasks; i += COOP_THREADS) f(i);
+    __syncthreads();
+  }
+};
+
+__global__ void __launch_bounds__(COOP_THREADS) k_decide_coop(size_t n, const uint8_t* accs, size_t acc_stride, uint8_t* out_ok, size_t ok_stride,
+                                                              const G2LineX* t_g2, const G2LineX* t_neg_sg2, const PairingConsts* consts, Fq* line_scratch) {
+  __shared__ CoopMem m;
+  __shared__ G1Affine pts[2];
+  __shared__ int pt_ok[2];
+  size_t i = blockIdx.x;
+  if (threadIdx.x < 2) {
+    G1Affine p = load_g1_canon(accs + i * acc_stride + 64 * threadIdx.x);
+    bool ok = Fq::is_canonical(p.x.v) && Fq::is_canonical(p.y.v);
+    if (!p.is_identity()) { p.x = p.x.to_mont(); p.y = p.y.to_mont(); }
+    ok = ok && g1_on_curve(p);
+    pts[threadIdx.x] = p;
+    pt_ok[threadIdx.x] = ok ? 1 : 0;
+  }
+  __syncthreads();
+  if (!(pt_ok[0] && pt_ok[1])) {  // not a `G1Affine` at all: reject (uniform across the block)
+    if (threadIdx.x == 0) out_ok[i * ok_stride] = 0;
+    return;
+  }
+  DevExec ex;
+  bool acc = coop_kzg_decide(ex, pts[0], pts[1], t_g2, t_neg_sg2, *consts, line_scratch + i * (size_t)(2 * SVK_N_LINES * COOP_BLK), m);
+  if (threadIdx.x == 0) out_ok[i * ok_stride] = acc ? 1 : 0;
+}
+
 int svk_decide_launch_strided(svk_ctx* ctx, int dk, size_t n, const void* d_accs, size_t acc_stride, void* d_ok, size_t ok_stride);
 int svk_decide_launch(svk_ctx* ctx, int dk, size_t n, const void* d_accs, void* d_ok) {
   return svk_decide_launch_strided(ctx, dk, n, d_accs, 128, d_ok, 1);
@@ -43,6 +79,15 @@ int svk_decide_launch_strided(svk_ctx* ctx, int dk, size_t n, const void* d_accs
   if (dk < 0 || dk >= (int)ctx->dks.size()) return svk_fail(ctx, "bad deciding-key id %d", dk);
   if (n == 0) return 0;
   const DkDevice& k = ctx->dks[dk];
+  if (n <= ctx->decide_coop_max) {
+    Fq* d_lines;
+    if (svk_scratch(ctx, 19, n * (size_t)(2 * SVK_N_LINES * COOP_BLK) * sizeof(Fq), (void**)&d_lines)) return -1;
+    SVK_LAUNCH(ctx, "k_decide_coop",
+               k_decide_coop<<<(unsigned)n, COOP_THREADS, 0, ctx->stream>>>(n, (const uint8_t*)d_accs, acc_stride, (uint8_t*)d_ok, ok_stride, k.d_linesx_g2,
+                                                                           k.d_linesx_neg_sg2, ctx->d_pairing_consts, d_lines));
+    SVK_CUDA(ctx, cudaGetLastError());
+    return 0;
+  }
   unsigned block = 64;
   unsigned grid = (unsigned)((n + block - 1) / block);
   SVK_LAUNCH(ctx, "k_decide",

@@ -12,7 +12,7 @@
 //   k_group_var / k_group_sum : the group MSMs (see below)
 //                   block's threads, shared-memory tree reduction of the partial sums, to_affine
 #include "straus.cuh"
-#include "poseidon.cuh"
+#include "poseidon_coop.cuh"
 #include "svk_ctx.h"
 
 __device__ __forceinline__ void load_canon32(u32* v, const uint8_t* p) {
@@ -67,19 +67,67 @@ __global__ void __launch_bounds__(32) k_fold_sponge(size_t n_seg, size_t n, size
   if (bad) atomicMax(status + seg * status_stride_words, bad);
 }
 
-__device__ __noinline__ G1Jac fold_mul_window4(const G1Affine& p, const u32* k) {
-  G1Jac tbl[16];
-  tbl[0] = G1Jac::identity();
-  tbl[1] = G1Jac::from_affine(p);
-  tbl[2] = tbl[1].dbl();
-  for (int i = 3; i < 16; i++) tbl[i] = tbl[i - 1].add_affine(p);
-  G1Jac acc = G1Jac::identity();
-  for (int w = 63; w >= 0; w--) {
-    if (w != 63) acc = acc.dbl().dbl().dbl().dbl();
-    u32 d = (k[w >> 3] >> ((w & 7) * 4)) & 0xf;
-    acc = acc.add(tbl[d]);
+// Latency form (poseidon_coop.cuh): 32 groups per block of three warps.  The levels of the fold tree of a 4096-proof batch
+// have 512, 64, 8 and 1 groups, each a lone serial chain of 2m + 1 permutations.  The permutation count is made uniform
+// across the warp (named barriers need whole warps): a lane whose group is shorter than the longest of its warp (the last
+// group of a segment, lanes past the end) captures its r after its own 2 len + 1 permutations and keeps permuting a dead state.
+__global__ void __launch_bounds__(PCOOP_THREADS) k_fold_sponge_coop(size_t n_seg, size_t n, size_t m, const uint8_t* accs, const PoseidonConsts* pk,
+                                                                    u32* scalars, u32* out_r, size_t out_r_stride_words, int32_t* status,
+                                                                    size_t status_stride_words) {
+  __shared__ PoseidonCoopShared sh;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp) {
+    pc_helper(&sh, *pk, warp, lane);
+    return;
   }
-  return acc;
+  size_t n_groups = (n + m - 1) / m;
+  size_t G = (size_t)blockIdx.x * 32 + lane;
+  if (G >= n_groups * n_seg) G = n_groups * n_seg - 1;  // duplicates store identical values
+  size_t seg = G / n_groups, g = G % n_groups;
+  size_t begin = seg * n + g * m, end = (g * m + m < n ? g * m + m : n) + seg * n;
+  u32 len = (u32)(end - begin), max_len = len;
+  for (int d = 16; d >= 1; d >>= 1) max_len = max(max_len, __shfl_xor_sync(0xffffffffu, max_len, d));
+  PoseidonCoopMain st;
+  st.sh = &sh;
+  st.lane = lane;
+  pcm_init(st, *pk);
+  int32_t bad = 0;
+  Fr r = Fr::zero();
+  for (u32 q = 0; q < 2 * max_len + 1; q++) {
+    Fr fx = Fr::zero(), fy = Fr::zero();
+    int n_in = 0;
+    if (q < 2 * len) {
+      size_t i = begin + (q >> 1);
+      int h = (int)(q & 1);
+      u32 x[8], y[8];
+      load_canon32(x, accs + i * 128 + h * 64);
+      load_canon32(y, accs + i * 128 + h * 64 + 32);
+      u32 any = 0;
+      for (int k = 0; k < 8; k++) any |= x[k] | y[k];
+      if (any == 0) bad = SVK_TRANSCRIPT | (SVK_T_POINT_IDENTITY << 8);
+      if (!Fq::is_canonical(x) || !Fq::is_canonical(y)) bad = SVK_TRANSCRIPT | (SVK_T_POINT_INVALID << 8);
+      fq_canon_to_fr_canon(fx.v, x);
+      fq_canon_to_fr_canon(fy.v, y);
+      fx = fx.to_mont();
+      fy = fy.to_mont();
+      n_in = 2;
+    }
+    pcm_permute(st, *pk, n_in, fx, fy);
+    if (q == 2 * len) r = st.s1;
+  }
+  pcm_exit(st);
+  Fr rc = r.from_mont();
+  if (out_r)
+    for (int k = 0; k < 8; k++) out_r[seg * out_r_stride_words + k] = rc.v[k];
+  Fr p = r;
+  for (size_t i = begin + 1; i < end; i++) {
+    Fr pc = p.from_mont();
+    uint4* o = reinterpret_cast<uint4*>(scalars + i * 8);
+    o[0] = make_uint4(pc.v[0], pc.v[1], pc.v[2], pc.v[3]);
+    o[1] = make_uint4(pc.v[4], pc.v[5], pc.v[6], pc.v[7]);
+    p = p * r;
+  }
+  if (bad) atomicMax(status + seg * status_stride_words, bad);
 }
 
 // Group MSM, split like the per-proof MSM (verify.cu):
@@ -180,9 +228,15 @@ int svk_fold_launch_seg(svk_ctx* ctx, size_t n_seg, size_t n, const uint8_t* d_a
     bool last = groups == 1;
     uint8_t* dst = last ? d_out : bufs[which];
     size_t total_groups = groups * n_seg;
-    SVK_LAUNCH(ctx, "k_fold_sponge",
-               k_fold_sponge<<<(unsigned)((total_groups + 31) / 32), 32, 0, s>>>(n_seg, cnt, m, cur, ctx->d_poseidon, d_scal, last ? d_r : nullptr,
-                                                                                out_stride / 4, d_status, out_stride / 4));
+    if (total_groups <= ctx->tape_coop_max)
+      SVK_LAUNCH(ctx, "k_fold_sponge_coop",
+                 k_fold_sponge_coop<<<(unsigned)((total_groups + 31) / 32), PCOOP_THREADS, 0, s>>>(n_seg, cnt, m, cur, ctx->d_poseidon, d_scal,
+                                                                                                   last ? d_r : nullptr, out_stride / 4, d_status,
+                                                                                                   out_stride / 4));
+    else
+      SVK_LAUNCH(ctx, "k_fold_sponge",
+                 k_fold_sponge<<<(unsigned)((total_groups + 31) / 32), 32, 0, s>>>(n_seg, cnt, m, cur, ctx->d_poseidon, d_scal, last ? d_r : nullptr,
+                                                                                  out_stride / 4, d_status, out_stride / 4));
     // lanes per (group, side): 1 while there are enough groups to fill the machine, else one lane per term
     size_t gm = cnt < m ? cnt : m;
     u32 vpl = 1;

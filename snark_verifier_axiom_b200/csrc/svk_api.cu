@@ -28,7 +28,7 @@ static thread_local std::string g_create_err;
 // Fixed-base window tables are identical for every context that compiles the same verifying key on the same
 // device (bench.py keeps 32 contexts in flight): share one device copy so the 4.7 MB table stays L2-resident.
 #include <mutex>
-struct SharedTable { G1Affine* d = nullptr; int refs = 0; };
+struct SharedTable { G1Affine* d = nullptr; int refs = 0; bool ready = false; };
 static std::mutex g_table_mu;
 static std::map<std::string, SharedTable> g_tables;
 
@@ -87,6 +87,23 @@ static size_t schedule_msm(const std::vector<MsmTermDev>& terms, std::vector<std
   return total + (L - 1) * 16 + 385;  // + lane-tree additions (none for one lane) + to_affine
 }
 
+// Frees everything a ProtocolDevice owns (svk_destroy and every error path of protocol_upload).
+static void protocol_release(ProtocolDevice* p) {
+  if (!p) return;
+  cudaFree(p->d_ops); cudaFree(p->d_aux); cudaFree(p->d_consts); cudaFree(p->d_sched); cudaFree(p->d_lhs); cudaFree(p->d_rhs);
+  cudaFree(p->d_fixed); cudaFree(p->d_fixed_lhs); cudaFree(p->d_fixed_rhs); cudaFree(p->d_old_idx);
+  for (auto& sc : p->sched) {
+    cudaFree(sc.d_var_items); cudaFree(sc.d_var_lane_off); cudaFree(sc.d_work_lhs); cudaFree(sc.d_work_rhs);
+    cudaFree(sc.d_lane_off_lhs); cudaFree(sc.d_lane_off_rhs);
+  }
+  if (p->d_fixed_tables) {
+    std::lock_guard<std::mutex> lk(g_table_mu);
+    auto it = g_tables.find(p->table_key);
+    if (it != g_tables.end() && --it->second.refs == 0) { cudaFree(it->second.d); g_tables.erase(it); }
+  }
+  delete p;
+}
+
 extern "C" {
 
 int svk_create(int device, svk_ctx** out) {
@@ -107,6 +124,9 @@ int svk_create(int device, svk_ctx** out) {
   svk_ctx* ctx = new svk_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("SVK_DECIDE_COOP_MAX")) ctx->decide_coop_max = (size_t)atoll(e);
+  if (const char* e = getenv("SVK_TAPE_COOP_MAX")) ctx->tape_coop_max = (size_t)atoll(e);
+  if (const char* e = getenv("SVK_MSM_LATENCY_THREADS_MAX")) ctx->msm_latency_threads_max = (size_t)atoll(e);
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; g_create_err = "stream create failed"; return -1; }
   ctx->own_stream = true;
   PairingConsts k = svk_host::make_pairing_consts();
@@ -126,14 +146,11 @@ void svk_destroy(svk_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (auto& k : ctx->dks) { cudaFree(k.d_lines_g2); cudaFree(k.d_lines_neg_sg2); }
+  for (auto& k : ctx->dks) { cudaFree(k.d_lines_g2); cudaFree(k.d_lines_neg_sg2); cudaFree(k.d_linesx_g2); cudaFree(k.d_linesx_neg_sg2); }
   for (int i = 0; i < 24; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   cudaFree(ctx->d_pairing_consts);
   cudaFree(ctx->d_poseidon);
-  for (auto* p : ctx->protocols) {
-    cudaFree(p->d_ops); cudaFree(p->d_aux); cudaFree(p->d_consts); cudaFree(p->d_sched); cudaFree(p->d_lhs); cudaFree(p->d_rhs); cudaFree(p->d_fixed); { std::lock_guard<std::mutex> lk(g_table_mu); auto it = g_tables.find(p->table_key); if (it != g_tables.end() && --it->second.refs == 0) { cudaFree(it->second.d); g_tables.erase(it); } } cudaFree(p->d_var_items); cudaFree(p->d_var_lane_off); cudaFree(p->d_fixed_lhs); cudaFree(p->d_fixed_rhs); cudaFree(p->d_work_lhs); cudaFree(p->d_work_rhs); cudaFree(p->d_lane_off_lhs); cudaFree(p->d_lane_off_rhs);
-    delete p;
-  }
+  for (auto* p : ctx->protocols) protocol_release(p);
   if (ctx->done) cudaEventDestroy(ctx->done);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -216,6 +233,13 @@ int svk_dk_load(svk_ctx* ctx, const svk_deciding_key* dk) {
   SVK_CUDA(ctx, cudaMalloc(&d.d_lines_neg_sg2, bytes));
   SVK_CUDA(ctx, cudaMemcpy(d.d_lines_g2, t1.data(), bytes, cudaMemcpyHostToDevice));
   SVK_CUDA(ctx, cudaMemcpy(d.d_lines_neg_sg2, t2.data(), bytes, cudaMemcpyHostToDevice));
+  std::vector<G2LineX> x1, x2;
+  for (auto& l : t1) x1.push_back({l.neg_lam, l.c3, l.neg_lam.mul_xi(), l.c3.mul_xi()});
+  for (auto& l : t2) x2.push_back({l.neg_lam, l.c3, l.neg_lam.mul_xi(), l.c3.mul_xi()});
+  SVK_CUDA(ctx, cudaMalloc(&d.d_linesx_g2, sizeof(G2LineX) * SVK_N_LINES));
+  SVK_CUDA(ctx, cudaMalloc(&d.d_linesx_neg_sg2, sizeof(G2LineX) * SVK_N_LINES));
+  SVK_CUDA(ctx, cudaMemcpy(d.d_linesx_g2, x1.data(), sizeof(G2LineX) * SVK_N_LINES, cudaMemcpyHostToDevice));
+  SVK_CUDA(ctx, cudaMemcpy(d.d_linesx_neg_sg2, x2.data(), sizeof(G2LineX) * SVK_N_LINES, cudaMemcpyHostToDevice));
   ctx->dks.push_back(d);
   return (int)ctx->dks.size() - 1;
 }
@@ -243,7 +267,7 @@ int svk_protocol_compile(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos,
   return svk_protocol_compile_ex(ctx, blob, len, mos, SVK_TRANSCRIPT_POSEIDON, dk);
 }
 
-static int protocol_upload(svk_ctx* ctx, svk_host::CompiledProtocol& cp, int mos, int transcript_kind, int dk);
+static int protocol_upload(svk_ctx* ctx, svk_host::CompiledProtocol& cp, int mos, int transcript_kind, int dk, int force_bits = 0);
 
 int svk_protocol_compile_ex(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos, int transcript_kind, int dk) {
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -270,7 +294,7 @@ int svk_protocol_compile_bincode(svk_ctx* ctx, const uint8_t* bytes, size_t len,
   return protocol_upload(ctx, cp, mos, transcript_kind, dk);
 }
 
-static int protocol_upload(svk_ctx* ctx, svk_host::CompiledProtocol& cp, int mos, int transcript_kind, int dk) {
+static int protocol_upload(svk_ctx* ctx, svk_host::CompiledProtocol& cp, int mos, int transcript_kind, int dk, int force_bits) {
   ProtocolDevice* pd = new ProtocolDevice();
   pd->mos = mos;
   pd->transcript_kind = transcript_kind;
@@ -290,7 +314,7 @@ static int protocol_upload(svk_ctx* ctx, svk_host::CompiledProtocol& cp, int mos
   pd->n_old = cp.n_old;
   pd->acc_limbs = cp.acc_limbs;
   pd->acc_bits = cp.acc_bits;
-  if (pd->n_old && upload(ctx, &pd->d_old_idx, cp.old_acc_idx)) { delete pd; return -1; }
+  if (pd->n_old && upload(ctx, &pd->d_old_idx, cp.old_acc_idx)) { protocol_release(pd); return -1; }
   pd->n_pre = (u32)cp.preprocessed.size();
   for (auto& p : cp.points) pd->points.push_back({p.byte_offset, (u32)(p.val_x < 0 ? 0 : p.val_x), (u32)(p.val_y < 0 ? 0 : p.val_y)});
   std::vector<G1Affine> fixed;
@@ -300,7 +324,7 @@ static int protocol_upload(svk_ctx* ctx, svk_host::CompiledProtocol& cp, int mos
     for (int i = 0; i < 32; i++) id = id && g.x.b[i] == 0 && g.y.b[i] == 0;
     if (!id) {
       if (!load_fq_canon(a.x, g.x) || !load_fq_canon(a.y, g.y) || !g1_on_curve(a)) {
-        delete pd;
+        protocol_release(pd);
         return svk_fail(ctx, "protocol: preprocessed commitment is not a canonical on-curve point");
       }
     }
@@ -324,61 +348,87 @@ static int protocol_upload(svk_ctx* ctx, svk_host::CompiledProtocol& cp, int mos
   pd->n_rhs = (u32)rhs.size();
   pd->h_lhs = lhs;
   pd->h_rhs = rhs;
-  std::vector<MsmWork> wl, wr, var_items;
-  std::vector<u32> ol, orr;
-  // k_msm_var lanes: `var_lanes` threads per proof for the lhs terms, and one more for the rhs side when it has
-  // scaled variable bases of its own (GWC: rhs = sum u^i W_i; SHPLONK's rhs is W' itself).
-  pd->var_lanes = 1;  // measured on B200 (profiles/r1_notes.md) with the signed-window Straus core: 1 lane = 1.37 M proofs/s, 2 lanes = 1.33 M
-                      // (one more 255-doubling chain per proof); 2 halves this kernel's latency for a lone small batch (SVK_VAR_LANES=2)
-  if (const char* e = getenv("SVK_VAR_LANES")) pd->var_lanes = (u32)std::max(1, std::min(8, atoi(e)));
-  bool rhs_var = false;
-  for (auto& t : rhs) rhs_var = rhs_var || (t.slot >= 0 && !t.fixed);
-  // a thread carries at most SVK_VAR_TERMS_MAX (16) terms: protocols with more variable bases (lookups, several proofs) get more lanes
-  u32 lhs_var = 0;
+  // k_msm_var lanes: `var_lanes` threads per proof for the lhs terms, plus lanes for the rhs side when it has scaled variable
+  // bases of its own (GWC: rhs = sum u^i W_i; SHPLONK's rhs is W' itself).  A thread carries at most SVK_VAR_TERMS_MAX (16) terms.
+  u32 lhs_var = 0, rhs_var = 0;
   for (auto& t : lhs) lhs_var += (t.slot >= 0 && !t.fixed) ? 1 : 0;
-  pd->var_lanes = std::max<u32>(pd->var_lanes, (lhs_var + 15) / 16);
-  std::vector<std::vector<MsmWork>> vlanes(pd->var_lanes + (rhs_var ? 1 : 0));
-  std::vector<FixedSlot> fl, fr;
+  for (auto& t : rhs) rhs_var += (t.slot >= 0 && !t.fixed) ? 1 : 0;
   // 16-bit windows halve the table additions of k_msm_sum; their tables (67 MB per base) are used while they stay under ~3 GB
   pd->fixed_bits = fixed.size() <= 48 ? SVK_FIXED_BITS_LARGE : SVK_FIXED_BITS_SMALL;
   if (const char* e = getenv("SVK_FIXED_BITS")) pd->fixed_bits = atoi(e) == 16 ? 16 : 8;
-  pd->msm_work_modmul = schedule_msm(lhs, vlanes, 0, pd->var_lanes, wl, ol, fl, pd->fixed_per_lhs, pd->fixed_bits) +
-                        schedule_msm(rhs, vlanes, pd->var_lanes, 1, wr, orr, fr, pd->fixed_per_rhs, pd->fixed_bits);
-  if (upload(ctx, &pd->d_fixed_lhs, fl) || upload(ctx, &pd->d_fixed_rhs, fr)) { delete pd; return -1; }
-  std::vector<u32> vloff;
-  for (auto& l : vlanes) {
+  if (force_bits) pd->fixed_bits = (u32)force_bits;
+  auto fail = [&](int rc) { protocol_release(pd); return rc; };
+  for (int which = 0; which < 2; which++) {
+    MsmSched& sc = pd->sched[which];
+    // [0]: measured on B200 (profiles/r1_notes.md) with the signed-window Straus core: 1 lane = 1.37 M proofs/s, 2 lanes = 1.33 M
+    // (one more 255-doubling chain per proof).  [1]: one lane per term.
+    u32 want = which == 0 ? 1 : 16;
+    if (which == 0)
+      if (const char* e = getenv("SVK_VAR_LANES")) want = (u32)std::max(1, std::min(16, atoi(e)));
+    u32 ll = std::max<u32>(std::min<u32>(want, std::max<u32>(lhs_var, 1)), (lhs_var + 15) / 16);
+    u32 rl = rhs_var ? std::max<u32>(std::min<u32>(want, rhs_var), (rhs_var + 15) / 16) : 0;
+    sc.var_lanes = ll;
+    std::vector<std::vector<MsmWork>> vlanes(ll + rl);
+    std::vector<MsmWork> wl, wr, var_items;
+    std::vector<u32> ol, orr;
+    std::vector<FixedSlot> fl, fr;
+    sc.msm_work_modmul = schedule_msm(lhs, vlanes, 0, ll, wl, ol, fl, pd->fixed_per_lhs, pd->fixed_bits) +
+                         schedule_msm(rhs, vlanes, ll, std::max<u32>(rl, 1), wr, orr, fr, pd->fixed_per_rhs, pd->fixed_bits);
+    if (which == 0 && (upload(ctx, &pd->d_fixed_lhs, fl) || upload(ctx, &pd->d_fixed_rhs, fr))) return fail(-1);
+    std::vector<u32> vloff;
+    for (auto& l : vlanes) {
+      vloff.push_back((u32)var_items.size());
+      var_items.insert(var_items.end(), l.begin(), l.end());
+      sc.var_terms_per_thread = std::max<u32>(sc.var_terms_per_thread, (u32)l.size());
+    }
     vloff.push_back((u32)var_items.size());
-    var_items.insert(var_items.end(), l.begin(), l.end());
-    pd->var_terms_per_thread = std::max<u32>(pd->var_terms_per_thread, (u32)l.size());
+    pd->n_var = (u32)var_items.size();
+    sc.var_lanes_total = (u32)vloff.size() - 1;
+    if (sc.var_terms_per_thread > 16) { protocol_release(pd); return svk_fail(ctx, "too many variable-base terms per thread"); }
+    if (upload(ctx, &sc.d_var_lane_off, vloff) || upload(ctx, &sc.d_var_items, var_items) || upload(ctx, &sc.d_work_lhs, wl) ||
+        upload(ctx, &sc.d_lane_off_lhs, ol) || upload(ctx, &sc.d_work_rhs, wr) || upload(ctx, &sc.d_lane_off_rhs, orr))
+      return fail(-1);
   }
-  vloff.push_back((u32)var_items.size());
-  pd->n_var = (u32)var_items.size();
-  pd->var_lanes_total = (u32)vloff.size() - 1;
-  if (pd->var_terms_per_thread > 16) { delete pd; return svk_fail(ctx, "too many variable-base terms per thread (raise SVK_VAR_LANES)"); }
-  if (upload(ctx, &pd->d_var_lane_off, vloff)) { delete pd; return -1; }
-  if (upload(ctx, &pd->d_var_items, var_items) || upload(ctx, &pd->d_work_lhs, wl) || upload(ctx, &pd->d_lane_off_lhs, ol) || upload(ctx, &pd->d_work_rhs, wr) ||
-      upload(ctx, &pd->d_lane_off_rhs, orr)) { delete pd; return -1; }
+  if (upload(ctx, &pd->d_ops, cp.ops) || upload(ctx, &pd->d_aux, cp.aux) || upload(ctx, &pd->d_consts, cp.consts) ||
+      upload(ctx, &pd->d_sched, pd->points) || upload(ctx, &pd->d_lhs, lhs) || upload(ctx, &pd->d_rhs, rhs) || upload(ctx, &pd->d_fixed, fixed))
+    return fail(-1);
+  // Fixed-base tables, shared by every context of the process that compiles the same key on the same device.  The entry is
+  // created, filled and marked ready under the mutex: a second context either fills it or finds it complete.
   pd->table_key = std::to_string(ctx->device) + ":" + std::to_string(pd->fixed_bits) + ":" + std::string((const char*)fixed.data(), fixed.size() * sizeof(G1Affine));
-  bool need_tables = false;
   {
     std::lock_guard<std::mutex> lk(g_table_mu);
     SharedTable& st = g_tables[pd->table_key];
     if (!st.d) {
-      if (cudaMalloc(&st.d, fixed.size() * (256 / pd->fixed_bits) * ((size_t)1 << pd->fixed_bits) * sizeof(G1Affine)) != cudaSuccess) { g_tables.erase(pd->table_key); delete pd; return svk_fail(ctx, "fixed table alloc"); }
-      need_tables = true;
+      size_t bytes = fixed.size() * (256 / pd->fixed_bits) * ((size_t)1 << pd->fixed_bits) * sizeof(G1Affine);
+      if (cudaMalloc(&st.d, bytes) != cudaSuccess) {
+        (void)cudaGetLastError();
+        g_tables.erase(pd->table_key);
+        bool retry = pd->fixed_bits == SVK_FIXED_BITS_LARGE;
+        protocol_release(pd);
+        if (retry) goto retry_small;  // the 16-bit tables do not fit next to the caller's allocations: 8-bit windows (128x smaller)
+        return svk_fail(ctx, "fixed-base table allocation of %zu bytes failed (SVK_FIXED_BITS=8 selects the 128x smaller tables)", bytes);
+      }
+      st.ready = false;
     }
     st.refs++;
     pd->d_fixed_tables = st.d;
+    if (!st.ready) {
+      if (svk_fixed_tables_launch(ctx, pd)) {  // synchronises the stream
+        std::string err = ctx->err;
+        st.refs--;
+        pd->d_fixed_tables = nullptr;
+        if (st.refs == 0) { cudaFree(st.d); g_tables.erase(pd->table_key); }
+        protocol_release(pd);
+        ctx->err = err;
+        return -1;
+      }
+      st.ready = true;
+    }
   }
-  if (upload(ctx, &pd->d_ops, cp.ops) || upload(ctx, &pd->d_aux, cp.aux) || upload(ctx, &pd->d_consts, cp.consts) ||
-      upload(ctx, &pd->d_sched, pd->points) || upload(ctx, &pd->d_lhs, lhs) || upload(ctx, &pd->d_rhs, rhs) || upload(ctx, &pd->d_fixed, fixed)) {
-    delete pd;
-    return -1;
-  }
-  if (need_tables && svk_fixed_tables_launch(ctx, pd)) { delete pd; return -1; }
-  if (!need_tables) SVK_CUDA(ctx, cudaDeviceSynchronize());  // another context may still be filling the shared table
   ctx->protocols.push_back(pd);
   return (int)ctx->protocols.size() - 1;
+retry_small:
+  return protocol_upload(ctx, cp, mos, transcript_kind, dk, SVK_FIXED_BITS_SMALL);
 }
 
 int svk_protocol_info(svk_ctx* ctx, int proto, uint32_t* out) {
@@ -386,7 +436,7 @@ int svk_protocol_info(svk_ctx* ctx, int proto, uint32_t* out) {
   ProtocolDevice* pd = ctx->protocols[proto];
   out[0] = pd->proof_len; out[1] = pd->n_instances; out[2] = pd->n_challenges; out[3] = pd->n_regs; out[4] = pd->n_ops;
   out[5] = (u32)pd->n_perm; out[6] = pd->verify_valid ? 1 : 0; out[7] = (u32)pd->n_fr_mul; out[8] = pd->n_lhs; out[9] = pd->n_rhs;
-  out[10] = (u32)pd->points.size(); out[11] = pd->n_scalar_slots; out[12] = (u32)pd->msm_work_modmul; out[13] = (u32)(pd->n_var * (133 + 50 * 11 + 16 * 7) + pd->var_lanes_total * (255 * 7 + 380));  /* straus.cuh: table 8 dbl + 7 madd + normalisation, ~50 mixed additions; 255 doublings + one inversion per lane */ out[14] = pd->n_var; out[15] = pd->var_lanes_total;
+  out[10] = (u32)pd->points.size(); out[11] = pd->n_scalar_slots; out[12] = (u32)pd->sched[0].msm_work_modmul; out[13] = (u32)(pd->n_var * (133 + 50 * 11 + 16 * 7) + pd->sched[0].var_lanes_total * (255 * 7 + 380));  /* straus.cuh: table 8 dbl + 7 madd + normalisation, ~50 mixed additions; 255 doublings + one inversion per lane */ out[14] = pd->n_var; out[15] = pd->sched[0].var_lanes_total;
   out[16] = pd->n_old; out[17] = pd->acc_limbs; out[18] = pd->acc_bits; out[19] = (u32)pd->transcript_kind;
   return 0;
 }

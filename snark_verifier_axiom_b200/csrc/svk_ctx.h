@@ -9,12 +9,14 @@
 #include <vector>
 
 #include "../../include/svk.h"
-#include "pairing.cuh"
+#include "coop_pairing.cuh"
 #include "poseidon.cuh"
 
 struct DkDevice {
   G2Line* d_lines_g2 = nullptr;       // SVK_N_LINES
   G2Line* d_lines_neg_sg2 = nullptr;  // SVK_N_LINES
+  G2LineX* d_linesx_g2 = nullptr;       // the same lines with their xi-images (coop_pairing.cuh)
+  G2LineX* d_linesx_neg_sg2 = nullptr;
   G1Affine g1;                        // svk.g (Montgomery)
   svk_g1 g1_canon;
 };
@@ -39,6 +41,9 @@ struct svk_ctx {
   std::string err;
   uint64_t launches = 0;
   int sm_count = 0;
+  size_t msm_latency_threads_max = 150000;  // per-proof MSM: one thread per TERM while proofs x terms stays under this
+  size_t tape_coop_max = 32768;   // launches with at most this many proofs (sponges) run the warp-cooperative Poseidon (poseidon_coop.cuh)
+  size_t decide_coop_max = 512;  // decide calls with at most this many accumulators run one accumulator per BLOCK (k_decide_coop)
   PairingConsts* d_pairing_consts = nullptr;
   PoseidonConsts* d_poseidon = nullptr;
   PoseidonConsts h_poseidon;

@@ -38,6 +38,20 @@ struct FixedSlot {
 #define SVK_FIXED_BITS_SMALL 8    // 524 KB per base
 #define SVK_FIXED_BITS_LARGE 16   // 67 MB per base, half the table additions; used while the tables stay under ~3 GB
 
+// Lane schedule of the per-proof MSM (k_msm_var + k_msm_sum).  Two are built per protocol: [0] minimises total work (one
+// Straus thread per proof and side: best when a launch has enough proofs to fill the machine), [1] minimises the dependent
+// chain (one k_msm_var thread per variable-base term: 255 doublings + 52 additions deep instead of 255 + 52 x terms).
+struct MsmSched {
+  MsmWork *d_work_lhs = nullptr, *d_work_rhs = nullptr;  // k_msm_sum items of lane l = work[lane_off[l] .. lane_off[l+1])
+  u32 *d_lane_off_lhs = nullptr, *d_lane_off_rhs = nullptr;
+  MsmWork* d_var_items = nullptr;      // variable-base terms of both sides
+  u32* d_var_lane_off = nullptr;       // items of var lane l = var_items[off[l] .. off[l+1]); partial index = lane
+  u32 var_lanes = 1;                   // k_msm_var threads per proof serving the lhs side
+  u32 var_lanes_total = 1;             // ... plus the lanes of the rhs side (GWC: rhs = sum u^i W_i)
+  u32 var_terms_per_thread = 0;
+  size_t msm_work_modmul = 0;          // algorithmic Fq mults per proof of this schedule (DESIGN.md work model)
+};
+
 struct ProtocolDevice {
   int mos = 0;
   int transcript_kind = 0;  // 0 Poseidon, 1 Keccak EvmTranscript
@@ -56,20 +70,13 @@ struct ProtocolDevice {
   MsmTermDev *d_lhs = nullptr, *d_rhs = nullptr;
   std::vector<MsmTermDev> h_lhs, h_rhs;  // host copies (svk_protocol_msm_terms)
   u32 n_lhs = 0, n_rhs = 0;
-  MsmWork *d_work_lhs = nullptr, *d_work_rhs = nullptr;  // lane schedules: items of lane l = work[lane_off[l] .. lane_off[l+1])
-  u32 *d_lane_off_lhs = nullptr, *d_lane_off_rhs = nullptr;
+  MsmSched sched[2];            // [0] throughput, [1] latency (chosen per launch by the number of proofs)
   FixedSlot *d_fixed_lhs = nullptr, *d_fixed_rhs = nullptr;  // [lane][per] table additions
   u32 fixed_per_lhs = 0, fixed_per_rhs = 0;
   u32 fixed_bits = SVK_FIXED_BITS_SMALL;
   G1Affine* d_fixed_tables = nullptr;  // [n_pre + 1][256 / bits windows][2^bits digits]: d * 2^(bits w) * B, affine Montgomery
-  MsmWork* d_var_items = nullptr;      // variable-base terms of both sides; partial index = position here
-  u32 n_var = 0;
+  u32 n_var = 0;                       // variable-base terms of both sides
   std::string table_key;               // key of the shared fixed-base table (svk_api.cu: g_tables)
-  u32 var_lanes = 1;                   // k_msm_var threads per proof serving the lhs side
-  u32 var_lanes_total = 1;             // ... plus the lanes of the rhs side (GWC: rhs = sum u^i W_i)
-  u32 var_terms_per_thread = 0;
-  u32* d_var_lane_off = nullptr;       // items of var lane l = var_items[off[l] .. off[l+1])
-  size_t msm_work_modmul = 0;          // algorithmic Fq mults per proof of the scheduled MSM (DESIGN.md work model)
   G1Affine* d_fixed = nullptr;  // preprocessed..., then g at index n_pre
   u32 n_pre = 0;
   int dk = -1;                  // deciding key whose g1 is baked in as `svk.g`

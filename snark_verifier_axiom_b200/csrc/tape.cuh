@@ -97,11 +97,19 @@ template <>
 struct TranscriptState<true> {
   KeccakSponge ks;
 };
+// Poseidon sponge interface of the tape: permute / squeeze / reset.  Implemented by the one-thread sponge (here) and by the
+// warp-cooperative one (poseidon_coop.cuh: PoseidonCoopMain, used when a launch has too few proofs to fill the machine).
+HD void ts_permute(TranscriptState<false>& st, const PoseidonConsts& pk, int n_in, const Fr& in0, const Fr& in1) { poseidon_permute(st.ps, pk, n_in, in0, in1); }
+HD Fr ts_squeeze(const TranscriptState<false>& st) { return st.ps.s[1]; }
+HD void ts_reset(TranscriptState<false>& st, const PoseidonConsts& pk) { poseidon_init(st.ps, pk); }
+HD void ts_permute(TranscriptState<true>&, const PoseidonConsts&, int, const Fr&, const Fr&) {}
+HD Fr ts_squeeze(const TranscriptState<true>&) { return Fr::zero(); }
+HD void ts_reset(TranscriptState<true>& st, const PoseidonConsts&) { keccak_reset(st.ks); }
 
 // Executes ops [begin, end) for one item.  Sponge state persists in `st` across calls.
-template <bool KECCAK, class Regs>
+template <bool KECCAK, class Regs, class TS>
 HD void tape_exec(const TapeOp* ops, u32 begin, u32 end, const uint16_t* aux, const Fr* consts, const PoseidonConsts& pk,
-                  const Regs& regs, const TapeIo& io, TranscriptState<KECCAK>& st, u32& err) {
+                  const Regs& regs, const TapeIo& io, TS& st, u32& err) {
   for (u32 pc = begin; pc < end; pc++) {
     TapeOp op = ops[pc];
     switch (op.op) {
@@ -171,15 +179,14 @@ HD void tape_exec(const TapeOp* ops, u32 begin, u32 end, const uint16_t* aux, co
           Fr in0 = Fr::zero(), in1 = Fr::zero();
           if (op.dst >= 1) in0 = regs.load(op.a);
           if (op.dst >= 2) in1 = regs.load(op.b);
-          poseidon_permute(st.ps, pk, op.dst, in0, in1);
+          ts_permute(st, pk, op.dst, in0, in1);
         }
         break;
       case T_SQUEEZE:
-        if constexpr (!KECCAK) regs.store(op.dst, st.ps.s[1]);
+        if constexpr (!KECCAK) regs.store(op.dst, ts_squeeze(st));
         break;
       case T_RESET:
-        if constexpr (!KECCAK) poseidon_init(st.ps, pk);
-        else keccak_reset(st.ks);
+        ts_reset(st, pk);
         break;
       case T_READ_SCALAR_BE:
         if constexpr (KECCAK) {

@@ -8,6 +8,7 @@
 //                    (util/msm.rs:70-77 -> NativeLoader::multi_scalar_multiplication, loader/native.rs:61-71)
 //   k_status       : per-proof `Result` -> status word (include/svk.h)
 #include "compiler.h"
+#include "poseidon_coop.cuh"
 #include "straus.cuh"
 #include "svk_ctx.h"
 #include "svk_protocol.h"
@@ -102,6 +103,44 @@ __global__ void __launch_bounds__(32) k_tape(size_t n_items, const TapeOp* ops, 
   if (e != SVK_NO_ERR) atomicMin(&err[item], e);
 }
 
+// Latency form of k_tape for the Poseidon transcript (poseidon_coop.cuh): 32 proofs per block of three warps; warp 0 runs the
+// tape, warps 1 and 2 hold the other two sponge words during the permutations.  Same tape, same values; lanes past the end
+// of the batch repeat the last proof (identical stores) so that every warp stays whole for the named barriers.
+__device__ __forceinline__ void ts_permute(PoseidonCoopMain& st, const PoseidonConsts& pk, int n_in, const Fr& in0, const Fr& in1) { pcm_permute(st, pk, n_in, in0, in1); }
+__device__ __forceinline__ Fr ts_squeeze(const PoseidonCoopMain& st) { return st.s1; }
+__device__ __forceinline__ void ts_reset(PoseidonCoopMain& st, const PoseidonConsts& pk) { pcm_init(st, pk); }
+
+__global__ void __launch_bounds__(PCOOP_THREADS) k_tape_coop(size_t n_items, const TapeOp* ops, u32 n_ops, const uint16_t* aux, const Fr* consts,
+                                                             const PoseidonConsts* pk, u32* regs, const uint8_t* proofs, size_t proof_stride,
+                                                             const u32* proof_lens, const uint8_t* instances, u32 n_instances, u32* out_scalars,
+                                                             u32* out_challenges, u32 n_challenges, u32* err) {
+  __shared__ PoseidonCoopShared sh;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp) {
+    pc_helper(&sh, *pk, warp, lane);
+    return;
+  }
+  size_t item = (size_t)blockIdx.x * 32 + lane;
+  if (item >= n_items) item = n_items - 1;
+  RegFile rf{regs, n_items, item};
+  TapeIo io;
+  io.proof = proofs + item * proof_stride;
+  io.proof_len = proof_lens ? proof_lens[item] : (u32)proof_stride;
+  io.instances = instances + item * (size_t)n_instances * 32;
+  io.n_instances = n_instances;
+  io.out_scalars = out_scalars;
+  io.out_challenges = out_challenges;
+  io.n_challenge_slots = n_challenges;
+  PoseidonCoopMain st;
+  st.sh = &sh;
+  st.lane = lane;
+  pcm_init(st, *pk);
+  u32 e = SVK_NO_ERR;
+  tape_exec<false>(ops, 0, n_ops, aux, consts, *pk, rf, io, st, e);
+  pcm_exit(st);
+  if (e != SVK_NO_ERR) atomicMin(&err[item], e);
+}
+
 // ------------------------------------------------------------------------------------------------
 #define MSM_LANES SVK_MSM_LANES
 
@@ -166,6 +205,7 @@ __global__ void __launch_bounds__(64) k_fixed_tables(u32 n_fixed, u32 bits, cons
 //                entries prefetched), then the partials and the scalar == 1 bases -> sums[side][proof]
 //   k_to_affine  one proof per thread: one inversion for both sides, canonical accumulator bytes
 #define SVK_VAR_TERMS_MAX 16
+template <bool AFFINE>
 __global__ void __launch_bounds__(64) k_msm_var(size_t n_items, const MsmWork* var_items, const u32* var_lane_off, u32 vpl, const G1Affine* pts,
                                                 const u32* scalars, G1Jac* tables, Fq* prefix, G1Jac* partials) {
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -185,8 +225,8 @@ __global__ void __launch_bounds__(64) k_msm_var(size_t n_items, const MsmWork* v
     G1Affine base = pts[(size_t)wk.base * n_items + it];
     straus_build_table(tables + ((size_t)nt * STRAUS_TABLE) * n_threads + gid, n_threads, base);
   }
-  straus_normalize(tables + gid, prefix + gid, n_threads, nt * STRAUS_TABLE);
-  G1Jac acc = straus_run<true>(&k[0][0], nt, tables + gid, n_threads);
+  if (AFFINE) straus_normalize(tables + gid, prefix + gid, n_threads, nt * STRAUS_TABLE);
+  G1Jac acc = straus_run<AFFINE>(&k[0][0], nt, tables + gid, n_threads);
   partials[gid] = acc;
 }
 
@@ -422,6 +462,11 @@ int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const
                  k_tape<true><<<(unsigned)((n + 31) / 32), 32, 0, s>>>(n, pd->d_ops, n_ops, pd->d_aux, pd->d_consts, ctx->d_poseidon, d_regs,
                                                                       d_proofs, proof_stride, d_proof_lens, d_instances, pd->n_instances,
                                                                       d_scalars, d_out_challenges, pd->n_challenges, d_err));
+    else if (n <= ctx->tape_coop_max)
+      SVK_LAUNCH(ctx, "k_tape_coop",
+                 k_tape_coop<<<(unsigned)((n + 31) / 32), PCOOP_THREADS, 0, s>>>(n, pd->d_ops, n_ops, pd->d_aux, pd->d_consts, ctx->d_poseidon, d_regs,
+                                                                                d_proofs, proof_stride, d_proof_lens, d_instances, pd->n_instances,
+                                                                                d_scalars, d_out_challenges, pd->n_challenges, d_err));
     else
       SVK_LAUNCH(ctx, "k_tape",
                  k_tape<false><<<(unsigned)((n + 31) / 32), 32, 0, s>>>(n, pd->d_ops, n_ops, pd->d_aux, pd->d_consts, ctx->d_poseidon, d_regs,
@@ -435,21 +480,29 @@ int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const
                                                                           pd->n_instances, d_err, d_out_acc, acc_stride));
   if (mode == 0) {
     G1Jac *d_partials, *d_sums, *d_tables;
-    u32 vpl = pd->var_lanes_total;
-    u32 terms_per_thread = pd->var_terms_per_thread;
+    // latency schedule (one k_msm_var thread per term) while its threads still fit the machine a few times over
+    const MsmSched& sc = pd->sched[(n * pd->sched[1].var_lanes_total <= ctx->msm_latency_threads_max) ? 1 : 0];
+    u32 vpl = sc.var_lanes_total;
+    u32 terms_per_thread = sc.var_terms_per_thread;
     if (svk_scratch(ctx, 7, (size_t)std::max<u32>(vpl, 1) * n * sizeof(G1Jac), (void**)&d_partials)) return -1;
     if (svk_scratch(ctx, 15, 2 * n * sizeof(G1Jac), (void**)&d_sums)) return -1;
     if (pd->n_var) {
       size_t total = n * vpl;
       Fq* d_prefix;
       if (svk_scratch(ctx, 6, (size_t)terms_per_thread * 16 * total * sizeof(G1Jac), (void**)&d_tables)) return -1;
-      if (svk_scratch(ctx, 21, (size_t)terms_per_thread * 16 * total * sizeof(Fq), (void**)&d_prefix)) return -1;
-      SVK_LAUNCH(ctx, "k_msm_var",
-                 k_msm_var<<<(unsigned)((total + 63) / 64), 64, 0, s>>>(n, pd->d_var_items, pd->d_var_lane_off, vpl, d_pts, d_scalars, d_tables, d_prefix, d_partials));
+      // threads that own >= 3 terms normalise their tables to affine (one inversion per thread) and use mixed additions
+      if (terms_per_thread >= 3) {
+        if (svk_scratch(ctx, 21, (size_t)terms_per_thread * 16 * total * sizeof(Fq), (void**)&d_prefix)) return -1;
+        SVK_LAUNCH(ctx, "k_msm_var",
+                   k_msm_var<true><<<(unsigned)((total + 63) / 64), 64, 0, s>>>(n, sc.d_var_items, sc.d_var_lane_off, vpl, d_pts, d_scalars, d_tables, d_prefix, d_partials));
+      } else {
+        SVK_LAUNCH(ctx, "k_msm_var",
+                   k_msm_var<false><<<(unsigned)((total + 63) / 64), 64, 0, s>>>(n, sc.d_var_items, sc.d_var_lane_off, vpl, d_pts, d_scalars, d_tables, nullptr, d_partials));
+      }
     }
     dim3 grid((unsigned)((n * MSM_LANES + 127) / 128), 2);
     SVK_LAUNCH(ctx, "k_msm_sum",
-               k_msm_sum<<<grid, 128, 0, s>>>(n, pd->d_work_lhs, pd->d_lane_off_lhs, pd->d_work_rhs, pd->d_lane_off_rhs, pd->d_fixed_lhs,
+               k_msm_sum<<<grid, 128, 0, s>>>(n, sc.d_work_lhs, sc.d_lane_off_lhs, sc.d_work_rhs, sc.d_lane_off_rhs, pd->d_fixed_lhs,
                                               pd->fixed_per_lhs, pd->d_fixed_rhs, pd->fixed_per_rhs, pd->fixed_bits, pd->d_fixed,
                                               pd->d_fixed_tables, d_pts, d_scalars, d_partials, d_sums));
     SVK_LAUNCH(ctx, "k_to_affine", k_to_affine<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(n, d_sums, d_err, d_out_acc, acc_stride));

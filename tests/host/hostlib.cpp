@@ -114,6 +114,40 @@ int host_pairing(const u32* p1_xy, const u32* q1, const u32* p2_xy, const u32* q
 }
 }
 
+#include "../../snark_verifier_axiom_b200/csrc/coop_pairing.cuh"
+struct HostExec {
+  template <class F>
+  void par(int n, F f) { for (int i = 0; i < n; i++) f(i); }
+};
+extern "C" {
+// The block-cooperative pairing program (coop_pairing.cuh) run lane by lane; outputs in the tower order of host_pairing
+int host_pairing_coop(const u32* p1_xy, const u32* q1, const u32* p2_xy, const u32* q2, u32* gt_out, u32* ml_out) {
+  static PairingConsts k = svk_host::make_pairing_consts();
+  G2Affine Q1 = load_g2(q1), Q2 = load_g2(q2);
+  if (!svk_host::g2_on_curve(Q1) || !svk_host::g2_on_curve(Q2)) return -1;
+  std::vector<G2Line> t1 = svk_host::make_line_table(Q1, k), t2 = svk_host::make_line_table(Q2, k);
+  std::vector<G2LineX> x1, x2;
+  for (auto& l : t1) x1.push_back({l.neg_lam, l.c3, l.neg_lam.mul_xi(), l.c3.mul_xi()});
+  for (auto& l : t2) x2.push_back({l.neg_lam, l.c3, l.neg_lam.mul_xi(), l.c3.mul_xi()});
+  G1Affine P1 = load_aff(p1_xy), P2 = load_aff(p2_xy);
+  std::vector<Fq> lb(2 * SVK_N_LINES * COOP_BLK);
+  static CoopMem m;
+  HostExec ex;
+  Fq ml[12], gt[12];
+  bool ok = coop_kzg_decide(ex, P1, P2, x1.data(), x2.data(), k, lb.data(), m, ml, gt);
+  Fq12 mt = coop_to_tower(ml), gtt = coop_to_tower(gt);
+  const Fq2* c[6] = {&gtt.c0.c0, &gtt.c0.c1, &gtt.c0.c2, &gtt.c1.c0, &gtt.c1.c1, &gtt.c1.c2};
+  const Fq2* mm[6] = {&mt.c0.c0, &mt.c0.c1, &mt.c0.c2, &mt.c1.c0, &mt.c1.c1, &mt.c1.c2};
+  for (int i = 0; i < 6; i++) {
+    Fq a = c[i]->c0.from_mont(), b = c[i]->c1.from_mont();
+    memcpy(gt_out + 16 * i, a.v, 32); memcpy(gt_out + 16 * i + 8, b.v, 32);
+    a = mm[i]->c0.from_mont(); b = mm[i]->c1.from_mont();
+    memcpy(ml_out + 16 * i, a.v, 32); memcpy(ml_out + 16 * i + 8, b.v, 32);
+  }
+  return ok ? 1 : 0;
+}
+}
+
 #include "../../snark_verifier_axiom_b200/csrc/poseidon_host.h"
 extern "C" {
 // state/in: canonical limbs; n_in in {0,1,2}; returns 0 ok

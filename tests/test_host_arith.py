@@ -168,6 +168,31 @@ def test_pairing_exact(lib):
         assert rd12(ml) == mlo and rd12(gt) == bn254.final_exponentiation(mlo) and rc == exp
 
 
+def test_coop_pairing_matches_tower(lib):
+    """The block-cooperative pairing (csrc/coop_pairing.cuh: 48 dot3 lanes + 12 combine lanes per Fq12 product), executed
+    lane by lane on the host, gives the oracle's exact Miller and GT values (decider.rs:60-68)."""
+    rng = random.Random(5)
+    s, d = rng.randrange(1, R), rng.randrange(1, R)
+    sg2 = bn254.g2_mul(bn254.G2_GEN, s)
+
+    def g2l(q):
+        return limbs([q[0][0], q[0][1], q[1][0], q[1][1]])
+
+    def rd12(a):
+        v = rd(a, 12)
+        f2 = [(v[2 * i], v[2 * i + 1]) for i in range(6)]
+        return ((f2[0], f2[1], f2[2]), (f2[3], f2[4], f2[5]))
+
+    G = bn254.G1_GEN
+    cases = [(bn254.g1_mul(G, s * d % R), bn254.g1_mul(G, d), 1), (bn254.g1_mul(G, (s * d + 1) % R), bn254.g1_mul(G, d), 0), (None, None, 1),
+             (None, bn254.g1_mul(G, d), 0)]
+    for lhs, rhs, exp in cases:
+        gt, ml = (ctypes.c_uint32 * 96)(), (ctypes.c_uint32 * 96)()
+        rc = lib.host_pairing_coop(g1l(lhs), g2l(bn254.G2_GEN), g1l(rhs), g2l(bn254.g2_neg(sg2)), gt, ml)
+        mlo = bn254.multi_miller_loop([(lhs, bn254.G2_GEN), (rhs, bn254.g2_neg(sg2))])
+        assert rd12(ml) == mlo and rd12(gt) == bn254.final_exponentiation(mlo) and rc == exp
+
+
 def test_poseidon_kat_and_random(lib):
     out = (ctypes.c_uint32 * 24)()
     assert lib.host_poseidon_permute(limbs([0, 1, 2]), 2, limbs([0]), limbs([0]), out) == 0
