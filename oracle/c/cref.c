@@ -127,8 +127,28 @@ static void j_to_affine(g1a* r, const g1j* p) {
   fe zi, zi2; f_inv(Q, &zi, &p->Z); f_sqr(Q, &zi2, &zi);
   f_mul(Q, &r->x, &p->X, &zi2); f_mul(Q, &r->y, &p->Y, &zi2); f_mul(Q, &r->y, &r->y, &zi); r->inf = 0;
 }
+/* Optional "optimised CPU" mode (bench.py cpu_baseline.optimised_value): the same group elements
+ * through a 4-bit fixed-window multiplication (15-entry table, 252 doublings + 64 additions instead of 256 doublings + 256
+ * additions) -- what a tuned CPU verifier would do without changing the reference's structure.  Default 0 = literal port. */
+static int CREF_OPT = 0;
+void cref_set_optimised(int on) { CREF_OPT = on; }
+static void g1_mul_win4(g1j* r, const g1a* p, const fe* k_canon) {
+  g1j tbl[16], acc;
+  j_identity(&tbl[0]);
+  tbl[1].X = p->x; tbl[1].Y = p->y; tbl[1].Z = FQ.one;
+  if (p->inf) j_identity(&tbl[1]);
+  for (int i = 2; i < 16; i++) j_add_affine(&tbl[i], &tbl[i - 1], p);
+  j_identity(&acc);
+  for (int w = 63; w >= 0; w--) {
+    if (w != 63) { j_dbl(&acc, &acc); j_dbl(&acc, &acc); j_dbl(&acc, &acc); j_dbl(&acc, &acc); }
+    unsigned d = (unsigned)(k_canon->v[w >> 4] >> ((w & 15) * 4)) & 0xf;
+    if (d) j_add(&acc, &acc, &tbl[d]);
+  }
+  *r = acc;
+}
 /* halo2curves `&G1Affine * &Fr`: all 256 bits of to_repr(), always add then conditional_select */
 static void g1_mul_ref(g1j* r, const g1a* p, const fe* k_canon) {
+  if (CREF_OPT) { g1_mul_win4(r, p, k_canon); return; }
   g1j acc, t; j_identity(&acc);
   for (int w = 3; w >= 0; w--) for (int b = 63; b >= 0; b--) {
     j_dbl(&acc, &acc);

@@ -71,10 +71,9 @@ __global__ void __launch_bounds__(32) k_fold_sponge(size_t n_seg, size_t n, size
 // have 512, 64, 8 and 1 groups, each a lone serial chain of 2m + 1 permutations.  The permutation count is made uniform
 // across the warp (named barriers need whole warps): a lane whose group is shorter than the longest of its warp (the last
 // group of a segment, lanes past the end) captures its r after its own 2 len + 1 permutations and keeps permuting a dead state.
-__global__ void __launch_bounds__(PCOOP_THREADS) k_fold_sponge_coop(size_t n_seg, size_t n, size_t m, const uint8_t* accs, const PoseidonConsts* pk,
-                                                                    u32* scalars, u32* out_r, size_t out_r_stride_words, int32_t* status,
-                                                                    size_t status_stride_words) {
-  __shared__ PoseidonCoopShared sh;
+__device__ __forceinline__ void fold_sponge_coop_block(PoseidonCoopShared& sh, size_t n_seg, size_t n, size_t m, const uint8_t* accs,
+                                                       const PoseidonConsts* pk, u32* scalars, u32* out_r, size_t out_r_stride_words,
+                                                       int32_t* status, size_t status_stride_words) {
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp) {
     pc_helper(&sh, *pk, warp, lane);
@@ -128,6 +127,13 @@ __global__ void __launch_bounds__(PCOOP_THREADS) k_fold_sponge_coop(size_t n_seg
     p = p * r;
   }
   if (bad) atomicMax(status + seg * status_stride_words, bad);
+}
+
+__global__ void __launch_bounds__(PCOOP_THREADS) k_fold_sponge_coop(size_t n_seg, size_t n, size_t m, const uint8_t* accs, const PoseidonConsts* pk,
+                                                                    u32* scalars, u32* out_r, size_t out_r_stride_words, int32_t* status,
+                                                                    size_t status_stride_words) {
+  __shared__ PoseidonCoopShared sh;
+  fold_sponge_coop_block(sh, n_seg, n, m, accs, pk, scalars, out_r, out_r_stride_words, status, status_stride_words);
 }
 
 // Group MSM, split like the per-proof MSM (verify.cu):
@@ -202,6 +208,96 @@ __global__ void __launch_bounds__(128) k_group_sum(size_t n_seg, size_t n, size_
   o[3] = make_uint4(y.v[4], y.v[5], y.v[6], y.v[7]);
 }
 
+// ---- Narrow levels: the doublings leave the critical path ---------------------------------------------------------------
+// A level of the tree is  sponge -> r -> sum_j r^j A_j.  The 254 doublings of a scalar multiplication do not depend on the
+// scalar when they are applied to the BASE (right-to-left): D_b = 2^b A_j.  So while the sponge blocks hash (a lone chain of
+// 2m + 1 permutations, ~2 ms), the other blocks of the SAME launch compute D_0..D_254 of every accumulator; once r is
+// known, r^j A_j = sum_b naf_b(r^j) D_b is ~85 independent additions, spread over 8 lanes and tree-reduced: ~0.1 ms
+// instead of a 255-doubling chain (1.4 ms) after the sponge.  Used while the table (255 x 96 B per point) stays small.
+#define FOLD_DBL_ENTRIES 255
+#define FOLD_ADD_LANES 8
+__global__ void __launch_bounds__(PCOOP_THREADS) k_fold_sponge_dbl(unsigned sponge_blocks, size_t n_seg, size_t n, size_t m, const uint8_t* accs,
+                                                                   const PoseidonConsts* pk, u32* scalars, u32* out_r, size_t out_r_stride_words,
+                                                                   int32_t* status, size_t status_stride_words, G1Jac* dbl) {
+  __shared__ PoseidonCoopShared sh;
+  if (blockIdx.x < sponge_blocks) {
+    fold_sponge_coop_block(sh, n_seg, n, m, accs, pk, scalars, out_r, out_r_stride_words, status, status_stride_words);
+    return;
+  }
+  size_t n_threads = n_seg * n * 2;
+  size_t tid = (size_t)(blockIdx.x - sponge_blocks) * PCOOP_THREADS + threadIdx.x;
+  if (tid >= n_threads) return;
+  size_t i = tid >> 1;
+  int h = (int)(tid & 1);
+  size_t seg = i / n, li = i % n;
+  if (li % m == 0) return;  // r^0 = 1: k_group_sum adds this base as it is
+  G1Affine base;
+  if (!load_acc_point(base, accs + i * 128 + h * 64)) {
+    atomicMax(status + seg * status_stride_words, SVK_TRANSCRIPT | (SVK_T_POINT_INVALID << 8));
+    base = G1Affine::identity();
+  }
+  G1Jac d = G1Jac::from_affine(base);
+  for (int b = 0; b < FOLD_DBL_ENTRIES; b++) {
+    dbl[(size_t)b * n_threads + tid] = d;
+    d = d.dbl();
+  }
+}
+
+__device__ __forceinline__ G1Jac shfl_xor_jac(const G1Jac& p, int mask) {
+  G1Jac r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.X.v[i] = __shfl_xor_sync(0xffffffffu, p.X.v[i], mask);
+    r.Y.v[i] = __shfl_xor_sync(0xffffffffu, p.Y.v[i], mask);
+    r.Z.v[i] = __shfl_xor_sync(0xffffffffu, p.Z.v[i], mask);
+  }
+  return r;
+}
+
+// partials[(G * 2 + h) * vpl + (j - 1)] = r^j A_j for member j >= 1 of group G; FOLD_ADD_LANES lanes per (accumulator, side)
+__global__ void __launch_bounds__(64) k_fold_add(size_t n_seg, size_t n, size_t m, u32 vpl, const u32* scalars, const G1Jac* dbl, G1Jac* partials) {
+  size_t n_threads = n_seg * n * 2;
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t tid = gid / FOLD_ADD_LANES;
+  u32 lane = (u32)(gid % FOLD_ADD_LANES);
+  bool active = tid < n_threads;
+  if (!active) tid = n_threads - 1;  // whole warps for the shuffles
+  size_t i = tid >> 1;
+  int h = (int)(tid & 1);
+  size_t seg = i / n, li = i % n, n_groups = (n + m - 1) / m;
+  size_t g = li / m, j = li % m;
+  G1Jac acc = G1Jac::identity();
+  if (j != 0) {
+    u32 k[9], k3[10];
+    load_canon32(k, reinterpret_cast<const uint8_t*>(scalars + i * 8));
+    k[8] = 0;
+    // 3k; NAF digit at weight 2^pos = bit(3k, pos + 1) - bit(k, pos + 1)
+    u32 c = 0;
+    for (int w = 0; w < 9; w++) {
+      u64 t = (u64)k[w] * 3 + c;
+      k3[w] = (u32)t;
+      c = (u32)(t >> 32);
+    }
+    k3[9] = 0;
+    const int per = 256 / FOLD_ADD_LANES;
+    for (int q = 0; q < per; q++) {
+      int pos = (int)lane * per + q;
+      if (pos >= FOLD_DBL_ENTRIES) break;
+      int bit = pos + 1;
+      int a = (k3[bit >> 5] >> (bit & 31)) & 1, b = (k[bit >> 5] >> (bit & 31)) & 1;
+      if (a == b) continue;
+      G1Jac d = dbl[(size_t)pos * n_threads + tid];
+      if (b) d.Y = d.Y.neg();
+      acc = acc.add(d);
+    }
+  }
+#pragma unroll
+  for (int d = FOLD_ADD_LANES / 2; d >= 1; d >>= 1) {
+    acc = acc.add(shfl_xor_jac(acc, d));  // butterfly: every lane ends with the sum of its 8-lane group
+  }
+  if (active && lane == 0 && j != 0) partials[((seg * n_groups + g) * 2 + h) * vpl + (j - 1)] = acc;
+}
+
 // Folds `n_seg` independent batches of `n` accumulators each (d_accs: [seg][n] x 128 B) down to one accumulator per
 // batch, written to d_out + seg * out_stride: { svk_acc (128) ; r of the last fold call (32) ; int32 status }.
 // The fold owns scratch slots 8 (ping-pong accumulators) and 9 (scalars).
@@ -228,6 +324,25 @@ int svk_fold_launch_seg(svk_ctx* ctx, size_t n_seg, size_t n, const uint8_t* d_a
     bool last = groups == 1;
     uint8_t* dst = last ? d_out : bufs[which];
     size_t total_groups = groups * n_seg;
+    size_t gm = cnt < m ? cnt : m;
+    size_t pt_threads = n_seg * cnt * 2;
+    G1Jac *d_tables, *d_partials;
+    u32 vpl = 1;
+    if (gm > 1 && gm - 1 <= 64 && pt_threads <= ctx->fold_dbl_threads_max && total_groups <= ctx->tape_coop_max) {
+      // narrow level: doublings of the bases run beside the sponge, the scalar multiplications become additions
+      vpl = (u32)(gm - 1);
+      size_t n_part = total_groups * 2 * vpl;
+      if (svk_scratch(ctx, 20, (size_t)FOLD_DBL_ENTRIES * pt_threads * sizeof(G1Jac), (void**)&d_tables)) return -1;
+      if (svk_scratch(ctx, 18, (n_part + 1) * sizeof(G1Jac), (void**)&d_partials)) return -1;
+      SVK_CUDA(ctx, cudaMemsetAsync(d_partials, 0, n_part * sizeof(G1Jac), s));  // absent members of a short last group: identity (Z = 0)
+      unsigned sponge_blocks = (unsigned)((total_groups + 31) / 32), dbl_blocks = (unsigned)((pt_threads + PCOOP_THREADS - 1) / PCOOP_THREADS);
+      SVK_LAUNCH(ctx, "k_fold_sponge_dbl",
+                 k_fold_sponge_dbl<<<sponge_blocks + dbl_blocks, PCOOP_THREADS, 0, s>>>(sponge_blocks, n_seg, cnt, m, cur, ctx->d_poseidon, d_scal,
+                                                                                       last ? d_r : nullptr, out_stride / 4, d_status, out_stride / 4,
+                                                                                       d_tables));
+      SVK_LAUNCH(ctx, "k_fold_add",
+                 k_fold_add<<<(unsigned)((pt_threads * FOLD_ADD_LANES + 63) / 64), 64, 0, s>>>(n_seg, cnt, m, vpl, d_scal, d_tables, d_partials));
+    } else {
     if (total_groups <= ctx->tape_coop_max)
       SVK_LAUNCH(ctx, "k_fold_sponge_coop",
                  k_fold_sponge_coop<<<(unsigned)((total_groups + 31) / 32), PCOOP_THREADS, 0, s>>>(n_seg, cnt, m, cur, ctx->d_poseidon, d_scal,
@@ -238,13 +353,10 @@ int svk_fold_launch_seg(svk_ctx* ctx, size_t n_seg, size_t n, const uint8_t* d_a
                  k_fold_sponge<<<(unsigned)((total_groups + 31) / 32), 32, 0, s>>>(n_seg, cnt, m, cur, ctx->d_poseidon, d_scal, last ? d_r : nullptr,
                                                                                   out_stride / 4, d_status, out_stride / 4));
     // lanes per (group, side): 1 while there are enough groups to fill the machine, else one lane per term
-    size_t gm = cnt < m ? cnt : m;
-    u32 vpl = 1;
     if (total_groups * 2 < 2048 && gm > 1) vpl = (u32)(gm - 1);
     size_t terms_per_thread = gm > 1 ? (gm - 1 + vpl - 1) / vpl : 0;
     if (terms_per_thread > FOLD_TERMS_MAX) vpl = (u32)((gm - 1 + FOLD_TERMS_MAX - 1) / FOLD_TERMS_MAX), terms_per_thread = (gm - 1 + vpl - 1) / vpl;
     size_t var_threads = total_groups * 2 * vpl;
-    G1Jac *d_tables, *d_partials;
     if (svk_scratch(ctx, 17, (terms_per_thread * 16 * var_threads + 1) * sizeof(G1Jac), (void**)&d_tables)) return -1;
     if (svk_scratch(ctx, 18, (var_threads + 1) * sizeof(G1Jac), (void**)&d_partials)) return -1;
     // threads that own >= 3 terms normalise their tables to affine (one inversion per thread) and use mixed additions
@@ -258,6 +370,7 @@ int svk_fold_launch_seg(svk_ctx* ctx, size_t n_seg, size_t n, const uint8_t* d_a
       SVK_LAUNCH(ctx, "k_group_var",
                  k_group_var<false><<<(unsigned)((var_threads + 63) / 64), 64, 0, s>>>(n_seg, cnt, m, vpl, cur, d_scal, d_tables, nullptr, d_partials,
                                                                                        d_status, out_stride / 4));
+    }
     }
     SVK_LAUNCH(ctx, "k_group_sum",
                k_group_sum<<<(unsigned)((total_groups * 2 + 127) / 128), 128, 0, s>>>(n_seg, cnt, m, vpl, cur, d_partials, dst,

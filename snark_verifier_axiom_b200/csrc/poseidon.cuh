@@ -29,6 +29,10 @@ struct PoseidonConsts {
   //   [0..3] = row_{2p+1}[0], row_{2p+1}[1] col_{2p}[0] + row_{2p+1}[2] col_{2p}[1], row_{2p+1}[1], row_{2p+1}[2]
   //   [4..5] = col_{2p+1}[0], col_{2p}[0]      [6..7] = col_{2p+1}[1], col_{2p}[1]
   Fr pair[SVK_POSEIDON_RP / 2][8];
+  // Warp-cooperative schedule (poseidon_coop.cuh): the round constant of a partial round is folded into the helpers' terms,
+  //   coop_rc[r] = row_r[0] * partial[r],   coop_cc[r][w] = col_hat_r[w] * partial[r]          (derived, value-identical)
+  Fr coop_rc[SVK_POSEIDON_RP];
+  Fr coop_cc[SVK_POSEIDON_RP][2];
 };
 
 struct PoseidonState {

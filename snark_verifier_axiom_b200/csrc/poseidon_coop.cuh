@@ -7,17 +7,18 @@
 // sponge l ("warp-specialised": warp 0 = the transcript owner, warps 1, 2 = helpers), so the warps never diverge and the
 // register-file layouts ([reg][item]) of the callers stay coalesced:
 //   full round     every warp: y_w = s_w^5 + c_w, exchange through shared memory, s_w = <M[w], y>          (4 products deep)
-//   partial round  warp 0: y = s_0^5 + c, post y, t = row_0 y, s_0 = t + P_1 + P_2                          (4 products deep)
-//                  warp w: P_w = row_w s_w (posted BEFORE y is needed), then s_w += col_w y
-// Warp 0 never waits for a helper in the partial rounds (P_w of round r only needs y of round r - 1); the helpers wait for
-// y.  Synchronisation = named barriers (bar.arrive / bar.sync, producer/consumer form), mailboxes double-buffered.
+//   partial round  warp 0: x = s_0^5, post x, t = row_0 x, s_0 = t + P                                       (4 products + 1 addition deep)
+//                  warp 2: P_2 = row_2 s_2 -> warp 1;   warp 1: P = row_1 s_1 + P_2 + row_0 c -> warp 0   (posted BEFORE x is needed)
+//                  warp w: s_w = col_w x + (s_w + col_w c)          (c = the round constant: y = x + c never materialises)
+// Warp 0 never waits for a helper in the partial rounds (P of round r only needs x of round r - 1); the helpers wait for
+// x.  Synchronisation = named barriers (bar.arrive / bar.sync, producer/consumer form), mailboxes double-buffered.
 // Dependent chain per permutation: 65 x 4 products + the exchanges, instead of ~475 product-equivalents.
 #pragma once
 #include "poseidon.cuh"
 
 #if defined(__CUDACC__)
 #define PCOOP_THREADS 96
-enum { PC_BAR_CMD = 1, PC_BAR_FULL = 2, PC_BAR_Y = 3 /* 3, 4 */, PC_BAR_P = 5 /* 5, 6 */ };
+enum { PC_BAR_CMD = 1, PC_BAR_FULL = 2, PC_BAR_Y = 3 /* 3, 4 */, PC_BAR_P = 5 /* 5, 6 */, PC_BAR_Q = 7 /* 7, 8 */ };
 #define PC_CMD_RESET 4
 #define PC_CMD_EXIT 8
 
@@ -31,6 +32,15 @@ struct __align__(16) PoseidonCoopShared {
 
 __device__ __forceinline__ void pc_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(PCOOP_THREADS) : "memory"); }
 __device__ __forceinline__ void pc_bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(PCOOP_THREADS) : "memory"); }
+// two-warp producer/consumer pairs (64 participants)
+__device__ __forceinline__ void pc_bar_sync2(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void pc_bar_arrive2(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+// products inlined: the loops below are short and run by lone warps (a by-value call costs ~20 moves per product)
+__device__ __forceinline__ Fr pc_pow5(const Fr& x) {
+  Fr x2 = Fr::sqr_inline(x);
+  Fr x4 = Fr::sqr_inline(x2);
+  return Fr::mul_inline(x4, x);
+}
 __device__ __forceinline__ void pc_st(uint4* p, const Fr& x) {
   p[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
   p[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
@@ -56,7 +66,7 @@ static __device__ __noinline__ void pc_permute(Fr& s, int role, int lane, Poseid
   }
   int buf = 0;
   auto full = [&](const Fr(*M)[3], const Fr* cr) {
-    Fr y = fr_pow5(s);
+    Fr y = pc_pow5(s);
     if (cr) y = y + cr[role];
     pc_st(sh->mail[buf][role][lane], y);
     pc_bar_sync(PC_BAR_FULL);
@@ -69,22 +79,34 @@ static __device__ __noinline__ void pc_permute(Fr& s, int role, int lane, Poseid
   // partial rounds with the sparse MDS factorisation (poseidon.rs:398-410)
   if (role == 0) {
     for (int r = 0; r < SVK_POSEIDON_RP; r++) {
-      Fr y = fr_pow5(s) + k.partial[r];
-      pc_st(sh->mail[buf][0][lane], y);
+      Fr x = pc_pow5(s);
+      pc_st(sh->mail[buf][0][lane], x);
       pc_bar_arrive(PC_BAR_Y + buf);
-      Fr t = k.sparse_row[r][0] * y;
-      pc_bar_sync(PC_BAR_P + buf);
-      s = t + pc_ld(sh->mail[buf][1][lane]) + pc_ld(sh->mail[buf][2][lane]);
+      Fr t = Fr::mul_inline(k.sparse_row[r][0], x);
+      pc_bar_sync2(PC_BAR_P + buf);
+      s = t + pc_ld(sh->mail[buf][1][lane]);
+      buf ^= 1;
+    }
+  } else if (role == 1) {
+    for (int r = 0; r < SVK_POSEIDON_RP; r++) {
+      Fr P = Fr::mul_inline(k.sparse_row[r][1], s) + k.coop_rc[r];
+      pc_bar_sync2(PC_BAR_Q + buf);
+      P = P + pc_ld(sh->mail[buf][2][lane]);
+      pc_st(sh->mail[buf][1][lane], P);
+      pc_bar_arrive2(PC_BAR_P + buf);
+      Fr u = s + k.coop_cc[r][0];
+      pc_bar_sync(PC_BAR_Y + buf);
+      s = Fr::mul_inline(k.sparse_col_hat[r][0], pc_ld(sh->mail[buf][0][lane])) + u;
       buf ^= 1;
     }
   } else {
     for (int r = 0; r < SVK_POSEIDON_RP; r++) {
-      Fr P = k.sparse_row[r][role] * s;
-      pc_st(sh->mail[buf][role][lane], P);
-      pc_bar_arrive(PC_BAR_P + buf);
+      Fr P = Fr::mul_inline(k.sparse_row[r][2], s);
+      pc_st(sh->mail[buf][2][lane], P);
+      pc_bar_arrive2(PC_BAR_Q + buf);
+      Fr u = s + k.coop_cc[r][1];
       pc_bar_sync(PC_BAR_Y + buf);
-      Fr y = pc_ld(sh->mail[buf][0][lane]);
-      s = k.sparse_col_hat[r][role - 1] * y + s;
+      s = Fr::mul_inline(k.sparse_col_hat[r][1], pc_ld(sh->mail[buf][0][lane])) + u;
       buf ^= 1;
     }
   }

@@ -184,6 +184,11 @@ inline bool make_poseidon_consts(PoseidonConsts& k, int secure_mds = 0) {
     k.pair[p][6] = k.sparse_col_hat[b][1];
     k.pair[p][7] = k.sparse_col_hat[a][1];
   }
+  for (int r = 0; r < SVK_POSEIDON_RP; r++) {
+    k.coop_rc[r] = k.sparse_row[r][0] * k.partial[r];
+    k.coop_cc[r][0] = k.sparse_col_hat[r][0] * k.partial[r];
+    k.coop_cc[r][1] = k.sparse_col_hat[r][1] * k.partial[r];
+  }
   Fr cap = Fr::zero();
   cap.v[2] = 1;  // 2^64
   k.capacity = cap.to_mont();
