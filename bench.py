@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="proofs in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tiled", action="store_true", help="tile the 64 fixture proofs instead of forging distinct ones")
+    ap.add_argument("--stream-priorities", type=int, default=0, help="1: slot i gets a higher stream priority than slot i + 1, so that concurrent launches finish "
+                    "one after the other and the narrow tail of one (fold levels, pairing) runs beside the wide kernels of the next")
     return ap.parse_args()
 
 
@@ -176,9 +178,9 @@ class Slot:
     keep several independent 4096-proof batches in flight, which is how a throughput device hides the
     latency-bound tail of a batch (serial fold sponge, the single pairing)."""
 
-    def __init__(self, torch, V, ShardedBatchVerifier, g, local, dev, world, rank, group_size, max_batches, mos):
+    def __init__(self, torch, V, ShardedBatchVerifier, g, local, dev, world, rank, group_size, max_batches, mos, priority=0):
         self.ctx = V.Context(local)
-        self.stream = torch.cuda.Stream(device=dev)
+        self.stream = torch.cuda.Stream(device=dev, priority=priority)
         self.ctx.set_stream(self.stream.cuda_stream)
         self.pv = V.PlonkVerifier(self.ctx, g["dk"], g["protocol"], mos)
         self.sv = ShardedBatchVerifier(self.pv, world, rank, dev, self.stream, group_size=group_size, max_batches=max_batches)
@@ -222,7 +224,8 @@ def run_ours(args):
     nb1 = args.batch           # proofs per batch (= per step)
     n = args.batch * B         # proofs per launch
     steps = -(-args.steps // B) * B  # whole launches
-    slots = [Slot(torch, V, ShardedBatchVerifier, g, local, dev, world, rank, args.group_size, B, mos) for _ in range(S)]
+    prio = [max(-5, -(S - 1 - i)) if args.stream_priorities else 0 for i in range(S)]
+    slots = [Slot(torch, V, ShardedBatchVerifier, g, local, dev, world, rank, args.group_size, B, mos, prio[i]) for i in range(S)]
     pv = slots[0].pv
     data = "synthetic: 64 distinct trapdoor-forged StandardPlonk k=8 proofs (tests/golden, oracle-generated) tiled to the batch"
     if args.scheme == "bdfg21" and not args.tiled:

@@ -100,21 +100,22 @@ HD void coop_combine_task(Fq* out, const Fq* part, int t) {
   out[12 + t] = c == 0 ? fq_mul9(mine) - other : fq_mul9(mine) + other;
 }
 
-// out = a * b   (blocks; out may alias a and/or b)
+// out = a * b   (blocks; out may alias a and/or b).  The block-level operations are out-of-line on the device: the pairing program
+// has ~50 call sites and one warp runs it, so inlining them (0.3 MB of code) would live in instruction-cache misses.
 template <class Ex>
-HD void coop_mul(Ex& ex, Fq* out, const Fq* a, const Fq* b, Fq* part) {
+HDN void coop_mul(Ex& ex, Fq* out, const Fq* a, const Fq* b, Fq* part) {
   ex.par(COOP_DOT_LANES, [&](int t) { coop_dot_task(part, a, b, t); });
   ex.par(12, [&](int t) { coop_combine_task(out, part, t); });
 }
 
 template <class Ex>
-HD void coop_copy(Ex& ex, Fq* out, const Fq* a) {
+HDN void coop_copy(Ex& ex, Fq* out, const Fq* a) {
   ex.par(COOP_BLK, [&](int t) { out[t] = a[t]; });
 }
 
 // conjugation over Fq6: the odd powers of w change sign (both halves of the block)
 template <class Ex>
-HD void coop_conj(Ex& ex, Fq* out, const Fq* a) {
+HDN void coop_conj(Ex& ex, Fq* out, const Fq* a) {
   ex.par(COOP_BLK, [&](int t) {
     int k = (t % 12) >> 1;
     out[t] = (k & 1) ? a[t].neg() : a[t];
@@ -123,7 +124,7 @@ HD void coop_conj(Ex& ex, Fq* out, const Fq* a) {
 
 // Frobenius^j (j = 1, 2, 3): coefficient k -> conj^j(f_k) * gamma_{j,k}   (pairing.cuh fq12_frob1/2/3)
 template <class Ex>
-HD void coop_frob(Ex& ex, Fq* out, const Fq* a, int j, const PairingConsts& K, Fq* scratch12) {
+HDN void coop_frob(Ex& ex, Fq* out, const Fq* a, int j, const PairingConsts& K, Fq* scratch12) {
   ex.par(12, [&](int t) {
     int k = t >> 1, c = t & 1;
     Fq a0 = a[2 * k], a1 = a[2 * k + 1];
@@ -165,14 +166,14 @@ HD void coop_from_tower(Fq* blk, const Fq12& f) {
 
 // inversion: once per pairing, on one lane through the tower (tower.cuh)
 template <class Ex>
-HD void coop_inv(Ex& ex, Fq* out, const Fq* a) {
+HDN void coop_inv(Ex& ex, Fq* out, const Fq* a) {
   ex.par(1, [&](int) { coop_from_tower(out, coop_to_tower(a).inv()); });
   ex.par(12, [&](int t) { coop_xi_task(out, t); });
 }
 
 // r = x^X for the BN parameter X (pairing.cuh fq12_pow_x); x in the cyclotomic subgroup.  r must not alias x.
 template <class Ex>
-HD void coop_pow_x(Ex& ex, Fq* r, const Fq* x, Fq* part) {
+HDN void coop_pow_x(Ex& ex, Fq* r, const Fq* x, Fq* part) {
   coop_copy(ex, r, x);
   for (int i = 61; i >= 0; i--) {
     coop_mul(ex, r, r, r, part);

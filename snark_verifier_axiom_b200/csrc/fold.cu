@@ -215,7 +215,6 @@ __global__ void __launch_bounds__(128) k_group_sum(size_t n_seg, size_t n, size_
 // known, r^j A_j = sum_b naf_b(r^j) D_b is ~85 independent additions, spread over 8 lanes and tree-reduced: ~0.1 ms
 // instead of a 255-doubling chain (1.4 ms) after the sponge.  Used while the table (255 x 96 B per point) stays small.
 #define FOLD_DBL_ENTRIES 255
-#define FOLD_ADD_LANES 8
 __global__ void __launch_bounds__(PCOOP_THREADS) k_fold_sponge_dbl(unsigned sponge_blocks, size_t n_seg, size_t n, size_t m, const uint8_t* accs,
                                                                    const PoseidonConsts* pk, u32* scalars, u32* out_r, size_t out_r_stride_words,
                                                                    int32_t* status, size_t status_stride_words, G1Jac* dbl) {
@@ -254,12 +253,16 @@ __device__ __forceinline__ G1Jac shfl_xor_jac(const G1Jac& p, int mask) {
   return r;
 }
 
-// partials[(G * 2 + h) * vpl + (j - 1)] = r^j A_j for member j >= 1 of group G; FOLD_ADD_LANES lanes per (accumulator, side)
+// partials[(G * 2 + h) * vpl + (j - 1)] = r^j A_j for member j >= 1 of group G; LANES lanes per (accumulator, side).
+// A lane first packs the positions of its non-zero NAF digits, then adds: the trip count of a warp is the longest list of its
+// lanes (~ a third of the positions), not the number of positions (a digit test inside the loop made every position cost an
+// addition for the whole warp: 0.41 ms per level instead of 0.1).
+template <int LANES>
 __global__ void __launch_bounds__(64) k_fold_add(size_t n_seg, size_t n, size_t m, u32 vpl, const u32* scalars, const G1Jac* dbl, G1Jac* partials) {
   size_t n_threads = n_seg * n * 2;
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t tid = gid / FOLD_ADD_LANES;
-  u32 lane = (u32)(gid % FOLD_ADD_LANES);
+  size_t tid = gid / LANES;
+  u32 lane = (u32)(gid % LANES);
   bool active = tid < n_threads;
   if (!active) tid = n_threads - 1;  // whole warps for the shuffles
   size_t i = tid >> 1;
@@ -267,6 +270,9 @@ __global__ void __launch_bounds__(64) k_fold_add(size_t n_seg, size_t n, size_t 
   size_t seg = i / n, li = i % n, n_groups = (n + m - 1) / m;
   size_t g = li / m, j = li % m;
   G1Jac acc = G1Jac::identity();
+  constexpr int per = 256 / LANES;
+  // non-zero digits of this lane: bit q of `nz`, sign in `ng`
+  u32 nz = 0, ng = 0;
   if (j != 0) {
     u32 k[9], k3[10];
     load_canon32(k, reinterpret_cast<const uint8_t*>(scalars + i * 8));
@@ -279,22 +285,26 @@ __global__ void __launch_bounds__(64) k_fold_add(size_t n_seg, size_t n, size_t 
       c = (u32)(t >> 32);
     }
     k3[9] = 0;
-    const int per = 256 / FOLD_ADD_LANES;
     for (int q = 0; q < per; q++) {
       int pos = (int)lane * per + q;
       if (pos >= FOLD_DBL_ENTRIES) break;
       int bit = pos + 1;
-      int a = (k3[bit >> 5] >> (bit & 31)) & 1, b = (k[bit >> 5] >> (bit & 31)) & 1;
-      if (a == b) continue;
-      G1Jac d = dbl[(size_t)pos * n_threads + tid];
-      if (b) d.Y = d.Y.neg();
+      u32 a = (k3[bit >> 5] >> (bit & 31)) & 1, b = (k[bit >> 5] >> (bit & 31)) & 1;
+      nz |= (a ^ b) << q;
+      ng |= b << q;
+    }
+  }
+  while (__any_sync(0xffffffffu, nz != 0)) {
+    if (nz) {
+      int q = __ffs(nz) - 1;
+      nz &= nz - 1;
+      G1Jac d = dbl[((size_t)lane * per + q) * n_threads + tid];
+      if ((ng >> q) & 1) d.Y = d.Y.neg();
       acc = acc.add(d);
     }
   }
 #pragma unroll
-  for (int d = FOLD_ADD_LANES / 2; d >= 1; d >>= 1) {
-    acc = acc.add(shfl_xor_jac(acc, d));  // butterfly: every lane ends with the sum of its 8-lane group
-  }
+  for (int d = LANES / 2; d >= 1; d >>= 1) acc = acc.add(shfl_xor_jac(acc, d));  // butterfly: every lane ends with the sum of its group
   if (active && lane == 0 && j != 0) partials[((seg * n_groups + g) * 2 + h) * vpl + (j - 1)] = acc;
 }
 
@@ -340,8 +350,11 @@ int svk_fold_launch_seg(svk_ctx* ctx, size_t n_seg, size_t n, const uint8_t* d_a
                  k_fold_sponge_dbl<<<sponge_blocks + dbl_blocks, PCOOP_THREADS, 0, s>>>(sponge_blocks, n_seg, cnt, m, cur, ctx->d_poseidon, d_scal,
                                                                                        last ? d_r : nullptr, out_stride / 4, d_status, out_stride / 4,
                                                                                        d_tables));
-      SVK_LAUNCH(ctx, "k_fold_add",
-                 k_fold_add<<<(unsigned)((pt_threads * FOLD_ADD_LANES + 63) / 64), 64, 0, s>>>(n_seg, cnt, m, vpl, d_scal, d_tables, d_partials));
+      // 8 lanes per point while the points alone fill the machine, 32 on the narrow levels
+      if (pt_threads >= 4096)
+        SVK_LAUNCH(ctx, "k_fold_add", k_fold_add<8><<<(unsigned)((pt_threads * 8 + 63) / 64), 64, 0, s>>>(n_seg, cnt, m, vpl, d_scal, d_tables, d_partials));
+      else
+        SVK_LAUNCH(ctx, "k_fold_add", k_fold_add<32><<<(unsigned)((pt_threads * 32 + 63) / 64), 64, 0, s>>>(n_seg, cnt, m, vpl, d_scal, d_tables, d_partials));
     } else {
     if (total_groups <= ctx->tape_coop_max)
       SVK_LAUNCH(ctx, "k_fold_sponge_coop",

@@ -67,19 +67,29 @@ class ShardedBatchVerifier:
         self.pv = pv
         self._n = 0
         self.max_batches = max_batches
+        # libsvk must run on the stream the collectives and the buffer initialisation are ordered on
+        if stream is not None and device.type == "cuda" and isinstance(self.ops, LibsvkOps):
+            pv.ctx.set_stream(stream.cuda_stream)
         kw = dict(dtype=torch.uint8, device=device)
-        self.d_records = torch.zeros(max_batches * RECORD, **kw)
-        self.d_gather = torch.zeros(world * max_batches * RECORD, **kw)
-        self.d_final = torch.zeros(max_batches * RECORD, **kw)
+        with self._on_stream():
+            self.d_records = torch.zeros(max_batches * RECORD, **kw)
+            self.d_gather = torch.zeros(world * max_batches * RECORD, **kw)
+            self.d_final = torch.zeros(max_batches * RECORD, **kw)
         self.d_accs = self.d_status = None
         self.nb = 1
 
     def _ensure(self, n):
         if self._n < n:
             apk = 1 + getattr(self.pv, "info", {}).get("n_old_accumulators", 0)  # [new, old...] per proof (verifier/plonk.rs:86-91)
-            self.d_accs = torch.zeros(n * apk * 128, dtype=torch.uint8, device=self.device)
-            self.d_status = torch.zeros(n, dtype=torch.int32, device=self.device)
+            self._sync()  # kernels of an earlier call may still use the buffers being replaced
+            with self._on_stream():
+                self.d_accs = torch.zeros(n * apk * 128, dtype=torch.uint8, device=self.device)
+                self.d_status = torch.zeros(n, dtype=torch.int32, device=self.device)
             self._n = n
+
+    def _sync(self):
+        if self.stream is not None and self.device.type == "cuda":
+            self.stream.synchronize()
 
     def _on_stream(self):
         if self.stream is not None and self.device.type == "cuda":
@@ -112,6 +122,7 @@ class ShardedBatchVerifier:
 
     def last_verdicts(self):
         nb = self.nb
+        self._sync()  # `.cpu()` below only orders against torch's current stream
         if self.world == 1:
             rec = self.d_records[: nb * RECORD].cpu().numpy().reshape(nb, RECORD)
             return [bool(x) for x in rec[:, OFF_OK]]
@@ -124,6 +135,7 @@ class ShardedBatchVerifier:
         return out
 
     def final_accumulator(self, b=0) -> bytes:
+        self._sync()
         src = self.d_records if self.world == 1 else self.d_final
         return src.cpu().numpy()[b * RECORD : b * RECORD + 128].tobytes()
 
