@@ -37,11 +37,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=1024, help="timed steps; one step = one 4096-proof batch (succinct verify each, fold, one pairing)")
     ap.add_argument("--inflight", type=int, default=16, help="launches in flight (one libsvk context + stream each)")
     ap.add_argument("--batches-per-launch", type=int, default=0, help="4096-proof batches verified by one call (each folded + decided on its own); "
-                    "0 = auto: the largest B <= 32 that divides --steps and still gives every in-flight slot a launch (measured on B200, 16 slots: "
-                    "B = 8 1.40 M proofs/s, B = 16 1.48 M, B = 32 1.53 M)")
+                    "0 = auto: the largest divisor B <= 32 of --steps that leaves at least two launches (choose_batches_per_launch)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4096, help="proofs per GPU per step")
-    ap.add_argument("--group-size", type=int, default=8, help="KzgAs fold group size (0 = the reference's flat fold)")
+    ap.add_argument("--group-size", type=int, default=4, help="KzgAs fold group size (0 = the reference's flat fold); 4 minimises the serial "
+                    "permutations of the tree over 4096 accumulators (6 levels x 9 = 54; groups of 8: 4 x 17 = 68)")
     ap.add_argument("--scheme", default="bdfg21", choices=["bdfg21", "gwc19"], help="multi-open scheme of the proofs (BASELINE config 2: SHPLONK; config 4: GWC)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="proofs in the CPU-baseline sample (0 = auto)")
@@ -187,13 +187,18 @@ class Slot:
 
 
 def choose_batches_per_launch(steps, slots, requested=0, cap=32):
-    """Batches carried by one call.  Auto (requested <= 0): the largest B <= cap that divides `steps` (so exactly `steps` batches
-    are timed) and still leaves every in-flight slot at least one launch."""
+    """Batches carried by one call.  Auto (requested <= 0): the LARGEST divisor B <= cap of `steps` that still leaves two launches,
+    so exactly `steps` batches are timed, the wide kernels of a launch fill the machine, and the narrow tail of one launch (fold
+    levels, the pairing) runs beside the wide kernels of another.  Measured on B200 at --steps 20 (profiles/r2_notes.md):
+    2 x 10 batches 1.30 M proofs/s, 1 x 20 1.25 M, 4 x 5 1.16 M, 20 x 1 0.70 M; at --steps 1024: 32 x 32.  A prime `steps` <= cap
+    goes out as ONE launch rather than `steps` single-batch launches."""
     if requested > 0:
         return requested
-    b = max(1, min(cap, steps // max(1, slots)))
-    while steps % b:
-        b -= 1
+    divs = [b for b in range(1, min(cap, steps) + 1) if steps % b == 0]
+    two = [b for b in divs if steps // b >= 2]
+    b = max(two) if two else max(divs)
+    if b == 1 and steps <= cap:
+        b = steps
     return b
 
 
@@ -216,9 +221,9 @@ def run_ours(args):
     from snark_verifier_axiom_b200 import verifier as V
     from snark_verifier_axiom_b200.distributed import ShardedBatchVerifier
 
-    S = max(1, args.inflight)
-    # K timed steps = K batches.  A launch carries B batches; with few steps, smaller launches keep all S slots busy.
-    B = choose_batches_per_launch(args.steps, S, args.batches_per_launch)
+    # K timed steps = K batches.  A launch carries B batches; no more slots (contexts, streams) than launches.
+    B = choose_batches_per_launch(args.steps, max(1, args.inflight), args.batches_per_launch)
+    S = max(1, min(args.inflight, -(-args.steps // B)))
     g, reps, np = make_workload(args.batch * B, args.scheme)
     mos = V.SHPLONK if args.scheme == "bdfg21" else V.GWC
     nb1 = args.batch           # proofs per batch (= per step)

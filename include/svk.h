@@ -114,7 +114,12 @@ int svk_protocol_info(svk_ctx* ctx, int proto, uint32_t* out);
  *   out_status[i]     = SVK_OK / SVK_INVALID_INSTANCES / SVK_INVALID_PROTOCOL /
  *                       SVK_TRANSCRIPT | subcode << 8 / SVK_ACCUMULATOR_PANIC
  * instances: n * n_instances field elements (all instance columns of a proof, concatenated);
- * n_instances != sum(protocol.num_instance) => SVK_INVALID_INSTANCES for every proof (proof.rs:66-69). */
+ * n_instances != sum(protocol.num_instance) => SVK_INVALID_INSTANCES for every proof (proof.rs:66-69).  The batch calls
+ * carry the FLAT count; the per-column comparison of proof.rs:66-69 is svk_plonk_instance_shape_ok below, which a host
+ * binding applies to every snark before flattening its columns (snark_verifier_axiom_b200/verifier.py: PlonkVerifier.pack).
+ * proof_lens[i] > proof_stride is clamped to proof_stride (a proof never reads its neighbour's bytes). */
+/* 1 when the column lengths equal protocol.num_instance (proof.rs:66-69), 0 when not, < 0 on a bad protocol id. */
+int svk_plonk_instance_shape_ok(svk_ctx* ctx, int proto, uint32_t n_cols, const uint32_t* col_lens);
 int svk_plonk_succinct_verify_batch(svk_ctx* ctx, int proto, size_t n, const svk_fe* instances, uint32_t n_instances,
                                     const uint8_t* proofs, size_t proof_stride, const uint32_t* proof_lens, svk_acc* out_acc,
                                     svk_fe* out_challenges, int32_t* out_status);

@@ -35,6 +35,7 @@ def _load():
     lib.svk_protocol_compile_ex.argtypes = [vp, u8p, sz, i32, i32, i32]
     lib.svk_protocol_compile_bincode.argtypes = [vp, u8p, sz, i32, i32, i32, i32, ctypes.POINTER(sz), ctypes.POINTER(i32)]
     lib.svk_protocol_info.argtypes = [vp, i32, u32p]
+    lib.svk_plonk_instance_shape_ok.argtypes = [vp, i32, ctypes.c_uint32, vp]
     lib.svk_plonk_succinct_verify_batch.argtypes = [vp, i32, sz, vp, ctypes.c_uint32, vp, sz, vp, vp, vp, vp]
     lib.svk_plonk_succinct_verify_batch_dev.argtypes = [vp, i32, sz, vp, ctypes.c_uint32, vp, sz, vp, vp, vp, vp]
     lib.svk_kzg_as_fold.argtypes = [vp, sz, vp, sz, vp, vp, vp]

@@ -442,6 +442,18 @@ int svk_protocol_info(svk_ctx* ctx, int proto, uint32_t* out) {
   return 0;
 }
 
+// The per-column instance check of `PlonkProof::read` (proof.rs:66-69): `instances[i].len() == protocol.num_instance[i]` for
+// every column.  The batch entry points carry the FLAT count only; a host binding calls this once per snark shape and
+// reports SVK_INVALID_INSTANCES for a snark whose columns differ ([[a], [b, c]] against num_instance [2, 1] has the right total).
+int svk_plonk_instance_shape_ok(svk_ctx* ctx, int proto, uint32_t n_cols, const uint32_t* col_lens) {
+  if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
+  const std::vector<u32>& want = ctx->protocols[proto]->num_instance;
+  if (want.size() != n_cols) return 0;
+  for (size_t i = 0; i < want.size(); i++)
+    if (want[i] != col_lens[i]) return 0;
+  return 1;
+}
+
 // ---- the unevaluated `Msm` of the final accumulator (util/msm.rs:20-24): terms and per-proof scalars -------------
 int svk_protocol_msm_terms(svk_ctx* ctx, int proto, int side, int32_t* out, size_t max_terms) {
   if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);

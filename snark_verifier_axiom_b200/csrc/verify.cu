@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(128) k_decompress(size_t n_items, u32 n_points
   size_t item = idx % n_items;
   u32 pi = (u32)(idx / n_items);
   PointSched s = sched[pi];
-  u32 len = proof_lens ? proof_lens[item] : (u32)proof_stride;
+  u32 len = proof_lens ? min(proof_lens[item], (u32)proof_stride) : (u32)proof_stride;
   G1Affine pt = G1Affine::identity();
   Fr fx = Fr::zero(), fy = Fr::zero();
   if (s.byte_offset + 32 > len) {
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(128) k_load_points_be(size_t n_items, u32 n_po
   size_t item = idx % n_items;
   u32 pi = (u32)(idx / n_items);
   PointSched s = sched[pi];
-  u32 len = proof_lens ? proof_lens[item] : (u32)proof_stride;
+  u32 len = proof_lens ? min(proof_lens[item], (u32)proof_stride) : (u32)proof_stride;
   G1Affine pt = G1Affine::identity();
   if (s.byte_offset + 64 > len) {
     atomicMin(&err[item], (s.byte_offset << 8) | SVK_T_EOF);
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(32) k_tape(size_t n_items, const TapeOp* ops, 
   RegFile rf{regs, n_items, item};
   TapeIo io;
   io.proof = proofs + item * proof_stride;
-  io.proof_len = proof_lens ? proof_lens[item] : (u32)proof_stride;
+  io.proof_len = proof_lens ? min(proof_lens[item], (u32)proof_stride) : (u32)proof_stride;
   io.instances = instances + item * (size_t)n_instances * 32;
   io.n_instances = n_instances;
   io.out_scalars = out_scalars;
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(PCOOP_THREADS) k_tape_coop(size_t n_items, con
   RegFile rf{regs, n_items, item};
   TapeIo io;
   io.proof = proofs + item * proof_stride;
-  io.proof_len = proof_lens ? proof_lens[item] : (u32)proof_stride;
+  io.proof_len = proof_lens ? min(proof_lens[item], (u32)proof_stride) : (u32)proof_stride;
   io.instances = instances + item * (size_t)n_instances * 32;
   io.n_instances = n_instances;
   io.out_scalars = out_scalars;

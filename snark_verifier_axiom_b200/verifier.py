@@ -272,23 +272,46 @@ class PlonkVerifier:
 
     # ---- packing ------------------------------------------------------------------------------
     def pack(self, snarks: Sequence[Snark]):
-        """-> (instances u8[n, n_inst*32], n_inst, proofs u8[n, stride], lens u32[n])"""
+        """-> (instances u8[n, n_inst*32], n_inst, proofs u8[n, stride], lens u32[n]).
+        `self.bad_shape` lists the snarks whose instance COLUMNS do not match `protocol.num_instance` (proof.rs:66-69: the
+        comparison is per column; the ABI carries the flat count): they are packed with zero instances and reported as
+        InvalidInstances by `_apply_shape`."""
         n = len(snarks)
-        n_inst = len([x for col in snarks[0].instances for x in col]) if n else 0
+        L, c = self.ctx._L, self.ctx._c
+        self.bad_shape = []
+        n_inst = self.info["n_instances"]
+        shapes = {}
+        for i, s in enumerate(snarks):
+            key = tuple(len(col) for col in s.instances)
+            if key not in shapes:
+                lens_ = np.array(key, np.uint32)
+                shapes[key] = L.svk_plonk_instance_shape_ok(c, self.pid, len(key), _ptr(lens_) if len(key) else None) == 1
+            if not shapes[key]:
+                self.bad_shape.append(i)
+        if n and len(self.bad_shape) == n:
+            # nothing in the batch has the protocol's shape: keep the caller's flat count so that libsvk reports the error itself
+            n_inst = len([x for col in snarks[0].instances for x in col])
         stride = max([len(s.proof) for s in snarks] + [32])
         stride = (stride + 31) // 32 * 32
         proofs = np.zeros((n, stride), np.uint8)
         lens = np.zeros(n, np.uint32)
         inst = np.zeros((n, max(n_inst, 1) * 32), np.uint8)
+        bad = set(self.bad_shape)
         for i, s in enumerate(snarks):
             flat = [x for col in s.instances for x in col]
-            if len(flat) != n_inst:
-                raise ValueError("all snarks of a batch must have the same instance shape")
             proofs[i, : len(s.proof)] = np.frombuffer(s.proof, np.uint8)
             lens[i] = len(s.proof)
-            if flat:
+            if flat and i not in bad:
+                inst[i, : n_inst * 32] = np.frombuffer(b"".join(_fe(x) for x in flat), np.uint8)
+            elif flat and len(bad) == n and len(flat) == n_inst:
                 inst[i, : n_inst * 32] = np.frombuffer(b"".join(_fe(x) for x in flat), np.uint8)
         return inst, n_inst, proofs, lens
+
+    def _apply_shape(self, st):
+        """InvalidInstances precedes everything else `read_proof` reports (proof.rs:66-69 is its first check)."""
+        for i in getattr(self, "bad_shape", []):
+            st[i] = 1
+        return st
 
     # ---- PlonkSuccinctVerifier::{read_proof, verify} ------------------------------------------------
     def succinct_verify(self, snarks: Sequence[Snark]):
@@ -305,6 +328,7 @@ class PlonkVerifier:
         L, c = self.ctx._L, self.ctx._c
         self.ctx._check(L.svk_plonk_succinct_verify_batch(c, self.pid, n, _ptr(inst), n_inst, _ptr(proofs), proofs.shape[1], _ptr(lens),
                                                           _ptr(acc), _ptr(ch), _ptr(st)))
+        st = self._apply_shape(st)
         if apk == 1:
             accs = [KzgAccumulator.from_bytes(acc[i, 0].tobytes()) if st[i] == 0 else None for i in range(n)]
         else:
@@ -322,6 +346,9 @@ class PlonkVerifier:
         L, c = self.ctx._L, self.ctx._c
         self.ctx._check(L.svk_plonk_verify_batch(c, self.pid, n, _ptr(inst), n_inst, _ptr(proofs), proofs.shape[1], _ptr(lens), group_size,
                                                  1 if locate_failures else 0, _ptr(st), _ptr(folded), _ptr(ok)))
+        st = self._apply_shape(st)
+        if self.bad_shape:
+            ok[0] = 0
         return BatchResult(bool(ok[0]), st, KzgAccumulator.from_bytes(folded.tobytes()) if ok[0] else None)
 
     def verify_batches(self, batches: Sequence[Sequence[Snark]], group_size: int = 0, locate_failures: bool = True) -> List[BatchResult]:
@@ -337,10 +364,11 @@ class PlonkVerifier:
         L, c = self.ctx._L, self.ctx._c
         self.ctx._check(L.svk_plonk_verify_multi(c, self.pid, nb, bs, _ptr(inst), n_inst, _ptr(proofs), proofs.shape[1], _ptr(lens), group_size,
                                                  1 if locate_failures else 0, _ptr(st), _ptr(rec)))
+        st = self._apply_shape(st)
         out = []
         for b in range(nb):
             r = rec[b * 256 : (b + 1) * 256]
-            ok = bool(r[165])
+            ok = bool(r[165]) and not any(b * bs <= i < (b + 1) * bs for i in self.bad_shape)
             out.append(BatchResult(ok, st[b * bs : (b + 1) * bs], KzgAccumulator.from_bytes(r[:128].tobytes()) if ok else None))
         return out
 

@@ -14,9 +14,10 @@ def _bench():
 
 def test_batches_per_launch_times_exactly_k_steps():
     f = _bench().choose_batches_per_launch
-    assert f(1024, 16) == 32 and f(512, 16) == 32 and f(256, 16) == 16 and f(128, 16) == 8
-    assert f(10, 16) == 1 and f(20, 16) == 1 and f(100, 16) == 6 - 1  # 100 // 16 = 6, largest divisor of 100 below it is 5
+    assert f(1024, 16) == 32 and f(512, 16) == 32 and f(256, 16) == 32 and f(64, 16) == 32
+    assert f(20, 16) == 10 and f(10, 16) == 5 and f(100, 16) == 25  # the driver's --steps 20: two launches of ten batches
+    assert f(7, 16) == 7 and f(1, 16) == 1 and f(37, 16) == 1       # a prime K <= 32 is one launch, beyond that single batches
     assert f(64, 16, requested=4) == 4
     for k in range(1, 300):
         b = f(k, 16)
-        assert 1 <= b <= 32 and k % b == 0 and (k // b >= min(k, 16) or b == 1)
+        assert 1 <= b <= 32 and k % b == 0

@@ -93,3 +93,36 @@ def test_succinct_verify_matches_oracle(env, scheme, mos):
     inst2 = np.zeros(n * 2 * 32, dtype=np.uint8)
     rc = L.svk_plonk_succinct_verify_batch(c, pid, n, ptr(inst2), 2, ptr(buf), stride, None, ptr(out_acc), ptr(out_ch), ptr(out_st))
     assert rc == 0 and (out_st == 1).all()
+
+
+@pytest.mark.gpu
+def test_instance_columns_and_length_clamp(env):
+    """proof.rs:66-69 compares the instance COLUMNS with protocol.num_instance ([[x], []] has the right flat count and the wrong
+    shape); a proof length beyond the row stride is clamped instead of reading the neighbour's bytes."""
+    from snark_verifier_axiom_b200 import verifier as V
+    from snark_verifier_axiom_b200.standard_plonk import standard_plonk_protocol
+
+    L, c, S, _kid, _blob = env
+    ctx = V.Context(0)
+    dk = V.KzgDecidingKey.new(S.dk.svk.g, S.dk.g2, S.dk.s_g2)
+    pv = V.PlonkVerifier(ctx, dk, standard_plonk_protocol(8, S.preprocessed, S.transcript_initial_state), V.SHPLONK)
+    insts, proofs = forge.forge_batch(S, "bdfg21", 3, seed0=4242)
+    good = [V.Snark(i, p) for i, p in zip(insts, proofs)]
+    bad = V.Snark([insts[1][0], []], proofs[1])  # two columns [1, 0] against num_instance [1]
+    accs, _, st = pv.succinct_verify([good[0], bad, good[2]])
+    assert list(st) == [0, 1, 0] and accs[1] is None
+    assert api.status_of(api.verify, S.dk, S.protocol, [insts[1][0], []], proofs[1], "bdfg21") == 1
+    res = pv.verify([good[0], bad, good[2]], group_size=0)
+    assert not res.ok and list(res.status) == [0, 1, 0]
+    assert pv.verify(good, group_size=0).ok
+    # lengths beyond the stride: identical to the stride itself
+    inst, n_inst, buf, lens = pv.pack(good)
+    out_acc, out_st = np.zeros((2, 3, 128), np.uint8), np.zeros((2, 3), np.int32)
+    n_ch = pv.info["n_challenges"]
+    ch = np.zeros((3, n_ch, 32), np.uint8)
+    for k, ln in enumerate((lens, lens + 1000)):
+        rc = L.svk_plonk_succinct_verify_batch(ctx._c, pv.pid, 3, ptr(inst), n_inst, ptr(buf), buf.shape[1], ptr(ln.astype(np.uint32)), ptr(out_acc[k]),
+                                               ptr(ch), ptr(out_st[k]))
+        assert rc == 0
+    assert (out_st == 0).all() and (out_acc[0] == out_acc[1]).all()
+    ctx.close()
