@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="proofs in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tiled", action="store_true", help="tile the 64 fixture proofs instead of forging distinct ones")
+    ap.add_argument("--no-preflight", action="store_true", help="N > 1: skip the parity pre-flight (256 proofs per rank, one corrupted on the last rank; "
+                    "cross-rank accumulator, root challenge and verdict against the oracle's fold of folds -- the checker, never the timed path)")
     ap.add_argument("--stream-priorities", type=int, default=0, help="1: slot i gets a higher stream priority than slot i + 1, so that concurrent launches finish "
                     "one after the other and the narrow tail of one (fold levels, pairing) runs beside the wide kernels of the next")
     return ap.parse_args()
@@ -116,14 +118,14 @@ def make_workload(batch, scheme="bdfg21"):
     return g, reps, np
 
 
-def cpu_baseline(g, sample, group_size, scheme="bdfg21"):
+def cpu_baseline(g, sample, group_size, scheme="bdfg21", optimised=True):
     """The reference's algorithm on the host: oracle/c (`kind: port`, C restatement: naive per-pair scalar
     multiplication, per-element Fermat inversion, serial sponge, one pairing) when built, else the Python
     oracle.  Bounded sample of the same workload; returns the cpu_baseline object."""
     try:
         from oracle.c import cref
 
-        return cref.bench_baseline(g, sample, group_size, scheme)
+        return cref.bench_baseline(g, sample, group_size, scheme, optimised=optimised)
     except Exception as e:  # C oracle not built: Python oracle, tiny sample
         note = f"python oracle (C oracle unavailable: {type(e).__name__})"
     from oracle import api, forge
@@ -145,28 +147,32 @@ def cpu_baseline(g, sample, group_size, scheme="bdfg21"):
 
 # ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
+    """The reference's CPU algorithm (oracle/c, all host threads) on the same workload.  A step of this arm is a BOUNDED SAMPLE of
+    the 4096-proof batch (`config.step_sample_proofs` proofs: succinct verify each, fold, one pairing), so that K + W steps end
+    within minutes; `ms_per_step` is the measured wall time of such a step, `value` = proofs per second over the timed steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     g, reps, np = make_workload(64, args.scheme)
-    vals = []
-    base = None
+    sample = args.cpu_sample or 512
+    times, base = [], None
     t_begin = time.time()
     for it in range(args.warmup + args.steps):
-        base = cpu_baseline(g, args.cpu_sample, args.group_size, args.scheme)
-        vals.append(base["value"])
-        # each step is a bounded sample of the workload; keep the whole run within a few minutes whatever K is
+        base = cpu_baseline(g, sample, args.group_size, args.scheme, optimised=False)
+        times.append(base.get("sample_seconds") or sample / base["value"])  # the timed region of the step: replay + fold + pairing
+        # keep the whole run within a few minutes whatever K is
         if it >= args.warmup and time.time() - t_begin > 150:
             break
-    timed = len(vals) - min(args.warmup, len(vals) - 1)
-    vals = vals[-timed:]
-    v = sum(vals) / len(vals)
+    timed = times[min(args.warmup, len(times) - 1):]
+    step_s = sum(timed) / len(timed)
+    v = sample / step_s
     base["value"] = v
     out = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "steps_sampled": timed, "warmup": args.warmup,
-        "ms_per_step": 1e3 * args.batch / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (254-bit Fq/Fr)",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(timed), "steps_requested": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (254-bit Fq/Fr)",
         "data": "synthetic: trapdoor-forged StandardPlonk k=8 SHPLONK proofs (tests/golden), CPU sample",
-        "config": {"workload": WORKLOAD.format(scheme="shplonk" if args.scheme == "bdfg21" else "gwc"), "batch_per_gpu": args.batch, "fold_group_size": args.group_size},
+        "config": {"workload": WORKLOAD.format(scheme="shplonk" if args.scheme == "bdfg21" else "gwc"), "batch_per_gpu": args.batch, "fold_group_size": args.group_size,
+                   "step_sample_proofs": sample, "note": "a step of this arm is a bounded sample of the 4096-proof batch; proofs/s does not depend on the sample size"},
         "cpu_baseline": base, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out))
@@ -264,6 +270,20 @@ def run_ours(args):
             sl.sv.verify_dev(di, n_inst, dp, n, n_batches=B)
         else:
             sl.sv.verify_dev(di.view(n, -1)[: nb * nb1], n_inst, dp[: nb * nb1], nb * nb1, n_batches=nb)
+
+    # ---- N > 1 pre-flight: the sharded job against the oracle's fold of folds (tests/workers/multi_rank_worker.py), untimed
+    preflight = None
+    if world > 1 and not args.no_preflight and args.scheme == "bdfg21":
+        import importlib.util
+
+        spec = importlib.util.spec_from_file_location("multi_rank_worker", os.path.join(ROOT, "tests", "workers", "multi_rank_worker.py"))
+        mrw = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mrw)
+        preflight = mrw.check(256, args.group_size, slots[0].sv, pv, g, dev)
+        if rank == 0:
+            assert preflight["valid"] == {"accumulator_equal": True, "root_challenge_equal": True, "verdict": True, "oracle_verdict": True}, preflight
+            assert preflight["corrupted"]["accumulator_equal"] and not preflight["corrupted"]["verdict"] and not preflight["corrupted"]["oracle_verdict"], preflight
+        barrier()
 
     # ---- warm-up (every slot)
     for k in range(max(args.warmup, 1) * S):
@@ -464,8 +484,9 @@ def run_ours(args):
             "scaled by proofs per launch)", "traffic_source": traffic_src,
             "peak_source": "measured in this run: svk_bench_modmul_peak (independent Montgomery-mul chains, 8 warps/SMSP on all SMs)",
             "kernel_ms_per_launch": ms_launch, "batches_per_launch": B, "kernels_one_launch_in_flight": kernels,
-            "whole_step_frac": (total_work_exec * world / (ms_per_step * 1e-3)) / peak,
-            "whole_step_frac_canonical": (total_work * world / (ms_per_step * 1e-3)) / peak,
+            # per GPU: every rank does `total_work` per step (weak scaling) against its own multiply peak
+            "whole_step_frac": (total_work_exec / (ms_per_step * 1e-3)) / peak,
+            "whole_step_frac_canonical": (total_work / (ms_per_step * 1e-3)) / peak,
             "hbm_gbs_algorithmic": (h2d + d2h) / (ms_per_step * 1e-3) / 1e9,
             "hbm_gbs_dominant_kernel": (traffic / (ms_launch * 1e-3) / 1e9) if traffic else None,
             "hbm_peak_gbs": hbm_peak, "hbm_frac_dominant_kernel": (traffic / (ms_launch * 1e-3) / 1e9 / hbm_peak) if (traffic and hbm_peak) else None,
@@ -480,7 +501,8 @@ def run_ours(args):
                        "fold": "flat (reference aggregation.rs:235-245)" if args.group_size in (0, 1) else f"tree, groups of {args.group_size}",
                        "batches_in_flight": S * B, "single_batch_latency_ms": latency_ms,
                        "l2": f"inputs rotate over {n_copies} distinct device copies ({n_copies * (h2d >> 20)} MiB > L2)",
-                       "parallelism": f"proof-sharded x{world}, NCCL all_gather of {world} folded accumulators" if world > 1 else "single GPU"},
+                       "parallelism": f"proof-sharded x{world}, NCCL all_gather of {world} folded accumulators" if world > 1 else "single GPU",
+                       "preflight_vs_oracle": preflight},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "roofline": roofline, "cpu_baseline": base,

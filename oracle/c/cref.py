@@ -170,7 +170,7 @@ def decide(acc, dk):
 _BENCH_CACHE = {}
 
 
-def bench_baseline(g, sample, group_size, scheme="bdfg21"):
+def bench_baseline(g, sample, group_size, scheme="bdfg21", optimised=True):
     """cpu_baseline object for bench.py: the reference's algorithm on the host cores.  `g` = the product's
     loaded golden fixture (snarks); sample = proofs per measurement (0 = 512)."""
     if "setup" not in _BENCH_CACHE:
@@ -191,10 +191,12 @@ def bench_baseline(g, sample, group_size, scheme="bdfg21"):
         buf[i, : len(p)] = np.frombuffer(p, dtype=np.uint8)
         lens[i] = len(p)
     inp = _limbs64([x for inst in insts for col in inst for x in col]).reshape(n, -1)
-    n1 = min(n, 64)
-    t0 = time.perf_counter()
-    replay_packed(tr, buf[:n1], lens[:n1], inp[:n1], 1)
-    single = n1 / (time.perf_counter() - t0)
+    if "single" not in _BENCH_CACHE:  # one thread, measured once per process
+        n1 = min(n, 64)
+        t0 = time.perf_counter()
+        replay_packed(tr, buf[:n1], lens[:n1], inp[:n1], 1)
+        _BENCH_CACHE["single"] = n1 / (time.perf_counter() - t0)
+    single = _BENCH_CACHE["single"]
     t0 = time.perf_counter()
     accs, st = replay_packed(tr, buf, lens, inp, cores)
     assert (st == 0).all()
@@ -202,6 +204,12 @@ def bench_baseline(g, sample, group_size, scheme="bdfg21"):
     ok = decide(acc, S.dk)
     dt = time.perf_counter() - t0
     assert ok and fst == 0
+    base = {"value": n / dt, "unit": "proofs/s", "cores": cores, "kind": "port", "single_thread_value": single, "sample_proofs": n, "sample_seconds": dt,
+            "sample": f"{n} proofs: succinct verify ({cores} threads, one proof per thread) + KzgAs fold (groups of {group_size}) + one pairing; "
+                      f"C restatement of the reference algorithm (oracle/c): {tr.n_scalar_muls} naive 256-step scalar muls, "
+                      f"{tr.counts['inv']} Fermat inversions, serial Poseidon sponge per proof"}
+    if not optimised:
+        return base
     # the same sample through the windowed scalar multiplication (value-identical accumulators): what a tuned CPU verifier gains
     lib().cref_set_optimised(1)
     try:
@@ -213,9 +221,7 @@ def bench_baseline(g, sample, group_size, scheme="bdfg21"):
     finally:
         lib().cref_set_optimised(0)
     assert ok2 and bytes(acc2) == bytes(acc) and (np.asarray(accs2) == np.asarray(accs)).all()
-    return {"value": n / dt, "unit": "proofs/s", "cores": cores, "kind": "port",
-            "single_thread_value": single, "optimised_value": n / dt2,
-            "optimised_note": "same sample with 4-bit fixed-window scalar multiplications instead of the reference's 256-step double-and-add-always (oracle/c cref_set_optimised); identical accumulators",
-            "sample": f"{n} proofs: succinct verify ({cores} threads, one proof per thread) + KzgAs fold (groups of {group_size}) + one pairing; "
-                      f"C restatement of the reference algorithm (oracle/c): {tr.n_scalar_muls} naive 256-step scalar muls, "
-                      f"{tr.counts['inv']} Fermat inversions, serial Poseidon sponge per proof"}
+    base["optimised_value"] = n / dt2
+    base["optimised_note"] = ("same sample with 4-bit fixed-window scalar multiplications instead of the reference's 256-step double-and-add-always "
+                              "(oracle/c cref_set_optimised); identical accumulators")
+    return base
