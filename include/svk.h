@@ -51,7 +51,8 @@ enum { SVK_TRANSCRIPT_POSEIDON = 0, SVK_TRANSCRIPT_EVM = 1 };
 enum { SVK_MOS_BDFG21 = 0 /* SHPLONK, pcs/kzg/multiopen/bdfg21.rs */, SVK_MOS_GWC19 = 1 /* pcs/kzg/multiopen/gwc19.rs */ };
 
 /* ---- context ------------------------------------------------------------------------------- */
-/* One context = one device + one stream.  Calls on one context are serialised by the caller.
+/* One context = one device + one stream.  Calls on one context are serialised by an internal (recursive) mutex; different
+ * contexts may be used concurrently from different threads.
  * Fails (returns < 0, *out = NULL) when no sm_100 GPU is present: there is no CPU fallback. */
 int svk_create(int device, svk_ctx** out);
 void svk_destroy(svk_ctx* ctx);
@@ -66,6 +67,11 @@ uint64_t svk_launch_count(svk_ctx* ctx);
  * a JSON object {"kernel": {"count": launches, "ms": total device ms}}; reading it resets it. */
 int svk_profile_enable(svk_ctx* ctx, int on);
 int svk_profile_report(svk_ctx* ctx, char* buf, size_t buf_len);
+
+/* Test hook: out[i] = `Poseidon::new().update(inputs[i]).squeeze()` (util/hash/poseidon.rs:448-467; T = 3, RATE = 2, R_F = 8,
+ * R_P = 57, the SDK transcript's hash: snark-verifier-sdk/src/halo2.rs:52-56), n sponges of n_inputs elements each.
+ * schedule 0 = one thread per sponge (poseidon.cuh), 1 = the warp-cooperative permutation (poseidon_coop.cuh). */
+int svk_poseidon_squeeze(svk_ctx* ctx, size_t n, const svk_fe* inputs, uint32_t n_inputs, int schedule, svk_fe* out);
 
 /* ---- KzgDecidingKey -------------------------------------------------------------------------
  * `KzgDecidingKey::new(g1, g2, s_g2)` (pcs/kzg/decider.rs:15-24) + halo2curves `G2Prepared::from`
@@ -149,6 +155,11 @@ int svk_kzg_as_fold(svk_ctx* ctx, size_t n, const svk_acc* accs, size_t group_si
                     int32_t* out_status);
 int svk_kzg_as_fold_dev(svk_ctx* ctx, size_t n, const void* d_accs, size_t group_size, void* d_out_acc, void* d_out_r,
                         void* d_out_status);
+/* `KzgAs::{read_proof, verify}` with a zero-knowledge accumulation proof (`KzgAsVerifyingKey::zk()`, pcs/kzg/accumulation.rs:45-49,
+ * 124-133): `as_proof` holds the two compressed blind points the prover wrote; they are absorbed after the n instances and
+ * folded in as the last pair with r^n.  Short stream / bad encoding / identity => SVK_TRANSCRIPT | sub << 8 in *out_status. */
+int svk_kzg_as_fold_zk(svk_ctx* ctx, size_t n, const svk_acc* accs, const uint8_t* as_proof, size_t as_proof_len, svk_acc* out_acc,
+                       svk_fe* out_r, int32_t* out_status);
 
 /* ---- PlonkVerifier::verify (verifier/plonk.rs:98-135) over a batch: succinct-verify every proof,
  * fold the accumulators (above), decide the folded accumulator with ONE pairing.
@@ -207,6 +218,23 @@ int svk_plonk_verify_multi(svk_ctx* ctx, int proto, size_t n_batches, size_t bat
 int svk_plonk_verify_multi_dev(svk_ctx* ctx, int proto, size_t n_batches, size_t batch_size, const void* d_instances, uint32_t n_instances,
                                const void* d_proofs, size_t proof_stride, const void* d_proof_lens, size_t group_size, void* d_out_accs,
                                void* d_out_status, void* d_out_records);
+/* ---- proof-sharded jobs over the GPUs of one box (one context per rank + an ncclComm_t) ---------------------------
+ * NCCL is bound at run time (dlopen of libnccl.so.2); single-GPU users never touch it.
+ *   svk_nccl_unique_id   rank 0 creates the 128-byte ncclUniqueId and hands it to the other ranks (any side channel)
+ *   svk_nccl_init        collective: creates this context's communicator (ncclCommInitRank)
+ *   svk_nccl_attach      uses a communicator the host already owns (ncclComm_t as void*); not destroyed with the context
+ *   svk_plonk_verify_sharded_dev
+ *       this rank's shard (n_batches x batch_size proofs): succinct verify + per-batch fold locally (no pairing), ncclAllGather of
+ *       the n_batches 256-byte records on the context stream, fold of batch b over the ranks (`KzgAs`, flat, rank order:
+ *       pcs/kzg/accumulation.rs:29-62) and ONE pairing per batch (decider.rs:60-68).  d_gather: world x n_batches x 256 B
+ *       ([rank][batch]), d_final_records: n_batches x 256 B { global accumulator ; r ; fold_status ; decide_ok ; ok } with
+ *       ok = every rank's local ok && fold_status == 0 && decide_ok.  Everything is enqueued on the stream, nothing blocks. */
+int svk_nccl_unique_id(uint8_t* out_id_128);
+int svk_nccl_init(svk_ctx* ctx, int world, int rank, const uint8_t* id_128);
+int svk_nccl_attach(svk_ctx* ctx, void* nccl_comm, int world, int rank);
+int svk_plonk_verify_sharded_dev(svk_ctx* ctx, int proto, size_t n_batches, size_t batch_size, const void* d_instances, uint32_t n_instances,
+                                 const void* d_proofs, size_t proof_stride, const void* d_proof_lens, size_t group_size, void* d_out_accs,
+                                 void* d_out_status, void* d_out_records, void* d_gather, void* d_final_records);
 /* The same without the pairing -- the per-rank half of a proof-sharded job: the per-batch folded accumulators of all
  * ranks are all-gathered, folded once more (svk_kzg_as_fold_multi_dev) and decided ONCE (svk_kzg_decide_records_dev).  Records
  * carry decide_ok = 1 ("not decided here"). */

@@ -39,6 +39,7 @@ def _load():
     lib.svk_plonk_succinct_verify_batch.argtypes = [vp, i32, sz, vp, ctypes.c_uint32, vp, sz, vp, vp, vp, vp]
     lib.svk_plonk_succinct_verify_batch_dev.argtypes = [vp, i32, sz, vp, ctypes.c_uint32, vp, sz, vp, vp, vp, vp]
     lib.svk_kzg_as_fold.argtypes = [vp, sz, vp, sz, vp, vp, vp]
+    lib.svk_kzg_as_fold_zk.argtypes = [vp, sz, vp, vp, sz, vp, vp, vp]
     lib.svk_kzg_as_fold_dev.argtypes = [vp, sz, vp, sz, vp, vp, vp]
     lib.svk_plonk_verify_batch.argtypes = [vp, i32, sz, vp, ctypes.c_uint32, vp, sz, vp, sz, i32, vp, vp, vp]
     lib.svk_plonk_verify_batch_dev.argtypes = [vp, i32, sz, vp, ctypes.c_uint32, vp, sz, vp, sz, vp, vp, vp]
@@ -57,6 +58,11 @@ def _load():
     lib.svk_msm_curve_dev.argtypes = [vp, i32, sz, vp, vp, vp, vp]
     lib.svk_ipa_decide_batch.argtypes = [vp, i32, ctypes.c_uint32, vp, sz, vp, vp, vp, vp]
     lib.svk_ipa_decide_batch_dev.argtypes = [vp, i32, ctypes.c_uint32, vp, sz, vp, vp, vp, vp]
+    lib.svk_poseidon_squeeze.argtypes = [vp, sz, vp, ctypes.c_uint32, i32, vp]
+    lib.svk_nccl_unique_id.argtypes = [vp]
+    lib.svk_nccl_init.argtypes = [vp, i32, i32, vp]
+    lib.svk_nccl_attach.argtypes = [vp, vp, i32, i32]
+    lib.svk_plonk_verify_sharded_dev.argtypes = [vp, i32, sz, sz, vp, ctypes.c_uint32, vp, sz, vp, sz, vp, vp, vp, vp, vp]
     lib.svk_bench_modmul_peak.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     return lib
 

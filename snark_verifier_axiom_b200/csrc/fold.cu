@@ -397,6 +397,34 @@ int svk_fold_launch_seg(svk_ctx* ctx, size_t n_seg, size_t n, const uint8_t* d_a
   return 0;
 }
 
+// `KzgAsProof::read` with zk = true (pcs/kzg/accumulation.rs:124-133): the two blind points are read from the accumulation proof
+// as compressed G1 (32 B each) and absorbed like the instances; `verify` appends them as the LAST pair (:45-49).  So the zk fold
+// of n accumulators IS the flat fold of n + 1 pairs, the last one decoded here.  An undecodable point is written as a
+// non-canonical coordinate, an identity as (0, 0): the fold reports them as POINT_INVALID / POINT_IDENTITY (transcript/halo2.rs:214-260).
+__global__ void k_blind_points(const uint8_t* blind, uint8_t* slot) {
+  int t = threadIdx.x;
+  if (t >= 2) return;
+  G1Affine pt;
+  u32 xc[8], yc[8];
+  int rc = g1_decompress(blind + 32 * t, pt, xc, yc);
+  uint4* o = reinterpret_cast<uint4*>(slot + 64 * t);
+  if (rc == 0) {
+    o[0] = make_uint4(xc[0], xc[1], xc[2], xc[3]);
+    o[1] = make_uint4(xc[4], xc[5], xc[6], xc[7]);
+    o[2] = make_uint4(yc[0], yc[1], yc[2], yc[3]);
+    o[3] = make_uint4(yc[4], yc[5], yc[6], yc[7]);
+  } else {
+    u32 v = rc == 2 ? 0u : 0xffffffffu;
+    for (int i = 0; i < 4; i++) o[i] = make_uint4(v, v, v, v);
+  }
+}
+
+int svk_blind_points_launch(svk_ctx* ctx, const uint8_t* d_blind, uint8_t* d_slot) {
+  SVK_LAUNCH(ctx, "k_blind_points", k_blind_points<<<1, 32, 0, ctx->stream>>>(d_blind, d_slot));
+  SVK_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
 // single batch, separate output pointers (svk_kzg_as_fold_dev): staged through a 256-byte record
 int svk_fold_launch(svk_ctx* ctx, size_t n, const uint8_t* d_accs, size_t group_size, uint8_t* d_out_acc, u32* d_out_r, int32_t* d_status) {
   uint8_t* rec;

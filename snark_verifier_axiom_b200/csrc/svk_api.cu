@@ -15,6 +15,8 @@ int svk_msm_curve_launch(svk_ctx* ctx, int curve, size_t n, const uint8_t* d_sca
 int svk_ipa_decide_launch(svk_ctx* ctx, int curve, u32 k, const uint8_t* d_g, size_t n, const uint8_t* d_xi, const uint8_t* d_u,
                           int32_t* d_out_status, int32_t* d_invalid);
 int svk_fixed_tables_launch(svk_ctx* ctx, ProtocolDevice* pd);
+int svk_blind_points_launch(svk_ctx* ctx, const uint8_t* d_blind, uint8_t* d_slot);
+int svk_poseidon_squeeze_launch(svk_ctx* ctx, size_t n, u32 n_in, const uint8_t* d_inputs, uint8_t* d_out, int coop, int* d_bad);
 int svk_fold_launch(svk_ctx* ctx, size_t n, const uint8_t* d_accs, size_t group_size, uint8_t* d_out_acc, u32* d_out_r, int32_t* d_status);
 int svk_fold_launch_seg(svk_ctx* ctx, size_t n_seg, size_t n, const uint8_t* d_accs, size_t group_size, uint8_t* d_out, size_t out_stride);
 int svk_decide_launch_strided(svk_ctx* ctx, int dk, size_t n, const void* d_accs, size_t acc_stride, void* d_ok, size_t ok_stride);
@@ -23,6 +25,7 @@ int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const
                                const uint8_t* d_proofs, size_t proof_stride, const u32* d_proof_lens, uint8_t* d_out_acc,
                                u32* d_out_challenges, int32_t* d_out_status);
 
+extern "C" void svk_nccl_release(svk_ctx* ctx);
 static thread_local std::string g_create_err;
 
 // Fixed-base window tables are identical for every context that compiles the same verifying key on the same
@@ -152,6 +155,7 @@ void svk_destroy(svk_ctx* ctx) {
   cudaFree(ctx->d_pairing_consts);
   cudaFree(ctx->d_poseidon);
   for (auto* p : ctx->protocols) protocol_release(p);
+  svk_nccl_release(ctx);
   if (ctx->done) cudaEventDestroy(ctx->done);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -160,6 +164,7 @@ void svk_destroy(svk_ctx* ctx) {
 const char* svk_last_error(svk_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
 int svk_set_stream(svk_ctx* ctx, void* s) {
+  SVK_LOCK(ctx);
   if (ctx->own_stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
   ctx->stream = (cudaStream_t)s;
   return 0;
@@ -170,12 +175,14 @@ int svk_sync(svk_ctx* ctx) { SVK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); 
 uint64_t svk_launch_count(svk_ctx* ctx) { return ctx->launches; }
 
 int svk_profile_enable(svk_ctx* ctx, int on) {
+  SVK_LOCK(ctx);
   ctx->profile = on != 0;
   return 0;
 }
 
 // JSON: {"kernel": {"count": c, "ms": total}, ...}; resets the statistics.  Returns bytes written or -1.
 int svk_profile_report(svk_ctx* ctx, char* buf, size_t buf_len) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (auto& pe : ctx->pending) {
     float ms = 0;
@@ -212,6 +219,7 @@ static bool load_fq_canon(Fq& out, const svk_fe& fe) {
 }
 
 int svk_dk_load(svk_ctx* ctx, const svk_deciding_key* dk) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   G2Affine g2, sg2;
   bool ok = load_fq_canon(g2.x.c0, dk->g2.x_c0) && load_fq_canon(g2.x.c1, dk->g2.x_c1) && load_fq_canon(g2.y.c0, dk->g2.y_c0) &&
@@ -246,11 +254,13 @@ int svk_dk_load(svk_ctx* ctx, const svk_deciding_key* dk) {
 }
 
 int svk_kzg_decide_batch_dev(svk_ctx* ctx, int dk, size_t n, const void* d_accs, void* d_out_ok) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   return svk_decide_launch(ctx, dk, n, d_accs, d_out_ok);
 }
 
 int svk_kzg_decide_batch(svk_ctx* ctx, int dk, size_t n, const svk_acc* accs, uint8_t* out_ok) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   if (n == 0) return 0;
   void *d_in, *d_out;
@@ -265,12 +275,14 @@ int svk_kzg_decide_batch(svk_ctx* ctx, int dk, size_t n, const svk_acc* accs, ui
 // ---- PlonkProtocol ingestion --------------------------------------------------------------------
 int svk_protocol_compile_ex(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos, int transcript_kind, int dk);
 int svk_protocol_compile(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos, int dk) {
+  SVK_LOCK(ctx);
   return svk_protocol_compile_ex(ctx, blob, len, mos, SVK_TRANSCRIPT_POSEIDON, dk);
 }
 
 static int protocol_upload(svk_ctx* ctx, svk_host::CompiledProtocol& cp, int mos, int transcript_kind, int dk, int force_bits = 0);
 
 int svk_protocol_compile_ex(svk_ctx* ctx, const uint8_t* blob, size_t len, int mos, int transcript_kind, int dk) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   if (dk < 0 || dk >= (int)ctx->dks.size()) return svk_fail(ctx, "bad deciding-key id %d", dk);
   svk_host::CompiledProtocol cp;
@@ -284,6 +296,7 @@ int svk_protocol_compile_ex(svk_ctx* ctx, const uint8_t* blob, size_t len, int m
 
 int svk_protocol_compile_bincode(svk_ctx* ctx, const uint8_t* bytes, size_t len, int fe_encoding, int mos, int transcript_kind, int dk,
                                  size_t* consumed, int* fe_used) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   if (dk < 0 || dk >= (int)ctx->dks.size()) return svk_fail(ctx, "bad deciding-key id %d", dk);
   svk_host::CompiledProtocol cp;
@@ -433,6 +446,7 @@ retry_small:
 }
 
 int svk_protocol_info(svk_ctx* ctx, int proto, uint32_t* out) {
+  SVK_LOCK(ctx);
   if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
   ProtocolDevice* pd = ctx->protocols[proto];
   out[0] = pd->proof_len; out[1] = pd->n_instances; out[2] = pd->n_challenges; out[3] = pd->n_regs; out[4] = pd->n_ops;
@@ -446,6 +460,7 @@ int svk_protocol_info(svk_ctx* ctx, int proto, uint32_t* out) {
 // every column.  The batch entry points carry the FLAT count only; a host binding calls this once per snark shape and
 // reports SVK_INVALID_INSTANCES for a snark whose columns differ ([[a], [b, c]] against num_instance [2, 1] has the right total).
 int svk_plonk_instance_shape_ok(svk_ctx* ctx, int proto, uint32_t n_cols, const uint32_t* col_lens) {
+  SVK_LOCK(ctx);
   if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
   const std::vector<u32>& want = ctx->protocols[proto]->num_instance;
   if (want.size() != n_cols) return 0;
@@ -456,6 +471,7 @@ int svk_plonk_instance_shape_ok(svk_ctx* ctx, int proto, uint32_t n_cols, const 
 
 // ---- the unevaluated `Msm` of the final accumulator (util/msm.rs:20-24): terms and per-proof scalars -------------
 int svk_protocol_msm_terms(svk_ctx* ctx, int proto, int side, int32_t* out, size_t max_terms) {
+  SVK_LOCK(ctx);
   if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
   const std::vector<MsmTermDev>& t = side ? ctx->protocols[proto]->h_rhs : ctx->protocols[proto]->h_lhs;
   if (t.size() > max_terms) return svk_fail(ctx, "terms buffer too small");
@@ -466,6 +482,7 @@ int svk_protocol_msm_terms(svk_ctx* ctx, int proto, int side, int32_t* out, size
 int svk_plonk_msm_scalars_batch(svk_ctx* ctx, int proto, size_t n, const svk_fe* instances, uint32_t n_instances, const uint8_t* proofs,
                                 size_t proof_stride, const uint32_t* proof_lens, svk_fe* out_scalars, svk_fe* out_challenges,
                                 int32_t* out_status) {
+  SVK_LOCK(ctx);
   if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
   ProtocolDevice* pd = ctx->protocols[proto];
   std::vector<svk_acc> accs(n * pd->accs_per_proof());
@@ -484,6 +501,7 @@ int svk_plonk_msm_scalars_batch(svk_ctx* ctx, int proto, size_t n, const svk_fe*
 int svk_plonk_succinct_verify_batch_dev(svk_ctx* ctx, int proto, size_t n, const void* d_instances, uint32_t n_instances,
                                         const void* d_proofs, size_t proof_stride, const void* d_proof_lens, void* d_out_acc,
                                         void* d_out_challenges, void* d_out_status) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
   return svk_succinct_verify_launch(ctx, ctx->protocols[proto], n, (const uint8_t*)d_instances, n_instances, (const uint8_t*)d_proofs,
@@ -494,6 +512,7 @@ int svk_plonk_succinct_verify_batch_dev(svk_ctx* ctx, int proto, size_t n, const
 int svk_plonk_succinct_verify_batch(svk_ctx* ctx, int proto, size_t n, const svk_fe* instances, uint32_t n_instances,
                                     const uint8_t* proofs, size_t proof_stride, const uint32_t* proof_lens, svk_acc* out_acc,
                                     svk_fe* out_challenges, int32_t* out_status) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
   if (n == 0) return 0;
@@ -521,11 +540,13 @@ int svk_plonk_succinct_verify_batch(svk_ctx* ctx, int proto, size_t n, const svk
 
 // ---- KzgAs fold ------------------------------------------------------------------------------------
 int svk_kzg_as_fold_dev(svk_ctx* ctx, size_t n, const void* d_accs, size_t group_size, void* d_out_acc, void* d_out_r, void* d_out_status) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   return svk_fold_launch(ctx, n, (const uint8_t*)d_accs, group_size, (uint8_t*)d_out_acc, (u32*)d_out_r, (int32_t*)d_out_status);
 }
 
 int svk_kzg_as_fold(svk_ctx* ctx, size_t n, const svk_acc* accs, size_t group_size, svk_acc* out_acc, svk_fe* out_r, int32_t* out_status) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   if (n == 0) return svk_fail(ctx, "fold of zero accumulators");
   uint8_t* d;
@@ -541,12 +562,43 @@ int svk_kzg_as_fold(svk_ctx* ctx, size_t n, const svk_acc* accs, size_t group_si
   return 0;
 }
 
+// `KzgAs::{read_proof, verify}` with `KzgAsVerifyingKey(true)` (zk; pcs/kzg/accumulation.rs:29-62, 113-136): `as_proof` = the 64 bytes
+// the prover wrote (two compressed blind points).  out_acc = sum_i r^i acc_i + r^n blind, r squeezed after absorbing all n + 1 pairs.
+int svk_kzg_as_fold_zk(svk_ctx* ctx, size_t n, const svk_acc* accs, const uint8_t* as_proof, size_t as_proof_len, svk_acc* out_acc, svk_fe* out_r,
+                       int32_t* out_status) {
+  SVK_LOCK(ctx);
+  SVK_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (n == 0) return svk_fail(ctx, "fold of zero accumulators");
+  if (as_proof_len < 64) {  // `read_ec_point` hits the end of the stream
+    *out_status = SVK_TRANSCRIPT | (SVK_T_EOF << 8);
+    memset(out_acc, 0, sizeof *out_acc);
+    if (out_r) memset(out_r, 0, sizeof *out_r);
+    return 0;
+  }
+  uint8_t* d;
+  if (svk_scratch(ctx, 0, (n + 1) * 128 + 512, (void**)&d)) return -1;
+  uint8_t* d_out = d + (n + 1) * 128;  // 128 acc + 32 r + 4 status
+  uint8_t* d_blind = d_out + 256;
+  cudaStream_t s = ctx->stream;
+  SVK_CUDA(ctx, cudaMemcpyAsync(d, accs, n * 128, cudaMemcpyHostToDevice, s));
+  SVK_CUDA(ctx, cudaMemcpyAsync(d_blind, as_proof, 64, cudaMemcpyHostToDevice, s));
+  if (svk_blind_points_launch(ctx, d_blind, d + n * 128)) return -1;
+  if (svk_fold_launch(ctx, n + 1, d, 0, d_out, (u32*)(d_out + 128), (int32_t*)(d_out + 160))) return -1;
+  SVK_CUDA(ctx, cudaMemcpyAsync(out_acc, d_out, 128, cudaMemcpyDeviceToHost, s));
+  if (out_r) SVK_CUDA(ctx, cudaMemcpyAsync(out_r, d_out + 128, 32, cudaMemcpyDeviceToHost, s));
+  SVK_CUDA(ctx, cudaMemcpyAsync(out_status, d_out + 160, 4, cudaMemcpyDeviceToHost, s));
+  if (svk_wait(ctx)) return -1;
+  return 0;
+}
+
 int svk_kzg_as_fold_multi_dev(svk_ctx* ctx, size_t n_seg, size_t n, const void* d_accs, size_t group_size, void* d_out_records) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   return svk_fold_launch_seg(ctx, n_seg, n, (const uint8_t*)d_accs, group_size, (uint8_t*)d_out_records, 256);
 }
 
 int svk_kzg_decide_records_dev(svk_ctx* ctx, int dk, size_t n_records, void* d_records) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   return svk_decide_launch_strided(ctx, dk, n_records, d_records, 256, (uint8_t*)d_records + 164, 256);
 }
@@ -557,6 +609,7 @@ int svk_kzg_decide_records_dev(svk_ctx* ctx, int dk, size_t n_records, void* d_r
 int svk_plonk_verify_multi_dev(svk_ctx* ctx, int proto, size_t n_batches, size_t batch_size, const void* d_instances, uint32_t n_instances,
                                const void* d_proofs, size_t proof_stride, const void* d_proof_lens, size_t group_size, void* d_out_accs,
                                void* d_out_status, void* d_out_records) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
   if (n_batches == 0 || batch_size == 0) return svk_fail(ctx, "empty batch");
@@ -578,6 +631,7 @@ int svk_plonk_verify_multi_dev(svk_ctx* ctx, int proto, size_t n_batches, size_t
 int svk_plonk_fold_multi_dev(svk_ctx* ctx, int proto, size_t n_batches, size_t batch_size, const void* d_instances, uint32_t n_instances,
                              const void* d_proofs, size_t proof_stride, const void* d_proof_lens, size_t group_size, void* d_out_accs,
                              void* d_out_status, void* d_out_records) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
   if (n_batches == 0 || batch_size == 0) return svk_fail(ctx, "empty batch");
@@ -595,6 +649,7 @@ int svk_plonk_fold_multi_dev(svk_ctx* ctx, int proto, size_t n_batches, size_t b
 int svk_plonk_verify_batch_dev(svk_ctx* ctx, int proto, size_t n, const void* d_instances, uint32_t n_instances, const void* d_proofs,
                                size_t proof_stride, const void* d_proof_lens, size_t group_size, void* d_out_accs, void* d_out_status,
                                void* d_out_folded) {
+  SVK_LOCK(ctx);
   return svk_plonk_verify_multi_dev(ctx, proto, 1, n, d_instances, n_instances, d_proofs, proof_stride, d_proof_lens, group_size, d_out_accs,
                                     d_out_status, d_out_folded);
 }
@@ -602,6 +657,7 @@ int svk_plonk_verify_batch_dev(svk_ctx* ctx, int proto, size_t n, const void* d_
 int svk_plonk_verify_multi(svk_ctx* ctx, int proto, size_t n_batches, size_t batch_size, const svk_fe* instances, uint32_t n_instances,
                            const uint8_t* proofs, size_t proof_stride, const uint32_t* proof_lens, size_t group_size, int locate_failures,
                            int32_t* out_status, uint8_t* out_records) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   if (proto < 0 || proto >= (int)ctx->protocols.size()) return svk_fail(ctx, "bad protocol id %d", proto);
   if (n_batches == 0 || batch_size == 0) return svk_fail(ctx, "empty batch");
@@ -645,6 +701,7 @@ int svk_plonk_verify_multi(svk_ctx* ctx, int proto, size_t n_batches, size_t bat
 int svk_plonk_verify_batch(svk_ctx* ctx, int proto, size_t n, const svk_fe* instances, uint32_t n_instances, const uint8_t* proofs,
                            size_t proof_stride, const uint32_t* proof_lens, size_t group_size, int locate_failures, int32_t* out_status,
                            svk_acc* out_folded, uint8_t* out_ok) {
+  SVK_LOCK(ctx);
   uint8_t rec[256];
   if (svk_plonk_verify_multi(ctx, proto, 1, n, instances, n_instances, proofs, proof_stride, proof_lens, group_size, locate_failures,
                              out_status, rec))
@@ -656,11 +713,13 @@ int svk_plonk_verify_batch(svk_ctx* ctx, int proto, size_t n, const svk_fe* inst
 
 // ---- MSM ------------------------------------------------------------------------------------------
 int svk_msm_g1_dev(svk_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out, void* d_status) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   return svk_msm_launch(ctx, n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, (int*)d_status);
 }
 
 int svk_msm_g1(svk_ctx* ctx, size_t n, const svk_fe* scalars, const svk_g1* points, svk_g1* out, int32_t* out_status) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   uint8_t* d;
@@ -679,11 +738,13 @@ int svk_msm_g1(svk_ctx* ctx, size_t n, const svk_fe* scalars, const svk_g1* poin
 
 // ---- MSM over a chosen curve + the IPA decider -------------------------------------------
 int svk_msm_curve_dev(svk_ctx* ctx, int curve, size_t n, const void* d_scalars, const void* d_points, void* d_out, void* d_status) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   return svk_msm_curve_launch(ctx, curve, n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out, (int*)d_status);
 }
 
 int svk_msm_curve(svk_ctx* ctx, int curve, size_t n, const svk_fe* scalars, const svk_g1* points, svk_g1* out, int32_t* out_status) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   uint8_t* d;
@@ -702,6 +763,7 @@ int svk_msm_curve(svk_ctx* ctx, int curve, size_t n, const svk_fe* scalars, cons
 
 int svk_ipa_decide_batch_dev(svk_ctx* ctx, int curve, uint32_t k, const void* d_g, size_t n, const void* d_xi, const void* d_u,
                              void* d_out_status, void* d_invalid) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   return svk_ipa_decide_launch(ctx, curve, k, (const uint8_t*)d_g, n, (const uint8_t*)d_xi, (const uint8_t*)d_u, (int32_t*)d_out_status,
                                (int32_t*)d_invalid);
@@ -709,6 +771,7 @@ int svk_ipa_decide_batch_dev(svk_ctx* ctx, int curve, uint32_t k, const void* d_
 
 int svk_ipa_decide_batch(svk_ctx* ctx, int curve, uint32_t k, const svk_g1* g, size_t n, const svk_fe* xi, const svk_g1* u,
                          int32_t* out_status, int32_t* out_invalid) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   if (k == 0 || k > 26) return svk_fail(ctx, "ipa_decide: k out of range");
   if (n == 0) return svk_fail(ctx, "ipa_decide: no accumulators (the reference asserts !accumulators.is_empty(), pcs/ipa/decider.rs:61)");
@@ -732,11 +795,13 @@ int svk_ipa_decide_batch(svk_ctx* ctx, int curve, uint32_t k, const svk_g1* g, s
 }
 
 int svk_g1_mul_batch_dev(svk_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, size_t n_points, void* d_out) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   return svk_g1_mul_batch_launch(ctx, n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, n_points, (uint8_t*)d_out);
 }
 
 int svk_g1_mul_batch(svk_ctx* ctx, size_t n, const svk_fe* scalars, const svk_g1* points, size_t n_points, svk_g1* out) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   if (n == 0) return 0;
   cudaStream_t s = ctx->stream;
@@ -751,7 +816,31 @@ int svk_g1_mul_batch(svk_ctx* ctx, size_t n, const svk_fe* scalars, const svk_g1
   return 0;
 }
 
+// Test hook: out[i] = Poseidon::new().update(inputs[i][0..n_inputs]).squeeze()  (util/hash/poseidon.rs:448-467,
+// T = 3, RATE = 2, R_F = 8, R_P = 57).  schedule 0: one thread per sponge, 1: the warp-cooperative permutation.
+// Returns -1 when an input is not a canonical Fr.
+int svk_poseidon_squeeze(svk_ctx* ctx, size_t n, const svk_fe* inputs, uint32_t n_inputs, int schedule, svk_fe* out) {
+  SVK_LOCK(ctx);
+  SVK_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (n == 0) return 0;
+  cudaStream_t s = ctx->stream;
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+  size_t in_bytes = n * (size_t)n_inputs * 32, off_out = al(in_bytes + 32), off_bad = off_out + al(n * 32);
+  uint8_t* d;
+  if (svk_scratch(ctx, 0, off_bad + 256, (void**)&d)) return -1;
+  if (in_bytes) SVK_CUDA(ctx, cudaMemcpyAsync(d, inputs, in_bytes, cudaMemcpyHostToDevice, s));
+  SVK_CUDA(ctx, cudaMemsetAsync(d + off_bad, 0, 4, s));
+  if (svk_poseidon_squeeze_launch(ctx, n, n_inputs, d, d + off_out, schedule != 0, (int*)(d + off_bad))) return -1;
+  int bad = 0;
+  SVK_CUDA(ctx, cudaMemcpyAsync(out, d + off_out, n * 32, cudaMemcpyDeviceToHost, s));
+  SVK_CUDA(ctx, cudaMemcpyAsync(&bad, d + off_bad, 4, cudaMemcpyDeviceToHost, s));
+  if (svk_wait(ctx)) return -1;
+  if (bad) return svk_fail(ctx, "poseidon_squeeze: input is not a canonical Fr");
+  return 0;
+}
+
 int svk_bench_modmul_peak(svk_ctx* ctx, int iters, double* out_modmul_per_s, double* out_ms) {
+  SVK_LOCK(ctx);
   SVK_CUDA(ctx, cudaSetDevice(ctx->device));
   return svk_modmul_peak_launch(ctx, iters, out_modmul_per_s, out_ms);
 }

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -53,7 +54,14 @@ struct svk_ctx {
   void* scratch[24] = {nullptr};
   size_t scratch_sz[24] = {0};
   std::vector<struct ProtocolDevice*> protocols;
+  // calls on one context are serialised inside the library (entry points nest: verify_batch -> verify_multi -> ...)
+  std::recursive_mutex mu;
+  // proof-sharded jobs (csrc/sharded.cu): this rank's NCCL communicator (ncclComm_t), created by svk_nccl_init or attached
+  void* nccl_comm = nullptr;
+  bool nccl_owned = false;
+  int world = 1, rank = 0;
 };
+#define SVK_LOCK(ctx) std::lock_guard<std::recursive_mutex> svk_lock_((ctx)->mu)
 
 inline int svk_fail(svk_ctx* ctx, const char* fmt, ...) {
   char buf[512];

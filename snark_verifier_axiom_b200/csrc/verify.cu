@@ -403,6 +403,45 @@ int svk_fixed_tables_launch(svk_ctx* ctx, ProtocolDevice* pd) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// `Poseidon::update(inputs); squeeze()` on a fresh sponge (util/hash/poseidon.rs:448-467), one sponge per thread: the buffer is
+// absorbed RATE elements at a time; a length that is a multiple of RATE gets one more permutation of the empty chunk.
+// mode 1: the same sponges through the warp-cooperative schedule (poseidon_coop.cuh), 32 per block of three warps.
+__global__ void __launch_bounds__(PCOOP_THREADS) k_poseidon_squeeze(size_t n, u32 n_in, const uint8_t* inputs, const PoseidonConsts* pk, uint8_t* out,
+                                                                    int coop, int* bad) {
+  __shared__ PoseidonCoopShared sh;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp) {
+    if (coop) pc_helper(&sh, *pk, warp, lane);
+    return;
+  }
+  size_t i = (size_t)blockIdx.x * 32 + lane;
+  if (i >= n) i = n - 1;
+  PoseidonState st;
+  PoseidonCoopMain cm;
+  cm.sh = &sh;
+  cm.lane = lane;
+  if (coop) pcm_init(cm, *pk); else poseidon_init(st, *pk);
+  u32 n_perm = n_in / 2 + 1;  // chunks of RATE = 2, plus the empty chunk when the length is exact
+  for (u32 q = 0; q < n_perm; q++) {
+    Fr a = Fr::zero(), b = Fr::zero();
+    int k = (int)min(2u, n_in - min(n_in, 2 * q));
+    if (k >= 1) { fe_load_le(a.v, inputs + (i * n_in + 2 * q) * 32); if (!Fr::is_canonical(a.v)) *bad = 1; a = a.to_mont(); }
+    if (k >= 2) { fe_load_le(b.v, inputs + (i * n_in + 2 * q + 1) * 32); if (!Fr::is_canonical(b.v)) *bad = 1; b = b.to_mont(); }
+    if (coop) pcm_permute(cm, *pk, k, a, b); else poseidon_permute(st, *pk, k, a, b);
+  }
+  if (coop) pcm_exit(cm);
+  Fr r = (coop ? cm.s1 : st.s[1]).from_mont();
+  fe_store_le(out + i * 32, r.v);
+}
+
+int svk_poseidon_squeeze_launch(svk_ctx* ctx, size_t n, u32 n_in, const uint8_t* d_inputs, uint8_t* d_out, int coop, int* d_bad) {
+  SVK_LAUNCH(ctx, "k_poseidon_squeeze",
+             k_poseidon_squeeze<<<(unsigned)((n + 31) / 32), PCOOP_THREADS, 0, ctx->stream>>>(n, n_in, d_inputs, ctx->d_poseidon, d_out, coop, d_bad));
+  SVK_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // mode: 0 normal, 1 InvalidInstances for all, 2 InvalidProtocol unless the read failed
 __global__ void k_status(size_t n_items, const u32* err, int mode, int32_t* status) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -34,6 +34,7 @@ class LibsvkOps:
         self.pv = pv
         self.ctx = pv.ctx
         self.L, self.c = pv.ctx._L, pv.ctx._c
+        self.sharded = False  # True once nccl_init gave the context its own communicator
 
     @staticmethod
     def _p(t):
@@ -48,6 +49,29 @@ class LibsvkOps:
                                                self._p(d_records))
         self.ctx._check(rc)
 
+    def nccl_init(self, world, rank, group=None):
+        """Creates this context's own NCCL communicator (C ABI: svk_nccl_unique_id / svk_nccl_init).  The 128-byte unique id travels
+        from rank 0 through `torch.distributed` (any side channel would do); collective over the job."""
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (ctypes.c_uint8 * 128)()
+            if self.L.svk_nccl_unique_id(buf) != 0:
+                raise RuntimeError("libsvk: NCCL is not available")
+            idt = torch.tensor(list(buf), dtype=torch.uint8)
+        dev = torch.device("cuda", self.ctx.device)
+        idd = idt.to(dev)
+        dist.broadcast(idd, src=0, group=group)
+        ids = bytes(idd.cpu().tolist())
+        self.ctx._check(self.L.svk_nccl_init(self.c, world, rank, ids))
+        self.sharded = True
+
+    def sharded_verify(self, d_inst, n_inst, d_proofs, n_batches, batch, group_size, d_accs, d_status, d_records, d_gather, d_final, d_lens=None):
+        """The whole sharded call inside the library: local verify + fold, ncclAllGather, cross-rank fold, one pairing per batch."""
+        rc = self.L.svk_plonk_verify_sharded_dev(self.c, self.pv.pid, n_batches, batch, self._p(d_inst), n_inst, self._p(d_proofs), d_proofs.shape[1],
+                                                 self._p(d_lens) if d_lens is not None else None, group_size, self._p(d_accs), self._p(d_status),
+                                                 self._p(d_records), self._p(d_gather), self._p(d_final))
+        self.ctx._check(rc)
+
     def fold(self, n_seg, n, d_accs, d_records):
         """flat KzgAs fold of n_seg x n accumulators -> one record per segment"""
         self.ctx._check(self.L.svk_kzg_as_fold_multi_dev(self.c, n_seg, n, self._p(d_accs), 0, self._p(d_records)))
@@ -60,7 +84,7 @@ class ShardedBatchVerifier:
     """Verifies `n_batches` batches per call on this rank's shard; with world > 1 the per-rank batch accumulators are
     all-gathered and batch b of every rank is folded into the global accumulator of batch b, then decided."""
 
-    def __init__(self, pv, world, rank, device, stream=None, group_size=8, ops=None, max_batches=1):
+    def __init__(self, pv, world, rank, device, stream=None, group_size=8, ops=None, max_batches=1, own_nccl=True):
         self.world, self.rank, self.device, self.stream = world, rank, device, stream
         self.group_size = group_size
         self.ops = ops or LibsvkOps(pv)
@@ -77,6 +101,10 @@ class ShardedBatchVerifier:
             self.d_final = torch.zeros(max_batches * RECORD, **kw)
         self.d_accs = self.d_status = None
         self.nb = 1
+        # world > 1 on GPUs: the context gets its own communicator and the exchange runs inside libsvk; `own_nccl=False` (or an
+        # injected `ops`, as in the gloo CPU test) keeps the torch.distributed all_gather below
+        if own_nccl and world > 1 and device.type == "cuda" and isinstance(self.ops, LibsvkOps):
+            self.ops.nccl_init(world, rank)
 
     def _ensure(self, n):
         if self._n < n:
@@ -105,6 +133,11 @@ class ShardedBatchVerifier:
         self._ensure(n)
         self.nb = n_batches
         nb = n_batches
+        if self.world > 1 and getattr(self.ops, "sharded", False):
+            # everything behind the C ABI (csrc/sharded.cu): ncclAllGather on the context stream, cross-rank fold, one pairing
+            self.ops.sharded_verify(d_inst, n_inst, d_proofs, nb, n // nb, self.group_size, self.d_accs, self.d_status, self.d_records,
+                                    self.d_gather, self.d_final, d_lens)
+            return
         self.ops.local_verify(d_inst, n_inst, d_proofs, nb, n // nb, self.group_size, self.d_accs, self.d_status, self.d_records, d_lens,
                               decide=self.world == 1)
         if self.world > 1:
@@ -131,7 +164,10 @@ class ShardedBatchVerifier:
         out = []
         for b in range(nb):
             fold_status = int(np.frombuffer(f[b, OFF_FOLD_STATUS : OFF_FOLD_STATUS + 4].tobytes(), np.int32)[0])
-            out.append(bool(g[:, b, OFF_OK].all() and fold_status == 0 and f[b, OFF_DECIDE_OK]))
+            ok = bool(g[:, b, OFF_OK].all() and fold_status == 0 and f[b, OFF_DECIDE_OK])
+            if getattr(self.ops, "sharded", False):
+                assert ok == bool(f[b, OFF_OK]), "k_sharded_verdict disagrees with the host-side combination"
+            out.append(ok)
         return out
 
     def final_accumulator(self, b=0) -> bytes:

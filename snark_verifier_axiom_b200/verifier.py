@@ -189,6 +189,20 @@ class KzgAs:
             raise Error(st[0])
         return KzgAccumulator.from_bytes(out.tobytes()), int.from_bytes(r.tobytes(), "little")
 
+    def verify_zk(self, accumulators: Sequence[KzgAccumulator], as_proof: bytes):
+        """`KzgAs::read_proof` + `verify` with `KzgAsVerifyingKey(true)` (accumulation.rs:29-62, 113-136): `as_proof` = the two
+        compressed blind points written by a zero-knowledge `create_proof` -> (KzgAccumulator, r)."""
+        n = len(accumulators)
+        assert n > 0, "assert!(!instances.is_empty())"
+        buf = np.frombuffer(b"".join(a.to_bytes() for a in accumulators), dtype=np.uint8).copy()
+        pf = np.frombuffer(bytes(as_proof) or b"\0", dtype=np.uint8).copy()
+        out, r, st = np.zeros(128, np.uint8), np.zeros(32, np.uint8), np.zeros(1, np.int32)
+        L, c = self.ctx._L, self.ctx._c
+        self.ctx._check(L.svk_kzg_as_fold_zk(c, n, _ptr(buf), _ptr(pf), len(as_proof), _ptr(out), _ptr(r), _ptr(st)))
+        if st[0] != 0:
+            raise Error(st[0])
+        return KzgAccumulator.from_bytes(out.tobytes()), int.from_bytes(r.tobytes(), "little")
+
     def decide_batch(self, accumulators: Sequence[KzgAccumulator]) -> List[bool]:
         n = len(accumulators)
         if n == 0:

@@ -156,3 +156,41 @@ def test_sharded_fold_then_single_pairing(env):
         got = V.KzgAccumulator.from_bytes(f[:128].tobytes())
         assert (got.lhs, got.rhs) == final
         assert bool(f[OFF_DECIDE_OK]) == api.decide(S.dk, final) == (not corrupt)
+
+
+def test_kzg_as_zero_knowledge_accumulation_proof(env):
+    """`KzgAs` with `KzgAsVerifyingKey(true)` (pcs/kzg/accumulation.rs:29-62, 113-136): the verifier reads two blind points from the
+    accumulation proof, absorbs them after the instances and folds them in with r^n.  The blind pair is what a zk
+    `create_proof` writes (:153-170): (s * G, G) for a random s -- itself a valid accumulator."""
+    import random
+
+    from oracle import bn254
+    from oracle.kzg import KzgAccumulator as OAcc, KzgAsBdfg21
+    from oracle.loader import NativeLoader
+    from oracle.transcript import PoseidonTranscript, VerifyError
+
+    V, S, ctx, AS, pv = env
+    rng = random.Random(77)
+    n = 5
+    insts, proofs = forge.forge_batch(S, "bdfg21", n, seed0=3100)
+    accs, _, st = pv[0].succinct_verify([V.Snark(i, p) for i, p in zip(insts, proofs)])
+    assert (st == 0).all()
+    k = rng.randrange(1, bn254.R)
+    blind = (bn254.g1_mul(bn254.G1_GEN, k * S.s % bn254.R), bn254.g1_mul(bn254.G1_GEN, k))
+    as_proof = bn254.g1_to_bytes(blind[0]) + bn254.g1_to_bytes(blind[1])
+    loader = NativeLoader()
+    o_accs = [OAcc(loader.ec_point_load_const(a.lhs), loader.ec_point_load_const(a.rhs)) for a in accs]
+    tr = PoseidonTranscript(loader, as_proof)
+    proof = KzgAsBdfg21.as_read_proof(True, o_accs, tr)
+    want = KzgAsBdfg21.as_verify(True, o_accs, proof)
+    got, r = AS.verify_zk(accs, as_proof)
+    assert (got.lhs, got.rhs) == (want.lhs.pt, want.rhs.pt) and r == proof[1].v
+    assert AS.decide_batch([got]) == [True] and api.decide(S.dk, (got.lhs, got.rhs))
+    # error paths of `read_ec_point` (transcript/halo2.rs:235-260): short stream, bad encoding, identity
+    bad_x = next(x for x in range(1, 100) if not bn254.g1_from_bytes(x.to_bytes(32, "little"))[0])
+    for bad_proof, sub in ((as_proof[:40], 1), (bad_x.to_bytes(32, "little") + as_proof[32:], 3), (bytes(32) + as_proof[32:], 4)):
+        with pytest.raises(V.Error) as e:
+            AS.verify_zk(accs, bad_proof)
+        assert e.value.status & 0xFF == 4 and (sub is None or e.value.status >> 8 == sub)
+        with pytest.raises(VerifyError):
+            KzgAsBdfg21.as_read_proof(True, o_accs, PoseidonTranscript(loader, bad_proof))

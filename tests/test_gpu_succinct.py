@@ -126,3 +126,33 @@ def test_instance_columns_and_length_clamp(env):
         assert rc == 0
     assert (out_st == 0).all() and (out_acc[0] == out_acc[1]).all()
     ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("schedule", [0, 1])
+def test_poseidon_squeeze_hook(env, schedule):
+    """svk_poseidon_squeeze (SURVEY 8b test hook): `Poseidon::update(..); squeeze()` (util/hash/poseidon.rs:448-467) for sponges of
+    0..7 inputs, through the one-thread permutation and through the warp-cooperative one (poseidon_coop.cuh)."""
+    import random
+
+    from oracle import poseidon
+    from oracle.bn254 import R
+
+    L, c, S, _kid, _blob = env
+    rng = random.Random(11 + schedule)
+    for n_in in range(0, 8):
+        n = 70  # more than two blocks of 32, with a ragged tail
+        vals = [[rng.randrange(R) for _ in range(n_in)] for _ in range(n)]
+        if n_in:
+            vals[0] = [0] * n_in
+            vals[1] = [R - 1] * n_in
+        buf = np_u8(b"".join(int(x).to_bytes(32, "little") for row in vals for x in row) or b"\0")
+        out = np.zeros((n, 32), np.uint8)
+        assert L.svk_poseidon_squeeze(c, n, ptr(buf), n_in, schedule, ptr(out)) == 0, L.svk_last_error(c)
+        for i in range(n):
+            h = poseidon.Poseidon()
+            h.update(vals[i])
+            assert int.from_bytes(out[i].tobytes(), "little") == h.squeeze(), (n_in, i)
+    bad = np_u8((R).to_bytes(32, "little"))
+    out = np.zeros((1, 32), np.uint8)
+    assert L.svk_poseidon_squeeze(c, 1, ptr(bad), 1, schedule, ptr(out)) != 0
