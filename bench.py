@@ -216,6 +216,11 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: native libraries (NCCL's version banner on the first communicator) write to fd 1
+    # directly, so fd 1 is pointed at stderr for the run and the line goes to a duplicate of the original stdout
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
         # NCCL writes its debug output (the version banner under NCCL_DEBUG=VERSION, NVLS / ring info under INFO) to stdout by
         # default; stdout is reserved for the one JSON line
@@ -507,7 +512,8 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "roofline": roofline, "cpu_baseline": base,
         }
-        print(json.dumps(out))
+        json_out.write(json.dumps(out) + "\n")
+        json_out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

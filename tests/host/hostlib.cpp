@@ -360,3 +360,13 @@ extern "C" int host_straus(int nt, const u32* pts_xy, const u32* ks, u32* out_xy
   store_aff(out_xy, a1);
   return 0;
 }
+
+// ---- GLV decomposition (csrc/glv.cuh): out = { |k1| (4 limbs), neg1, |k2| (4 limbs), neg2 }, returns 1 when both < 2^128
+#include "../../snark_verifier_axiom_b200/csrc/glv.cuh"
+extern "C" int host_glv_decompose(const u32* k, u32* out) {
+  u32 k1[4], k2[4], n1, n2;
+  bool ok = glv_decompose(k, k1, n1, k2, n2);
+  memcpy(out, k1, 16); out[4] = n1; memcpy(out + 5, k2, 16); out[9] = n2;
+  return ok ? 1 : 0;
+}
+extern "C" void host_glv_beta(u32* out) { Fq b = glv_beta_mont().from_mont(); memcpy(out, b.v, 32); }

@@ -85,3 +85,19 @@ def test_msm_rejects_bad_input(ctx):
         V.multi_scalar_multiplication(c, [1, 2], [bn254.G1_GEN, (1, 3)])
     with pytest.raises(ValueError):
         V.multi_scalar_multiplication(c, [R, 2], [bn254.G1_GEN, bn254.G1_GEN])
+
+
+def test_msm_skewed_scalars_heavy_buckets(ctx):
+    """Every point in ONE bucket (all scalars 1), in a handful (scalars < 8), and one huge repeated scalar: the heavy-bucket path
+    (k_msm_heavy: chunks of a bucket summed by warps, msm.cu) gives the naive sum (native.rs:61-71)."""
+    V, c = ctx
+    n = 1 << 16
+    rng = random.Random(21)
+    dl = [rng.randrange(1, R) for _ in range(n)]
+    pts = V.g1_mul_batch(c, dl, [bn254.G1_GEN])
+    assert V.multi_scalar_multiplication(c, [1] * n, pts) == g_mul(sum(dl) % R)
+    small = [rng.randrange(8) for _ in range(n)]
+    assert V.multi_scalar_multiplication(c, small, pts) == g_mul(sum(x * d for x, d in zip(small, dl)) % R)
+    k = rng.randrange(R)
+    assert V.multi_scalar_multiplication(c, [k] * n, pts) == g_mul(k * sum(dl) % R)
+    assert V.multi_scalar_multiplication(c, [R - 1] * 5000, pts[:5000]) == g_mul((R - 1) * sum(dl[:5000]) % R)

@@ -193,6 +193,29 @@ def test_coop_pairing_matches_tower(lib):
         assert rd12(ml) == mlo and rd12(gt) == bn254.final_exponentiation(mlo) and rc == exp
 
 
+def test_glv_decompose(lib):
+    """csrc/glv.cuh: k = (+-k1) + (+-k2) lambda (mod r) with |k1|, |k2| < 2^128, and phi(P) = (beta x, y) = lambda P
+    (constants derived by tools/glv_constants.py)."""
+    lam = 4407920970296243842393367215006156084916469457145843978461
+    out = (ctypes.c_uint32 * 8)()
+    lib.host_glv_beta(out)
+    beta = rd(out, 1)[0]
+    G = bn254.G1_GEN
+    assert pow(lam, 3, R) == 1 and pow(beta, 3, bn254.P) == 1 and bn254.g1_mul(G, lam) == (beta * G[0] % bn254.P, G[1])
+    rng = random.Random(9)
+    ks = [0, 1, 2, R - 1, R - 2, lam, R - lam, (lam * lam) % R, 1 << 127, 1 << 128, (1 << 253) + 1, R // 2, R // 3] + [rng.randrange(R) for _ in range(3000)]
+    buf = (ctypes.c_uint32 * 10)()
+    worst = 0
+    for k in ks:
+        assert lib.host_glv_decompose(limbs([k]), buf) == 1
+        v = list(buf)
+        k1 = sum(v[i] << (32 * i) for i in range(4)) * (-1 if v[4] else 1)
+        k2 = sum(v[5 + i] << (32 * i) for i in range(4)) * (-1 if v[9] else 1)
+        assert (k1 + k2 * lam - k) % R == 0, k
+        worst = max(worst, abs(k1), abs(k2))
+    assert worst < 1 << 128
+
+
 def test_poseidon_kat_and_random(lib):
     out = (ctypes.c_uint32 * 24)()
     assert lib.host_poseidon_permute(limbs([0, 1, 2]), 2, limbs([0]), limbs([0]), out) == 0
