@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--tiled", action="store_true", help="tile the 64 fixture proofs instead of forging distinct ones")
     ap.add_argument("--no-preflight", action="store_true", help="N > 1: skip the parity pre-flight (256 proofs per rank, one corrupted on the last rank; "
                     "cross-rank accumulator, root challenge and verdict against the oracle's fold of folds -- the checker, never the timed path)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configs (MSM 2^20 / 2^24, decide 2^16, single-proof latency)")
     ap.add_argument("--stream-priorities", type=int, default=0, help="1: slot i gets a higher stream priority than slot i + 1, so that concurrent launches finish "
                     "one after the other and the narrow tail of one (fold levels, pairing) runs beside the wide kernels of the next")
     return ap.parse_args()
@@ -206,6 +207,138 @@ def choose_batches_per_launch(steps, slots, requested=0, cap=32):
     if b == 1 and steps <= cap:
         b = steps
     return b
+
+
+def run_secondary(torch, dist, V, ctx, stream, dev, g, peak, world, rank, args):
+    """The other BASELINE configs, bounded (< 60 s): config 3 G1 MSM at 2^20 and 2^24 points per GPU (uniform scalars; powers of r at
+    2^20; sharded over the ranks with an all-gather of the partial sums when N > 1), config 5 batched decide of 2^16 accumulators,
+    config 1 single-proof latency.  Each entry carries its own roofline (canonical work: 176 M per MSM point = 16 windows x 11 M,
+    20 k M per decide) and a CPU figure from the C restatement of the reference (oracle/c), timed on a bounded sample.
+    Collective when N > 1 (every rank calls it); returns the dict on rank 0."""
+    import numpy as np
+
+    from snark_verifier_axiom_b200.distributed import LibsvkMsmOps, msm_sharded
+
+    L, c = ctx._L, ctx._c
+    p = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    R_ = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    out = {}
+
+    def rand_scalars(n, seed):
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed)
+        t = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=gen)
+        t[:, 31] &= 0x1F  # < 2^253 < r
+        return t.contiguous()
+
+    def timed(fn, iters):
+        fn()
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(iters):
+            fn()
+        e1.record(stream)
+        stream.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    try:
+        from oracle.c import cref
+    except Exception:
+        cref = None
+    cores = os.cpu_count() or 1
+
+    # ---- config 3
+    nmax = 1 << 24
+    with torch.cuda.stream(stream):
+        dl = rand_scalars(nmax, 42 + rank)
+        gen1 = torch.zeros(64, dtype=torch.uint8, device=dev)
+        gen1[0], gen1[32] = 1, 2
+        pts = torch.empty(nmax * 64, dtype=torch.uint8, device=dev)
+    ctx._check(L.svk_g1_mul_batch_dev(c, nmax, p(dl), p(gen1), 1, p(pts)))
+    stream.synchronize()
+    ops = LibsvkMsmOps(ctx)
+    msm_cpu = None
+    if rank == 0 and cref is not None:
+        ns = 1 << 16
+        h_sc, h_pt = rand_scalars(ns, 7).cpu().numpy(), pts[: ns * 64].cpu().numpy().reshape(ns, 64)
+        t0 = time.perf_counter()
+        cref.msm(h_sc, h_pt, cores)
+        msm_cpu = {"value": ns / (time.perf_counter() - t0), "unit": "points/s", "cores": cores, "kind": "port",
+                   "sample": f"2^16 points: util::msm::multi_scalar_multiplication (util/msm.rs:238-317: window ln n + 2, chunked over {cores} threads), C restatement (oracle/c cref_msm)"}
+    msm = []
+    for lg, kind in ((20, "uniform"), (20, "powers_of_r"), (24, "uniform")):
+        n = 1 << lg
+        if kind == "uniform":
+            with torch.cuda.stream(stream):
+                sc = rand_scalars(n, 1000 + lg + rank)
+        else:  # the fold's distribution: 1, r, r^2, ...  (accumulation.rs:51-59)
+            r, cur, rows = 0x1F2E3D4C5B6A79880123456789ABCDEF0FEDCBA9876543211122334455667788 % R_, 1, bytearray()
+            for _ in range(n):
+                rows += cur.to_bytes(32, "little")
+                cur = cur * r % R_
+            sc = torch.frombuffer(rows, dtype=torch.uint8).to(dev).view(n, 32)
+        ms = timed(lambda: msm_sharded(ops, world, dev, sc.view(-1), pts, n, stream), 3 if lg <= 22 else 2)
+        pps = n * world / (ms * 1e-3)
+        msm.append({"log_n_per_gpu": lg, "scalars": kind, "n_gpus": world, "ms": ms, "value": pps, "unit": "points/s",
+                    "roofline": {"bound": "imad", "achieved": n * 176 / (ms * 1e-3) / 1e9, "peak": peak / 1e9, "unit": "Gmodmul/s canonical (176 M per point)",
+                                 "frac": n * 176 / (ms * 1e-3) / peak, "hbm_gbs_algorithmic": n * 96 / (ms * 1e-3) / 1e9},
+                    "cpu_baseline": msm_cpu})
+        del sc
+    del pts, dl
+    out["config3_msm_g1"] = msm
+
+    if rank == 0:
+        # ---- config 5: 2^16 accumulators, 1/64 corrupted (valid ones: the oracle-checked golden accumulators, tiled)
+        kid = ctx.load_deciding_key(g["dk"])
+        pv = V.PlonkVerifier(ctx, g["dk"], g["protocol"], V.SHPLONK)
+        accs, _, stt = pv.succinct_verify(g["schemes"]["bdfg21"]["snarks"])
+        assert (stt == 0).all()
+        n = 1 << 16
+        base = np.frombuffer(b"".join(a.to_bytes() for a in accs), dtype=np.uint8).reshape(len(accs), 128)
+        host = np.tile(base, (n // len(accs) + 1, 1))[:n].copy()
+        bad = np.arange(0, n, 64)
+        host[bad, 64:128] = host[(bad + 1) % n, 64:128]
+        expect = np.ones(n, dtype=np.uint8)
+        expect[bad] = 0
+        d_accs, d_ok = torch.from_numpy(host).to(dev), torch.zeros(n, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        world1 = world
+        world = 1  # rank-0 only from here on: no collectives inside `timed`
+        ms = timed(lambda: ctx._check(L.svk_kzg_decide_batch_dev(c, kid, n, p(d_accs), p(d_ok))), 2)
+        assert (d_ok.cpu().numpy() == expect).all(), "decide mismatch"
+        dec_cpu = None
+        if cref is not None:
+            S_dk = __import__("oracle.forge", fromlist=["Setup"]).Setup(0).dk
+            t0 = time.perf_counter()
+            for i in range(32):
+                assert cref.decide(host[i], S_dk) == bool(expect[i])
+            dec_cpu = {"value": 32 / (time.perf_counter() - t0), "unit": "decides/s", "cores": 1, "kind": "port",
+                       "sample": "32 accumulators, one thread: 2-pair Miller loop + final exponentiation (decider.rs:60-68), C restatement (oracle/c)"}
+        out["config5_kzg_decide"] = {"n": n, "corrupted": int(len(bad)), "ms": ms, "value": n / (ms * 1e-3), "unit": "decides/s",
+                                     "roofline": {"bound": "imad", "achieved": n * 20000 / (ms * 1e-3) / 1e9, "peak": peak / 1e9,
+                                                  "unit": "Gmodmul/s canonical (20 k M per decide; 16.4 k executed)", "frac": n * 20000 / (ms * 1e-3) / peak,
+                                                  "frac_executed": n * 16400 / (ms * 1e-3) / peak},
+                                     "cpu_baseline": dec_cpu}
+        # ---- config 1: one SHPLONK proof through the host call (succinct verify + fold of one + the pairing)
+        sn = g["schemes"]["bdfg21"]["snarks"][0]
+        pv.verify_one(sn)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            pv.verify_one(sn)
+        lat = 1e3 * (time.perf_counter() - t0) / 5
+        out["config1_single_proof"] = {"gpu_ms_host_call": lat, "value": 1e3 / lat, "unit": "proofs/s (one at a time)",
+                                       "note": "latency of PlonkVerifier::verify for ONE proof (27 serial Poseidon permutations, one Straus MSM, one pairing): the "
+                                               "B200 path is a throughput device; the one-thread CPU figure is cpu_baseline.single_thread_value"}
+        world = world1
+    if world > 1:
+        dist.barrier()
+    return out if rank == 0 else None
 
 
 def run_ours(args):
@@ -424,9 +557,15 @@ def run_ours(args):
     L.svk_profile_report(c, buf, len(buf))
     L.svk_profile_enable(c, 0)
     barrier()
+    peak, peak_ms = sl.ctx.modmul_peak(4000)
+    secondary = None
+    if not args.no_secondary and args.scheme == "bdfg21":
+        for sl_ in slots[1:]:
+            sl_.ctx.close()  # the secondary configs need the memory (2^24-point MSM: ~6 GB of scratch)
+        torch.cuda.empty_cache()
+        secondary = run_secondary(torch, dist, V, sl.ctx, sl.stream, dev, g, peak, world, rank, args)
     if rank == 0:
         prof = json.loads(buf.value.decode())
-        peak, peak_ms = sl.ctx.modmul_peak(4000)
         info = pv.info
         # Work per launch, two ways (DESIGN.md "work model"):
         #  canonical -- SURVEY 8d's algorithmic count (a squaring = 1 M, a Poseidon permutation = 600 M, a Fermat chain = 380 M);
@@ -510,7 +649,7 @@ def run_ours(args):
                        "preflight_vs_oracle": preflight},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
-            "roofline": roofline, "cpu_baseline": base,
+            "roofline": roofline, "cpu_baseline": base, "secondary": secondary,
         }
         json_out.write(json.dumps(out) + "\n")
         json_out.flush()

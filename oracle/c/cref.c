@@ -337,6 +337,58 @@ static void load_acc_point(g1a* p, const uint8_t* b) {
   if (fe_is_zero(&x) && fe_is_zero(&y)) { memset(p, 0, sizeof *p); p->inf = 1; return; }
   f_to_mont(Q, &p->x, &x); f_to_mont(Q, &p->y, &y); p->inf = 0;
 }
+/* `util::msm::multi_scalar_multiplication` (snark-verifier/src/util/msm.rs:238-317): window = ceil(ln n) + 2 bits over the 256-bit
+ * `to_repr()`, 2^w - 1 buckets per window (MSB window first: w doublings of the running result, bucket fill with mixed additions,
+ * running-sum reduction), and with the `parallel` feature one serial MSM per chunk of n / threads points, results added.
+ * scalars: n x 32 B LE canonical, points: n x 64 B affine canonical ((0, 0) = identity), out: 64 B affine canonical. */
+#include <math.h>
+static void msm_serial(int n, const uint8_t* scalars, const g1a* bases, g1j* result) {
+  int w = (int)ceil(log((double)n)) + 2;
+  if (w < 1) w = 1;
+  int nbuckets = (1 << w) - 1, num_window = (256 + w - 1) / w;
+  g1j* buckets = (g1j*)malloc(sizeof(g1j) * (size_t)nbuckets);
+  for (int idx = num_window - 1; idx >= 0; idx--) {
+    for (int k = 0; k < w; k++) j_dbl(result, result);
+    for (int b = 0; b < nbuckets; b++) j_identity(&buckets[b]);
+    for (int i = 0; i < n; i++) {
+      int skip_bits = idx * w, skip_bytes = skip_bits / 8;
+      uint64_t v = 0;
+      for (int q = 0; q < 8 && skip_bytes + q < 32; q++) v |= (uint64_t)scalars[32 * (size_t)i + skip_bytes + q] << (8 * q);
+      uint64_t d = (v >> (skip_bits - skip_bytes * 8)) & (uint64_t)nbuckets;
+      if (d) j_add_affine(&buckets[d - 1], &buckets[d - 1], &bases[i]);
+    }
+    g1j running; j_identity(&running);
+    for (int b = nbuckets - 1; b >= 0; b--) { j_add(&running, &running, &buckets[b]); j_add(result, result, &running); }
+  }
+  free(buckets);
+}
+typedef struct { int n; const uint8_t* scalars; const g1a* bases; g1j result; } msm_job_t;
+static void* msm_worker(void* arg) { msm_job_t* j = (msm_job_t*)arg; j_identity(&j->result); if (j->n) msm_serial(j->n, j->scalars, j->bases, &j->result); return NULL; }
+int cref_msm(int n, const uint8_t* scalars, const uint8_t* points, uint8_t* out, int threads) {
+  if (threads < 1) threads = 1;
+  if (threads > 256) threads = 256;
+  g1a* bases = (g1a*)malloc(sizeof(g1a) * (size_t)(n ? n : 1));
+  for (int i = 0; i < n; i++) load_acc_point(&bases[i], points + 64 * (size_t)i);
+  if (n < threads) threads = 1;  /* msm.rs:296-300 */
+  int chunk = (n + threads - 1) / threads;
+  pthread_t th[256]; msm_job_t jobs[256];
+  for (int t = 0; t < threads; t++) {
+    int lo = t * chunk, hi = lo + chunk > n ? n : lo + chunk;
+    if (lo > n) lo = n;
+    msm_job_t j = {hi > lo ? hi - lo : 0, scalars + 32 * (size_t)lo, bases + lo, {{{0}}}};
+    jobs[t] = j;
+    if (t > 0) pthread_create(&th[t], NULL, msm_worker, &jobs[t]);
+  }
+  msm_worker(&jobs[0]);
+  g1j acc = jobs[0].result;
+  for (int t = 1; t < threads; t++) { pthread_join(th[t], NULL); j_add(&acc, &acc, &jobs[t].result); }
+  g1a a; j_to_affine(&a, &acc);
+  memset(out, 0, 64);
+  if (!a.inf) { fe x, y; f_from_mont(Q, &x, &a.x); f_from_mont(Q, &y, &a.y); memcpy(out, x.v, 32); memcpy(out + 32, y.v, 32); }
+  free(bases);
+  return 0;
+}
+
 /* KzgAs::create_proof / verify, zk = false, one group (accumulation.rs:45-61,113-136). returns status */
 int cref_fold_group(int n, const uint8_t* accs, uint8_t* out_acc, u64* out_r_canon) {
   sponge sp; sp_init(&sp);

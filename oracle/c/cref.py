@@ -160,6 +160,17 @@ def fold(accs, group_size=0, threads=1):
             return cur[0], res[-1][2], 0
 
 
+def msm(scalars, points, threads=1):
+    """`util::msm::multi_scalar_multiplication` (util/msm.rs:238-317) restated in C: scalars uint8[n,32] LE canonical, points
+    uint8[n,64] affine canonical -> uint8[64]."""
+    sc, pt = np.ascontiguousarray(scalars, dtype=np.uint8), np.ascontiguousarray(points, dtype=np.uint8)
+    n = sc.size // 32
+    out = np.zeros(64, dtype=np.uint8)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    lib().cref_msm(n, p(sc), p(pt), p(out), threads)
+    return out
+
+
 def decide(acc, dk):
     g2 = _limbs64([dk.g2[0][0], dk.g2[0][1], dk.g2[1][0], dk.g2[1][1]])
     sg2 = _limbs64([dk.s_g2[0][0], dk.s_g2[0][1], dk.s_g2[1][0], dk.s_g2[1][1]])

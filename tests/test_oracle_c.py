@@ -45,3 +45,25 @@ def test_replay_matches_python_oracle(S, scheme):
     acc_bad, _, _ = cref.fold(good, 0)  # contains the mutated proof's accumulator
     assert cref.decide(acc_bad, S.dk) is False
     assert cref.decide(np.frombuffer(acc_bytes(None, None), dtype=np.uint8), S.dk) is True
+
+
+def test_c_pippenger_matches_naive_msm():
+    """oracle/c `cref_msm` (C restatement of util/msm.rs:238-317, the reference's Pippenger incl. its chunking over threads) against
+    the naive sum of scalar multiplications (loader/native.rs:61-71) on the Python oracle."""
+    import random
+
+    rng = random.Random(3)
+    n = 150
+    pts = [bn254.g1_mul(bn254.G1_GEN, rng.randrange(1, bn254.R)) for _ in range(n)]
+    pts[5] = None
+    pts[9] = pts[8]
+    sc = [rng.randrange(bn254.R) for _ in range(n)]
+    sc[0], sc[1], sc[9] = 0, bn254.R - 1, (bn254.R - sc[8]) % bn254.R
+    S_ = np.frombuffer(b"".join(x.to_bytes(32, "little") for x in sc), np.uint8).reshape(n, 32)
+    P_ = np.frombuffer(b"".join(acc_bytes(p, None)[:64] for p in pts), np.uint8).reshape(n, 64)
+    exp = None
+    for s_, p in zip(sc, pts):
+        exp = bn254.g1_add(exp, bn254.g1_mul(p, s_))
+    for th in (1, 4):
+        assert g1_from(cref.msm(S_, P_, th).tobytes()) == exp
+    assert g1_from(cref.msm(S_[:1], P_[:1], 8).tobytes()) is None  # 0 * P
