@@ -11,6 +11,7 @@
 // 4-bit windows of the first version (15-entry table, 64 additions, 252 doublings): ~10 additions fewer per term.
 #pragma once
 #include "g1.cuh"
+#include "glv.cuh"
 
 #define STRAUS_WINDOWS 52
 #define STRAUS_TABLE 16
@@ -120,6 +121,55 @@ HD JacT<F> straus_run(const u32* k, u32 nt, const JacT<F>* tables, size_t stride
         if (AFFINE) acc = acc.add_affine(AffT<F>{cur.X, cur.Y});
         else acc = acc.add(cur);
       }
+    }
+  }
+  return acc;
+}
+
+
+// ---- one term per thread, GLV form (latency schedule of the per-proof MSM: a lone 255-doubling chain is most of k_msm_var's time)
+// k P = (+-k1) P + (+-k2) phi(P) with 128-bit halves (glv.cuh): 25 signed 5-bit windows + an unsigned top window per half, ONE
+// 16-entry Jacobian table of P (phi(T) = (beta X, Y, Z) in Jacobian coordinates too), 125 doublings instead of 255.
+#define STRAUS_GLV_WINDOWS 26
+// k (4 limbs, < 2^128) += sum_{i<25} 16 * 32^i ; digit_i = ((k' >> 5 i) & 31) - 16 for i < 25, digit_25 = k' >> 125 (0..9)
+HD void straus_glv_recode(const u32* k, u32* out5) {
+  const u32 C[4] = {0x21084210u, 0x08421084u, 0x42108421u, 0x10842108u};  // sum_{i<25} 16 * 32^i  (bits 4, 9, .., 124)
+  out5[0] = ptx::add_cc(k[0], C[0]);
+  out5[1] = ptx::addc_cc(k[1], C[1]);
+  out5[2] = ptx::addc_cc(k[2], C[2]);
+  out5[3] = ptx::addc_cc(k[3], C[3] & 0x1fffffffu);
+  out5[4] = ptx::addc(0, 0);
+}
+HD u32 straus_glv_digit(const u32* k5, int w, u32& neg) {
+  u32 bit = 5u * (u32)w, word = bit >> 5, sh = bit & 31;
+  u64 two = (u64)k5[word] | ((u64)(word < 4 ? k5[word + 1] : 0) << 32);
+  neg = 0;
+  if (w == STRAUS_GLV_WINDOWS - 1) return (u32)(two >> sh);  // k' >> 125: everything that is left
+  int s = (int)((two >> sh) & 31) - 16;
+  neg = s < 0;
+  return (u32)(s < 0 ? -s : s);
+}
+template <class F>
+HD JacT<F> straus_run_glv1(const u32* k1, u32 neg1, const u32* k2, u32 neg2, const JacT<F>* table, size_t stride, const F& beta) {
+  typedef JacT<F> J;
+  u32 r1[5], r2[5];
+  straus_glv_recode(k1, r1);
+  straus_glv_recode(k2, r2);
+  J acc = J::identity();
+  for (int w = STRAUS_GLV_WINDOWS - 1; w >= 0; w--) {
+    if (w != STRAUS_GLV_WINDOWS - 1) acc = acc.dbl().dbl().dbl().dbl().dbl();
+    u32 n1, n2;
+    u32 d1 = straus_glv_digit(r1, w, n1), d2 = straus_glv_digit(r2, w, n2);
+    if (d1) {
+      J e = table[(size_t)(d1 - 1) * stride];
+      if (n1 ^ neg1) e.Y = e.Y.neg();
+      acc = acc.add(e);
+    }
+    if (d2) {
+      J e = table[(size_t)(d2 - 1) * stride];
+      e.X = e.X * beta;  // phi
+      if (n2 ^ neg2) e.Y = e.Y.neg();
+      acc = acc.add(e);
     }
   }
   return acc;

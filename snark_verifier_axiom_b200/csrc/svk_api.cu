@@ -51,8 +51,7 @@ static int upload(svk_ctx* ctx, T** d, const std::vector<T>& v) {
 // `var_lane_base`: index of this side's first k_msm_var lane; `var_lanes`: how many lanes this side may use.
 static size_t schedule_msm(const std::vector<MsmTermDev>& terms, std::vector<std::vector<MsmWork>>& var_lanes_items, u32 var_lane_base,
                            u32 var_lanes, std::vector<MsmWork>& work, std::vector<u32>& lane_off, std::vector<FixedSlot>& fixed_sched,
-                           u32& fixed_per, u32 fixed_bits) {
-  const int L = SVK_MSM_LANES;
+                           u32& fixed_per, u32 fixed_bits, int L) {
   const size_t FW = 256 / fixed_bits;  // table windows per fixed base
   std::vector<std::vector<MsmWork>> lanes(L);
   size_t total = 0;
@@ -94,10 +93,10 @@ static size_t schedule_msm(const std::vector<MsmTermDev>& terms, std::vector<std
 static void protocol_release(ProtocolDevice* p) {
   if (!p) return;
   cudaFree(p->d_ops); cudaFree(p->d_aux); cudaFree(p->d_consts); cudaFree(p->d_sched); cudaFree(p->d_lhs); cudaFree(p->d_rhs);
-  cudaFree(p->d_fixed); cudaFree(p->d_fixed_lhs); cudaFree(p->d_fixed_rhs); cudaFree(p->d_old_idx);
+  cudaFree(p->d_fixed); cudaFree(p->d_old_idx);
   for (auto& sc : p->sched) {
     cudaFree(sc.d_var_items); cudaFree(sc.d_var_lane_off); cudaFree(sc.d_work_lhs); cudaFree(sc.d_work_rhs);
-    cudaFree(sc.d_lane_off_lhs); cudaFree(sc.d_lane_off_rhs);
+    cudaFree(sc.d_lane_off_lhs); cudaFree(sc.d_lane_off_rhs); cudaFree(sc.d_fixed_lhs); cudaFree(sc.d_fixed_rhs);
   }
   if (p->d_fixed_tables) {
     std::lock_guard<std::mutex> lk(g_table_mu);
@@ -386,9 +385,10 @@ static int protocol_upload(svk_ctx* ctx, svk_host::CompiledProtocol& cp, int mos
     std::vector<MsmWork> wl, wr, var_items;
     std::vector<u32> ol, orr;
     std::vector<FixedSlot> fl, fr;
-    sc.msm_work_modmul = schedule_msm(lhs, vlanes, 0, ll, wl, ol, fl, pd->fixed_per_lhs, pd->fixed_bits) +
-                         schedule_msm(rhs, vlanes, ll, std::max<u32>(rl, 1), wr, orr, fr, pd->fixed_per_rhs, pd->fixed_bits);
-    if (which == 0 && (upload(ctx, &pd->d_fixed_lhs, fl) || upload(ctx, &pd->d_fixed_rhs, fr))) return fail(-1);
+    sc.msm_lanes = which == 0 ? 1 : SVK_MSM_LANES_LATENCY;
+    sc.msm_work_modmul = schedule_msm(lhs, vlanes, 0, ll, wl, ol, fl, sc.fixed_per_lhs, pd->fixed_bits, (int)sc.msm_lanes) +
+                         schedule_msm(rhs, vlanes, ll, std::max<u32>(rl, 1), wr, orr, fr, sc.fixed_per_rhs, pd->fixed_bits, (int)sc.msm_lanes);
+    if (upload(ctx, &sc.d_fixed_lhs, fl) || upload(ctx, &sc.d_fixed_rhs, fr)) return fail(-1);
     std::vector<u32> vloff;
     for (auto& l : vlanes) {
       vloff.push_back((u32)var_items.size());

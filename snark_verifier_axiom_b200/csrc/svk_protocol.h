@@ -33,7 +33,7 @@ struct FixedSlot {
   int32_t w;     // 8-bit window index
   int32_t slot;  // scalar slot
 };
-#define SVK_MSM_LANES 1
+#define SVK_MSM_LANES_LATENCY 8
 // Fixed-base tables use `fixed_bits`-wide windows (8 or 16, chosen per protocol): 256 / bits windows of 2^bits entries per base.
 #define SVK_FIXED_BITS_SMALL 8    // 524 KB per base
 #define SVK_FIXED_BITS_LARGE 16   // 67 MB per base, half the table additions; used while the tables stay under ~3 GB
@@ -49,6 +49,9 @@ struct MsmSched {
   u32 var_lanes = 1;                   // k_msm_var threads per proof serving the lhs side
   u32 var_lanes_total = 1;             // ... plus the lanes of the rhs side (GWC: rhs = sum u^i W_i)
   u32 var_terms_per_thread = 0;
+  u32 msm_lanes = 1;                   // k_msm_sum threads per (proof, side): 1 (throughput) or 8 + shuffle tree (latency)
+  FixedSlot *d_fixed_lhs = nullptr, *d_fixed_rhs = nullptr;  // [lane][per] fixed-base table additions
+  u32 fixed_per_lhs = 0, fixed_per_rhs = 0;
   size_t msm_work_modmul = 0;          // algorithmic Fq mults per proof of this schedule (DESIGN.md work model)
 };
 
@@ -71,8 +74,6 @@ struct ProtocolDevice {
   std::vector<MsmTermDev> h_lhs, h_rhs;  // host copies (svk_protocol_msm_terms)
   u32 n_lhs = 0, n_rhs = 0;
   MsmSched sched[2];            // [0] throughput, [1] latency (chosen per launch by the number of proofs)
-  FixedSlot *d_fixed_lhs = nullptr, *d_fixed_rhs = nullptr;  // [lane][per] table additions
-  u32 fixed_per_lhs = 0, fixed_per_rhs = 0;
   u32 fixed_bits = SVK_FIXED_BITS_SMALL;
   G1Affine* d_fixed_tables = nullptr;  // [n_pre + 1][256 / bits windows][2^bits digits]: d * 2^(bits w) * B, affine Montgomery
   u32 n_var = 0;                       // variable-base terms of both sides

@@ -142,8 +142,7 @@ __global__ void __launch_bounds__(PCOOP_THREADS) k_tape_coop(size_t n_items, con
 }
 
 // ------------------------------------------------------------------------------------------------
-#define MSM_LANES SVK_MSM_LANES
-
+template <int MSM_LANES>
 __device__ __forceinline__ G1Jac shfl_down_jac(const G1Jac& p, int delta) {
   G1Jac r;
 #pragma unroll
@@ -201,7 +200,8 @@ __global__ void __launch_bounds__(64) k_fixed_tables(u32 n_fixed, u32 bits, cons
 //                doublings and one inversion per thread.  Each thread has its own host-scheduled item list (lanes never mix the
 //                lhs and rhs sides); fewer lanes minimise total work, more lanes shorten the latency.
 //                Jacobian partial -> partials[(lane * n_items) + proof]
-//   k_msm_sum    one thread per (proof, side) (SVK_MSM_LANES = 1): the fixed-base table windows (mixed additions only,
+//   k_msm_sum    MSM_LANES threads per (proof, side) -- 1 in the throughput schedule, 8 + a shuffle tree in the latency schedule
+//                (155 serial additions = 0.9 ms on a lone thread) --: the fixed-base table windows (mixed additions only,
 //                entries prefetched), then the partials and the scalar == 1 bases -> sums[side][proof]
 //   k_to_affine  one proof per thread: one inversion for both sides, canonical accumulator bytes
 #define SVK_VAR_TERMS_MAX 16
@@ -216,6 +216,20 @@ __global__ void __launch_bounds__(64) k_msm_var(size_t n_items, const MsmWork* v
   size_t n_threads = n_items * vpl;
   u32 k[SVK_VAR_TERMS_MAX][8];
   u32 nt = 0;
+  if (!AFFINE && var_lane_off[lane + 1] - var_lane_off[lane] == 1) {
+    // latency schedule, one term per thread: GLV halves the doubling chain (straus.cuh straus_run_glv1)
+    MsmWork wk = var_items[var_lane_off[lane]];
+    u32 kk[8], k1[4], k2[4], n1, n2;
+    const uint4* sp = reinterpret_cast<const uint4*>(scalars + ((size_t)wk.slot * n_items + it) * 8);
+    uint4 lo = sp[0], hi = sp[1];
+    kk[0] = lo.x; kk[1] = lo.y; kk[2] = lo.z; kk[3] = lo.w; kk[4] = hi.x; kk[5] = hi.y; kk[6] = hi.z; kk[7] = hi.w;
+    if (glv_decompose(kk, k1, n1, k2, n2)) {
+      G1Affine base = pts[(size_t)wk.base * n_items + it];
+      straus_build_table(tables + gid, n_threads, base);
+      partials[gid] = straus_run_glv1(k1, n1, k2, n2, tables + gid, n_threads, glv_beta_mont());
+      return;
+    }
+  }
   for (u32 vi = var_lane_off[lane]; vi < var_lane_off[lane + 1] && nt < SVK_VAR_TERMS_MAX; vi++, nt++) {
     MsmWork wk = var_items[vi];
     const uint4* sp = reinterpret_cast<const uint4*>(scalars + ((size_t)wk.slot * n_items + it) * 8);
@@ -231,6 +245,7 @@ __global__ void __launch_bounds__(64) k_msm_var(size_t n_items, const MsmWork* v
 }
 
 // work: per side, per lane a list of items of kind 1 (fixed-base window slice), 2 (add base), 3 (add partial #base)
+template <int MSM_LANES>
 __global__ void __launch_bounds__(128) k_msm_sum(size_t n_items, const MsmWork* work_lhs, const u32* off_lhs, const MsmWork* work_rhs,
                                                  const u32* off_rhs, const FixedSlot* fixed_lhs, u32 per_lhs, const FixedSlot* fixed_rhs,
                                                  u32 per_rhs, u32 fixed_bits, const G1Affine* fixed_bases, const G1Affine* tables,
@@ -294,7 +309,7 @@ __global__ void __launch_bounds__(128) k_msm_sum(size_t n_items, const MsmWork* 
   if (off[MSM_LANES] > 1 || per) {  // a side with a single item (SHPLONK rhs = W') has nothing to reduce
 #pragma unroll
     for (int d = MSM_LANES / 2; d >= 1; d >>= 1) {
-      G1Jac o = shfl_down_jac(acc, d);
+      G1Jac o = shfl_down_jac<MSM_LANES>(acc, d);
       if (lane < (u32)d) acc = acc.add(o);
     }
   }
@@ -539,11 +554,18 @@ int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const
                    k_msm_var<false><<<(unsigned)((total + 63) / 64), 64, 0, s>>>(n, sc.d_var_items, sc.d_var_lane_off, vpl, d_pts, d_scalars, d_tables, nullptr, d_partials));
       }
     }
-    dim3 grid((unsigned)((n * MSM_LANES + 127) / 128), 2);
-    SVK_LAUNCH(ctx, "k_msm_sum",
-               k_msm_sum<<<grid, 128, 0, s>>>(n, sc.d_work_lhs, sc.d_lane_off_lhs, sc.d_work_rhs, sc.d_lane_off_rhs, pd->d_fixed_lhs,
-                                              pd->fixed_per_lhs, pd->d_fixed_rhs, pd->fixed_per_rhs, pd->fixed_bits, pd->d_fixed,
-                                              pd->d_fixed_tables, d_pts, d_scalars, d_partials, d_sums));
+    dim3 grid((unsigned)((n * sc.msm_lanes + 127) / 128), 2);
+    if (sc.msm_lanes == 1)
+      SVK_LAUNCH(ctx, "k_msm_sum",
+                 k_msm_sum<1><<<grid, 128, 0, s>>>(n, sc.d_work_lhs, sc.d_lane_off_lhs, sc.d_work_rhs, sc.d_lane_off_rhs, sc.d_fixed_lhs,
+                                                   sc.fixed_per_lhs, sc.d_fixed_rhs, sc.fixed_per_rhs, pd->fixed_bits, pd->d_fixed,
+                                                   pd->d_fixed_tables, d_pts, d_scalars, d_partials, d_sums));
+    else
+      SVK_LAUNCH(ctx, "k_msm_sum",
+                 k_msm_sum<SVK_MSM_LANES_LATENCY><<<grid, 128, 0, s>>>(n, sc.d_work_lhs, sc.d_lane_off_lhs, sc.d_work_rhs, sc.d_lane_off_rhs,
+                                                                       sc.d_fixed_lhs, sc.fixed_per_lhs, sc.d_fixed_rhs, sc.fixed_per_rhs,
+                                                                       pd->fixed_bits, pd->d_fixed, pd->d_fixed_tables, d_pts, d_scalars,
+                                                                       d_partials, d_sums));
     SVK_LAUNCH(ctx, "k_to_affine", k_to_affine<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(n, d_sums, d_err, d_out_acc, acc_stride));
   } else {
     SVK_CUDA(ctx, cudaMemsetAsync(d_out_acc, 0, n * acc_stride, s));

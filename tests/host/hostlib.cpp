@@ -370,3 +370,13 @@ extern "C" int host_glv_decompose(const u32* k, u32* out) {
   return ok ? 1 : 0;
 }
 extern "C" void host_glv_beta(u32* out) { Fq b = glv_beta_mont().from_mont(); memcpy(out, b.v, 32); }
+
+// one-term GLV Straus (straus.cuh straus_run_glv1): out = k * P
+extern "C" int host_straus_glv1(const u32* p_xy, const u32* k, u32* out_xy) {
+  static G1Jac table[STRAUS_TABLE];
+  u32 k1[4], k2[4], n1, n2;
+  if (!glv_decompose(k, k1, n1, k2, n2)) return 1;
+  straus_build_table(table, 1, load_aff(p_xy));
+  store_aff(out_xy, straus_run_glv1(k1, n1, k2, n2, table, 1, glv_beta_mont()).to_affine());
+  return 0;
+}

@@ -216,6 +216,21 @@ def test_glv_decompose(lib):
     assert worst < 1 << 128
 
 
+def test_straus_glv_single_term(lib):
+    """straus.cuh straus_run_glv1 (the latency schedule of the per-proof MSM): k P through the GLV split and signed 5-bit windows
+    equals the oracle's scalar multiplication, incl. 0, 1, r - 1, lambda and the window-boundary patterns."""
+    rng = random.Random(31)
+    lam = 4407920970296243842393367215006156084916469457145843978461
+    P_ = bn254.g1_mul(bn254.G1_GEN, rng.randrange(1, R))
+    ks = [0, 1, 2, 15, 16, 17, 31, 32, R - 1, R - 2, lam, R - lam, (1 << 128) - 1, 1 << 127, sum(16 << (5 * i) for i in range(25)),
+          sum(15 << (5 * i) for i in range(50)) % R] + [rng.randrange(R) for _ in range(40)]
+    out = (ctypes.c_uint32 * 16)()
+    for k in ks:
+        assert lib.host_straus_glv1(limbs(list(P_)), limbs([k]), out) == 0
+        assert rd_g1(out) == bn254.g1_mul(P_, k), k
+    assert lib.host_straus_glv1(limbs([0, 0]), limbs([5]), out) == 0 and rd_g1(out) is None
+
+
 def test_poseidon_kat_and_random(lib):
     out = (ctypes.c_uint32 * 24)()
     assert lib.host_poseidon_permute(limbs([0, 1, 2]), 2, limbs([0]), limbs([0]), out) == 0
