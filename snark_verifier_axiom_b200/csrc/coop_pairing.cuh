@@ -38,11 +38,63 @@ struct CoopMem {
 
 HD Fq fq_mul9(const Fq& x) { return x.dbl().dbl().dbl() + x; }
 
+// 9 x + y (minus = false) or 9 x - y (minus = true), both operands reduced: ONE integer pass instead of five modular additions.
+// t = 9 x + w with w = y or p - y, t < 10 p < 2^258 (nine limbs); q = floor(t / p) is estimated from the top 34 bits against the
+// top 30 bits of p (never too large, at most one too small), t - q p < 2p, one conditional subtraction.
+HD Fq fq_mul9_addsub(const Fq& x, const Fq& y, bool minus) {
+  u32 t[9];
+  u64 c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    u32 w = minus ? 0 : y.v[i];
+    u64 v = (u64)x.v[i] * 9 + w + c;
+    t[i] = (u32)v;
+    c = v >> 32;
+  }
+  t[8] = (u32)c;
+  if (minus) {  // + (p - y)
+    u64 br = 0, cy = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      u64 d = (u64)FqParams::mod(i) - y.v[i] - br;
+      br = (d >> 32) & 1;
+      u64 v = (u64)t[i] + (u32)d + cy;
+      t[i] = (u32)v;
+      cy = v >> 32;
+    }
+    t[8] += (u32)cy;
+  }
+  u64 hi = ((u64)t[8] << 32) | t[7];
+  const u64 ptop = (u64)FqParams::mod(7) + 1;
+  u32 q = 0;
+#pragma unroll
+  for (int b = 3; b >= 0; b--) {
+    u64 m = ptop << b;
+    if (hi >= m) { hi -= m; q |= 1u << b; }
+  }
+  // r = t - q p  (fits eight limbs: < 2p)
+  u32 r[8];
+  u64 mc = 0, br = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    u64 m = (u64)FqParams::mod(i) * q + mc;
+    mc = m >> 32;
+    u64 d = (u64)t[i] - (u32)m - br;
+    r[i] = (u32)d;
+    br = (d >> 32) & 1;
+  }
+  Fq::reduce_once(r);
+  Fq out;
+#pragma unroll
+  for (int i = 0; i < 8; i++) out.v[i] = r[i];
+  return out;
+}
+
 // xi-half of a block from its value half: xi (a + b u) = (9a - b) + (9b + a) u.  task t in [0, 12)
 HD void coop_xi_task(Fq* blk, int t) {
   int k = t >> 1, c = t & 1;
   const Fq &a = blk[2 * k], &b = blk[2 * k + 1];
-  blk[12 + t] = c == 0 ? fq_mul9(a) - b : fq_mul9(b) + a;
+  blk[12 + t] = c == 0 ? fq_mul9_addsub(a, b, true) : fq_mul9_addsub(b, a, false);
 }
 
 // task t in [0, 48): partial dot product number (t & 3) of output coefficient (t >> 2)
@@ -93,11 +145,20 @@ HD Fq coop_sum4(const Fq* part, int o) {
 }
 
 // task t in [0, 12): output coefficient t and its xi-image (needs the partner component: summed here as well)
-HD void coop_combine_task(Fq* out, const Fq* part, int t) {
+// `warp12`: the twelve tasks run on lanes 0..11 of one warp (the device executor): the partner's sum comes by shuffle.
+HD void coop_combine_task(Fq* out, const Fq* part, int t, bool warp12 = false) {
   int c = t & 1;
-  Fq mine = coop_sum4(part, t), other = coop_sum4(part, t ^ 1);
+  Fq mine = coop_sum4(part, t), other;
+#if defined(__CUDA_ARCH__)
+  if (warp12) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) other.v[i] = __shfl_xor_sync(0xfffu, mine.v[i], 1);
+  } else
+#endif
+    other = coop_sum4(part, t ^ 1);
+  (void)warp12;
   out[t] = mine;
-  out[12 + t] = c == 0 ? fq_mul9(mine) - other : fq_mul9(mine) + other;
+  out[12 + t] = fq_mul9_addsub(mine, other, c == 0);
 }
 
 // out = a * b   (blocks; out may alias a and/or b).  The block-level operations are out-of-line on the device: the pairing program
@@ -105,7 +166,7 @@ HD void coop_combine_task(Fq* out, const Fq* part, int t) {
 template <class Ex>
 HDN void coop_mul(Ex& ex, Fq* out, const Fq* a, const Fq* b, Fq* part) {
   ex.par(COOP_DOT_LANES, [&](int t) { coop_dot_task(part, a, b, t); });
-  ex.par(12, [&](int t) { coop_combine_task(out, part, t); });
+  ex.par(12, [&](int t) { coop_combine_task(out, part, t, Ex::kWarp12); });
 }
 
 template <class Ex>
@@ -214,8 +275,14 @@ HD void coop_line_task(Fq* lb, const G1Affine& p1, const G2LineX* t1, const G1Af
   lb[idx] = v;
 }
 
+// Scratch per accumulator (Fq values): the 2 x SVK_N_LINES line blocks, the partial dot products of their pairwise products and the
+// SVK_N_LINES product blocks.
+#define COOP_SCRATCH_FQ (2 * SVK_N_LINES * COOP_BLK + SVK_N_LINES * COOP_DOT_LANES + SVK_N_LINES * COOP_BLK)
+
 // KzgAs::decide for one accumulator (decider.rs:60-68): e(lhs, g2) e(rhs, -s_g2) == 1.
-// `lb`: 2 * SVK_N_LINES * 24 Fq of scratch (global memory on the device), `m`: block-shared memory.
+// `lb`: COOP_SCRATCH_FQ values of scratch (global memory on the device), `m`: block-shared memory.
+// The two lines of a Miller step (one per pair) are multiplied with each other FIRST -- all SVK_N_LINES products are independent
+// of f and of each other, so every thread of the block works on them -- and f then takes ONE product per step instead of two.
 template <class Ex>
 HD bool coop_kzg_decide(Ex& ex, const G1Affine& lhs, const G1Affine& rhs, const G2LineX* t_g2, const G2LineX* t_neg_sg2,
                         const PairingConsts& K, Fq* lb, CoopMem& m, Fq* out_ml = nullptr, Fq* out_gt = nullptr) {
@@ -225,21 +292,28 @@ HD bool coop_kzg_decide(Ex& ex, const G1Affine& lhs, const G1Affine& rhs, const 
   ex.par(COOP_BLK, [&](int t) { f[t] = (t == 0 || t == 13) ? Fq::one() : (t == 12 ? fq_mul9(Fq::one()) : Fq::zero()); });
   const Fq* l1 = lb;
   const Fq* l2 = lb + SVK_N_LINES * COOP_BLK;
+  Fq* lpart = lb + 2 * SVK_N_LINES * COOP_BLK;
+  Fq* lprod = lpart + SVK_N_LINES * COOP_DOT_LANES;
+  ex.par(SVK_N_LINES * COOP_DOT_LANES, [&](int idx) {
+    int l = idx / COOP_DOT_LANES, t = idx % COOP_DOT_LANES;
+    coop_dot_task(lpart + l * COOP_DOT_LANES, l1 + l * COOP_BLK, l2 + l * COOP_BLK, t);
+  });
+  ex.par(SVK_N_LINES * 12, [&](int idx) {
+    int l = idx / 12, t = idx % 12;
+    coop_combine_task(lprod + l * COOP_BLK, lpart + l * COOP_DOT_LANES, t);
+  });
   int li = 0;
   for (int i = 63; i >= 0; i--) {
     coop_mul(ex, f, f, f, part);
-    coop_mul(ex, f, f, l1 + li * COOP_BLK, part);
-    coop_mul(ex, f, f, l2 + li * COOP_BLK, part);
+    coop_mul(ex, f, f, lprod + li * COOP_BLK, part);
     li++;
     if (ate_bit(i)) {
-      coop_mul(ex, f, f, l1 + li * COOP_BLK, part);
-      coop_mul(ex, f, f, l2 + li * COOP_BLK, part);
+      coop_mul(ex, f, f, lprod + li * COOP_BLK, part);
       li++;
     }
   }
   for (int s = 0; s < 2; s++) {
-    coop_mul(ex, f, f, l1 + li * COOP_BLK, part);
-    coop_mul(ex, f, f, l2 + li * COOP_BLK, part);
+    coop_mul(ex, f, f, lprod + li * COOP_BLK, part);
     li++;
   }
   if (out_ml) ex.par(12, [&](int t) { out_ml[t] = f[t]; });  // test hook: the Miller value

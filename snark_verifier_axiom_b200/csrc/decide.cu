@@ -37,8 +37,9 @@ __global__ void __launch_bounds__(64, SVK_DECIDE_MINBLOCKS) k_decide(size_t n, c
 // Latency form (coop_pairing.cuh): one accumulator per block of COOP_THREADS threads.  Used when there are too few
 // accumulators to fill the machine with one thread each (the single pairing that ends a batch, the per-rank or per-batch
 // pairings of a sharded / multi-batch call).
-#define COOP_THREADS 64
+#define COOP_THREADS 128
 struct DevExec {
+  static constexpr bool kWarp12 = true;  // a 12-task phase runs on lanes 0..11 of warp 0
   template <class F>
   __device__ __forceinline__ void par(int n_tasks, F f) {
     for (int i = threadIdx.x; i < n_tasks; i += COOP_THREADS) f(i);
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(COOP_THREADS) k_decide_coop(size_t n, const ui
     return;
   }
   DevExec ex;
-  bool acc = coop_kzg_decide(ex, pts[0], pts[1], t_g2, t_neg_sg2, *consts, line_scratch + i * (size_t)(2 * SVK_N_LINES * COOP_BLK), m);
+  bool acc = coop_kzg_decide(ex, pts[0], pts[1], t_g2, t_neg_sg2, *consts, line_scratch + i * (size_t)COOP_SCRATCH_FQ, m);
   if (threadIdx.x == 0) out_ok[i * ok_stride] = acc ? 1 : 0;
 }
 
@@ -81,7 +82,7 @@ int svk_decide_launch_strided(svk_ctx* ctx, int dk, size_t n, const void* d_accs
   const DkDevice& k = ctx->dks[dk];
   if (n <= ctx->decide_coop_max) {
     Fq* d_lines;
-    if (svk_scratch(ctx, 19, n * (size_t)(2 * SVK_N_LINES * COOP_BLK) * sizeof(Fq), (void**)&d_lines)) return -1;
+    if (svk_scratch(ctx, 19, n * (size_t)COOP_SCRATCH_FQ * sizeof(Fq), (void**)&d_lines)) return -1;
     SVK_LAUNCH(ctx, "k_decide_coop",
                k_decide_coop<<<(unsigned)n, COOP_THREADS, 0, ctx->stream>>>(n, (const uint8_t*)d_accs, acc_stride, (uint8_t*)d_ok, ok_stride, k.d_linesx_g2,
                                                                            k.d_linesx_neg_sg2, ctx->d_pairing_consts, d_lines));

@@ -116,6 +116,7 @@ int host_pairing(const u32* p1_xy, const u32* q1, const u32* p2_xy, const u32* q
 
 #include "../../snark_verifier_axiom_b200/csrc/coop_pairing.cuh"
 struct HostExec {
+  static constexpr bool kWarp12 = false;
   template <class F>
   void par(int n, F f) { for (int i = 0; i < n; i++) f(i); }
 };
@@ -130,7 +131,7 @@ int host_pairing_coop(const u32* p1_xy, const u32* q1, const u32* p2_xy, const u
   for (auto& l : t1) x1.push_back({l.neg_lam, l.c3, l.neg_lam.mul_xi(), l.c3.mul_xi()});
   for (auto& l : t2) x2.push_back({l.neg_lam, l.c3, l.neg_lam.mul_xi(), l.c3.mul_xi()});
   G1Affine P1 = load_aff(p1_xy), P2 = load_aff(p2_xy);
-  std::vector<Fq> lb(2 * SVK_N_LINES * COOP_BLK);
+  std::vector<Fq> lb(COOP_SCRATCH_FQ);
   static CoopMem m;
   HostExec ex;
   Fq ml[12], gt[12];
