@@ -68,7 +68,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -77,9 +77,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples taken inside [t0, t1] (host clock around the timed region); the sampler itself starts earlier, because
+        nvidia-smi needs longer to start than a short timed region lasts.  With no sample inside the window (a region shorter than
+        the polling period) the two samples around it are used."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -89,7 +92,16 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        rows = list(self.lines)
+        if t0 is not None:
+            inside = [ln for t, ln in rows if t0 <= t <= t1 + 0.05]
+            if not inside:
+                before, after = [ln for t, ln in rows if t < t0][-1:], [ln for t, ln in rows if t > t1][:1]
+                inside = before + after
+            rows = inside
+        else:
+            rows = [ln for _, ln in rows]
+        for ln in rows:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -423,7 +435,9 @@ def run_ours(args):
             assert preflight["corrupted"]["accumulator_equal"] and not preflight["corrupted"]["verdict"] and not preflight["corrupted"]["oracle_verdict"], preflight
         barrier()
 
-    # ---- warm-up (every slot)
+    # ---- warm-up (every slot).  The clock sampler starts here: nvidia-smi takes longer to start than a short timed region lasts.
+    sampler = ClockSampler(local)
+    sampler.start()
     for k in range(max(args.warmup, 1) * S):
         launch(k)
     torch.cuda.synchronize()
@@ -447,9 +461,8 @@ def run_ours(args):
 
     # ---- timed: exactly K steps (batches), round-robin over the in-flight slots; device time by CUDA
     # events on the launching streams: from a common start event to the last slot's end event
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
+    t_wall0 = time.time()
     l0 = sum(sl.ctx.launch_count for sl in slots)
     master = torch.cuda.current_stream(dev)
     e_start = torch.cuda.Event(enable_timing=True)
@@ -465,7 +478,9 @@ def run_ours(args):
         e.record(sl.stream)
         e_ends.append(e)
     barrier()
-    clocks = sampler.stop()
+    t_wall1 = time.time()
+    time.sleep(0.06)  # one more polling period, so that a sample lands right behind a short region
+    clocks = sampler.stop(t_wall0, t_wall1)
     launches = sum(sl.ctx.launch_count for sl in slots) - l0
     ms_total = max(e_start.elapsed_time(e) for e in e_ends)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)

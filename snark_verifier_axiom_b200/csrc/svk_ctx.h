@@ -1,6 +1,7 @@
 // Internal context shared by the libsvk translation units.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cstdarg>
 #include <cstdio>
@@ -61,7 +62,15 @@ struct svk_ctx {
   bool nccl_owned = false;
   int world = 1, rank = 0;
 };
-#define SVK_LOCK(ctx) std::lock_guard<std::recursive_mutex> svk_lock_((ctx)->mu)
+// NVTX range per C-ABI call (header-only NVTX 3: a no-op unless a profiler injects itself), so nsys / ncu timelines show the
+// reference-level operation (verify batch, fold, decide, msm) above the kernels it launched.
+struct SvkNvtxRange {
+  explicit SvkNvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~SvkNvtxRange() { nvtxRangePop(); }
+};
+#define SVK_LOCK(ctx)                                              \
+  std::lock_guard<std::recursive_mutex> svk_lock_((ctx)->mu);      \
+  SvkNvtxRange svk_nvtx_(__func__)
 
 inline int svk_fail(svk_ctx* ctx, const char* fmt, ...) {
   char buf[512];

@@ -1,0 +1,15 @@
+# Round-2 evidence pass (one gpurun call): plain runs first, then the same commands under ncu.
+set -x
+B="python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-secondary"
+python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_n1_k20.json 2> gpurun_out/r2_bench_n1_k20.err
+python bench.py > gpurun_out/r2_bench_n1_default.json 2> gpurun_out/r2_bench_n1_default.err
+python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r2_bench_reference_arm.json 2>/dev/null
+python tools/lat_probe.py --group-size 4 > gpurun_out/r2_latency_probe.json 2>/dev/null
+python tools/lat_probe.py --group-size 4 --batch 1 >> gpurun_out/r2_latency_probe.json 2>/dev/null
+python tools/bench_configs.py --only msm --max-log-n 26 > gpurun_out/r2_msm_sweep.jsonl 2>/dev/null
+python tools/bench_configs.py --only decide >> gpurun_out/r2_msm_sweep.jsonl 2>/dev/null
+$B > gpurun_out/plain1.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_ncu_launches.csv $B > gpurun_out/ncu1.log 2>&1
+$B > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"k_tape|k_msm_var|k_msm_sum|k_decompress|k_group_var|k_fold_sponge" -s 60 -c 8 -o gpurun_out/r2_full $B > gpurun_out/ncu2.log 2>&1
+python tools/bench_configs.py --only msm --max-log-n 20 > gpurun_out/plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"k_msm_buckets|k_msm_reduce|k_msm_combine|k_msm_prepare|k_msm_scatter" -s 15 -c 5 -o gpurun_out/r2_msm python tools/bench_configs.py --only msm --max-log-n 20 > gpurun_out/ncu3.log 2>&1
+python tools/bench_configs.py --only decide > gpurun_out/plain4.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"k_decide" -c 1 -o gpurun_out/r2_decide python tools/bench_configs.py --only decide > gpurun_out/ncu4.log 2>&1
+echo done
