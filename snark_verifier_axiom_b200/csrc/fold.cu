@@ -168,6 +168,30 @@ __global__ void __launch_bounds__(64) k_group_var(size_t n_seg, size_t n, size_t
   size_t begin = seg * n + g * m, end = (g * m + m < n ? g * m + m : n) + seg * n;
   u32 k[FOLD_TERMS_MAX][8];
   u32 nt = 0;
+  if (!AFFINE && vpl + 1 >= m) {
+    // one member per thread: GLV halves the doubling chain (straus.cuh straus_run_glv1)
+    size_t i = begin + 1 + lane;
+    G1Jac acc = G1Jac::identity();
+    if (i < end) {
+      u32 kk[8], k1[4], k2[4], n1, n2;
+      load_canon32(kk, reinterpret_cast<const uint8_t*>(scalars + i * 8));
+      G1Affine base;
+      if (!load_acc_point(base, accs + i * 128 + h * 64)) {
+        atomicMax(status + seg * status_stride_words, SVK_TRANSCRIPT | (SVK_T_POINT_INVALID << 8));
+        base = G1Affine::identity();
+      }
+      if (glv_decompose(kk, k1, n1, k2, n2)) {
+        straus_build_table(tables + gid, n_threads, base);
+        acc = straus_run_glv1(k1, n1, k2, n2, tables + gid, n_threads, glv_beta_mont());
+      } else {  // cannot happen for a canonical scalar; the plain path gives the same point
+        straus_recode(kk);
+        straus_build_table(tables + gid, n_threads, base);
+        acc = straus_run<false>(kk, 1, tables + gid, n_threads);
+      }
+    }
+    partials[gid] = acc;
+    return;
+  }
   for (size_t i = begin + 1 + lane; i < end && nt < FOLD_TERMS_MAX; i += vpl, nt++) {
     load_canon32(k[nt], reinterpret_cast<const uint8_t*>(scalars + i * 8));
     G1Affine base;
@@ -366,7 +390,7 @@ int svk_fold_launch_seg(svk_ctx* ctx, size_t n_seg, size_t n, const uint8_t* d_a
                  k_fold_sponge<<<(unsigned)((total_groups + 31) / 32), 32, 0, s>>>(n_seg, cnt, m, cur, ctx->d_poseidon, d_scal, last ? d_r : nullptr,
                                                                                   out_stride / 4, d_status, out_stride / 4));
     // lanes per (group, side): 1 while there are enough groups to fill the machine, else one lane per term
-    if (total_groups * 2 < 2048 && gm > 1) vpl = (u32)(gm - 1);
+    if (total_groups * 2 < ctx->fold_lanes_groups_max && gm > 1) vpl = (u32)(gm - 1);
     size_t terms_per_thread = gm > 1 ? (gm - 1 + vpl - 1) / vpl : 0;
     if (terms_per_thread > FOLD_TERMS_MAX) vpl = (u32)((gm - 1 + FOLD_TERMS_MAX - 1) / FOLD_TERMS_MAX), terms_per_thread = (gm - 1 + vpl - 1) / vpl;
     size_t var_threads = total_groups * 2 * vpl;

@@ -129,6 +129,7 @@ int svk_create(int device, svk_ctx** out) {
   if (const char* e = getenv("SVK_DECIDE_COOP_MAX")) ctx->decide_coop_max = (size_t)atoll(e);
   if (const char* e = getenv("SVK_TAPE_COOP_MAX")) ctx->tape_coop_max = (size_t)atoll(e);
   if (const char* e = getenv("SVK_FOLD_DBL_THREADS_MAX")) ctx->fold_dbl_threads_max = (size_t)atoll(e);
+  if (const char* e = getenv("SVK_FOLD_LANES_GROUPS_MAX")) ctx->fold_lanes_groups_max = (size_t)atoll(e);
   if (const char* e = getenv("SVK_MSM_LATENCY_THREADS_MAX")) ctx->msm_latency_threads_max = (size_t)atoll(e);
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; g_create_err = "stream create failed"; return -1; }
   ctx->own_stream = true;

@@ -44,6 +44,7 @@ struct svk_ctx {
   uint64_t launches = 0;
   int sm_count = 0;
   size_t msm_latency_threads_max = 150000;  // per-proof MSM: one thread per TERM while proofs x terms stays under this
+  size_t fold_lanes_groups_max = 2048;  // wide fold levels (Straus path): one thread per MEMBER while (groups x sides) stays under this
   size_t fold_dbl_threads_max = 32768;  // fold levels with at most this many (accumulator, side) pairs precompute the doublings beside the sponge
   size_t tape_coop_max = 32768;   // launches with at most this many proofs (sponges) run the warp-cooperative Poseidon (poseidon_coop.cuh)
   size_t decide_coop_max = 512;  // decide calls with at most this many accumulators run one accumulator per BLOCK (k_decide_coop)

@@ -12,4 +12,10 @@ $B > gpurun_out/plain1.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-
 $B > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"k_tape|k_msm_var|k_msm_sum|k_decompress|k_group_var|k_fold_sponge" -s 60 -c 8 -o gpurun_out/r2_full $B > gpurun_out/ncu2.log 2>&1
 python tools/bench_configs.py --only msm --max-log-n 20 > gpurun_out/plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"k_msm_buckets|k_msm_reduce|k_msm_combine|k_msm_prepare|k_msm_scatter" -s 15 -c 5 -o gpurun_out/r2_msm python tools/bench_configs.py --only msm --max-log-n 20 > gpurun_out/ncu3.log 2>&1
 python tools/bench_configs.py --only decide > gpurun_out/plain4.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"k_decide" -c 1 -o gpurun_out/r2_decide python tools/bench_configs.py --only decide > gpurun_out/ncu4.log 2>&1
+# summaries are made here; the raw reports are too large to travel back (64 MiB cap)
+python tools/ncu_to_json.py gpurun_out/r2_full.ncu-rep "$B under ncu --set full --clock-control none -k regex:k_tape|k_msm_var|k_msm_sum|k_decompress|k_group_var|k_fold_sponge -s 60 -c 8 (launches of 10 batches = 40960 proofs)" > gpurun_out/r2_ncu_full_summary.json
+python tools/ncu_to_json.py gpurun_out/r2_msm.ncu-rep "python tools/bench_configs.py --only msm --max-log-n 20 under ncu --set full -k regex:k_msm_* -s 15 -c 5 (the 2^18-point MSM)" > gpurun_out/r2_ncu_msm_summary.json
+python tools/ncu_to_json.py gpurun_out/r2_decide.ncu-rep "python tools/bench_configs.py --only decide under ncu --set full -k regex:k_decide -c 1 (65536 accumulators)" > gpurun_out/r2_ncu_decide_summary.json
+rm -f gpurun_out/r2_full.ncu-rep gpurun_out/r2_msm.ncu-rep gpurun_out/r2_decide.ncu-rep
+du -sh gpurun_out
 echo done
