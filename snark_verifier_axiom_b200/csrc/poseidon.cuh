@@ -33,6 +33,15 @@ struct PoseidonConsts {
   //   coop_rc[r] = row_r[0] * partial[r],   coop_cc[r][w] = col_hat_r[w] * partial[r]          (derived, value-identical)
   Fr coop_rc[SVK_POSEIDON_RP];
   Fr coop_cc[SVK_POSEIDON_RP][2];
+  // Scaled partial rounds: x -> x^5 commutes with scaling ((sigma t)^5 = sigma^5 t^5), so the product row_r[0] * x of the s0 chain is
+  // pushed into the constants: s0 = sigma_r t_r, v_r = t_r^5, t_{r+1} = v_r + Q_r with
+  //   sigma_{r+1} = row_r[0] sigma_r^5,   Q_r = (row_r[0] c_r + row_r[1] s1 + row_r[2] s2) / sigma_{r+1},   s_w += col_r[w] sigma_r^5 v_r + col_r[w] c_r
+  //   sc_a[r][w] = col_hat_r[w] sigma_r^5,  sc_r[r][w] = row_r[w+1] / sigma_{r+1},  sc_k[r] = row_r[0] c_r / sigma_{r+1},  sc_end = sigma_57
+  // The s0 chain of a partial round is then 3 products + 1 addition instead of 4 + 1 (value-identical: exact field arithmetic).
+  Fr sc_a[SVK_POSEIDON_RP][2];
+  Fr sc_r[SVK_POSEIDON_RP][2];
+  Fr sc_k[SVK_POSEIDON_RP];
+  Fr sc_end;
 };
 
 struct PoseidonState {

@@ -7,12 +7,14 @@
 // sponge l ("warp-specialised": warp 0 = the transcript owner, warps 1, 2 = helpers), so the warps never diverge and the
 // register-file layouts ([reg][item]) of the callers stay coalesced:
 //   full round     every warp: y_w = s_w^5 + c_w, exchange through shared memory, s_w = <M[w], y>          (4 products deep)
-//   partial round  warp 0: x = s_0^5, post x, t = row_0 x, s_0 = t + P                                       (4 products + 1 addition deep)
-//                  warp 2: P_2 = row_2 s_2 -> warp 1;   warp 1: P = row_1 s_1 + P_2 + row_0 c -> warp 0   (posted BEFORE x is needed)
-//                  warp w: s_w = col_w x + (s_w + col_w c)          (c = the round constant: y = x + c never materialises)
+//   partial round  warp 0 holds t with s_0 = sigma t (the S-box commutes with scaling, poseidon.cuh sc_*): v = t^5, post v, t = v + Q
+//                                                                                                             (3 products + 1 addition deep)
+//                  warp 2: Q_2 = (row_2 / sigma') s_2 -> warp 1;   warp 1: Q = (row_1 / sigma') s_1 + Q_2 + row_0 c / sigma' -> warp 0
+//                                                                                                             (posted BEFORE v is needed)
+//                  warp w: s_w = (col_w sigma^5) v + (s_w + col_w c)     (c = the round constant: y = x + c never materialises)
 // Warp 0 never waits for a helper in the partial rounds (P of round r only needs x of round r - 1); the helpers wait for
 // x.  Synchronisation = named barriers (bar.arrive / bar.sync, producer/consumer form), mailboxes double-buffered.
-// Dependent chain per permutation: 65 x 4 products + the exchanges, instead of ~475 product-equivalents.
+// Dependent chain per permutation: 57 x 3 + 8 x 4 products + the exchanges, instead of ~475 product-equivalents.
 #pragma once
 #include "poseidon.cuh"
 
@@ -74,36 +76,37 @@ static __device__ __noinline__ void pc_permute(Fr& s, int role, int lane, Poseid
   for (int r = 1; r < SVK_POSEIDON_RF / 2; r++) full(k.mds, k.start[r]);
   full(k.pre_sparse_mds, k.start[SVK_POSEIDON_RF / 2]);
   // partial rounds with the sparse MDS factorisation (poseidon.rs:398-410)
+  // scaled form (poseidon.cuh: sc_*): warp 0 holds t with s0 = sigma_r t
   if (role == 0) {
     for (int r = 0; r < SVK_POSEIDON_RP; r++) {
-      Fr x = pc_pow5(s);
-      pc_st(sh->mail[buf][0][lane], x);
+      Fr v = pc_pow5(s);
+      pc_st(sh->mail[buf][0][lane], v);
       pc_bar_arrive(PC_BAR_Y + buf);
-      Fr t = k.sparse_row[r][0] * x;
       pc_bar_sync2(PC_BAR_P + buf);
-      s = t + pc_ld(sh->mail[buf][1][lane]);
+      s = v + pc_ld(sh->mail[buf][1][lane]);
       buf ^= 1;
     }
+    s = k.sc_end * s;
   } else if (role == 1) {
     for (int r = 0; r < SVK_POSEIDON_RP; r++) {
-      Fr P = k.sparse_row[r][1] * s + k.coop_rc[r];
+      Fr P = k.sc_r[r][0] * s + k.sc_k[r];
       pc_bar_sync2(PC_BAR_Q + buf);
       P = P + pc_ld(sh->mail[buf][2][lane]);
       pc_st(sh->mail[buf][1][lane], P);
       pc_bar_arrive2(PC_BAR_P + buf);
       Fr u = s + k.coop_cc[r][0];
       pc_bar_sync(PC_BAR_Y + buf);
-      s = k.sparse_col_hat[r][0] * pc_ld(sh->mail[buf][0][lane]) + u;
+      s = k.sc_a[r][0] * pc_ld(sh->mail[buf][0][lane]) + u;
       buf ^= 1;
     }
   } else {
     for (int r = 0; r < SVK_POSEIDON_RP; r++) {
-      Fr P = k.sparse_row[r][2] * s;
+      Fr P = k.sc_r[r][1] * s;
       pc_st(sh->mail[buf][2][lane], P);
       pc_bar_arrive2(PC_BAR_Q + buf);
       Fr u = s + k.coop_cc[r][1];
       pc_bar_sync(PC_BAR_Y + buf);
-      s = k.sparse_col_hat[r][1] * pc_ld(sh->mail[buf][0][lane]) + u;
+      s = k.sc_a[r][1] * pc_ld(sh->mail[buf][0][lane]) + u;
       buf ^= 1;
     }
   }

@@ -189,6 +189,21 @@ inline bool make_poseidon_consts(PoseidonConsts& k, int secure_mds = 0) {
     k.coop_cc[r][0] = k.sparse_col_hat[r][0] * k.partial[r];
     k.coop_cc[r][1] = k.sparse_col_hat[r][1] * k.partial[r];
   }
+  {
+    Fr sigma = Fr::one();
+    for (int r = 0; r < SVK_POSEIDON_RP; r++) {
+      Fr s2 = sigma.sqr(), s5 = s2.sqr() * sigma;
+      k.sc_a[r][0] = k.sparse_col_hat[r][0] * s5;
+      k.sc_a[r][1] = k.sparse_col_hat[r][1] * s5;
+      sigma = k.sparse_row[r][0] * s5;
+      if (sigma.is_zero()) return false;  // a zero first row entry: the scaled schedule does not exist for these parameters
+      Fr inv = sigma.inv();
+      k.sc_r[r][0] = k.sparse_row[r][1] * inv;
+      k.sc_r[r][1] = k.sparse_row[r][2] * inv;
+      k.sc_k[r] = k.coop_rc[r] * inv;
+    }
+    k.sc_end = sigma;
+  }
   Fr cap = Fr::zero();
   cap.v[2] = 1;  // 2^64
   k.capacity = cap.to_mont();
