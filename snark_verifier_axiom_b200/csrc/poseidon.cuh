@@ -6,8 +6,8 @@
 // R_F = 8, R_P = 57 (snark-verifier-sdk/src/halo2.rs:52-56).  All values in Montgomery form.
 // Cost: 8 full rounds x (3 x 3 + 9) + 57 partial rounds x (3 + 5) = 600 Fr multiplications in the textbook count; every
 // MDS row is ONE fused 3-term dot product (field.cuh `dot3`: 3 limb products, 1 reduction, no additions), which is
-// value-identical; with the partial rounds taken two at a time (one dot4 + two dot2 per pair) the permutation costs ~475
-// multiplication-equivalents of integer-pipe work.
+// value-identical; with the partial rounds in scaled form and taken two at a time (three dot2 + one dot3 per pair) the permutation
+// costs ~450 multiplication-equivalents of integer-pipe work.
 #pragma once
 #include "field.cuh"
 
@@ -25,10 +25,6 @@ struct PoseidonConsts {
   Fr sparse_row[SVK_POSEIDON_RP][3];      // SparseMDSMatrix.row
   Fr sparse_col_hat[SVK_POSEIDON_RP][2];  // SparseMDSMatrix.col_hat
   Fr capacity;                            // 2^64  (State::default, poseidon.rs:335-342)
-  // Two partial rounds at a time (derived from sparse_row / sparse_col_hat, value-identical): pair p = rounds (2p, 2p+1),
-  //   [0..3] = row_{2p+1}[0], row_{2p+1}[1] col_{2p}[0] + row_{2p+1}[2] col_{2p}[1], row_{2p+1}[1], row_{2p+1}[2]
-  //   [4..5] = col_{2p+1}[0], col_{2p}[0]      [6..7] = col_{2p+1}[1], col_{2p}[1]
-  Fr pair[SVK_POSEIDON_RP / 2][8];
   // Warp-cooperative schedule (poseidon_coop.cuh): the round constant of a partial round is folded into the helpers' terms,
   //   coop_rc[r] = row_r[0] * partial[r],   coop_cc[r][w] = col_hat_r[w] * partial[r]          (derived, value-identical)
   Fr coop_rc[SVK_POSEIDON_RP];
@@ -42,6 +38,11 @@ struct PoseidonConsts {
   Fr sc_r[SVK_POSEIDON_RP][2];
   Fr sc_k[SVK_POSEIDON_RP];
   Fr sc_end;
+  // the same two rounds at a time for the one-thread permutation (pair p = rounds a = 2p, b = 2p + 1; derived, value-identical):
+  //   [0..2]  Q_a = [0] s1 + [1] s2 + [2]                        t_b = v_a + Q_a
+  //   [3..6]  Q_b = [3] v_a + [4] s1 + [5] s2 + [6]              t'  = v_b + Q_b      ([3] = r_b0 a_a0 + r_b1 a_a1)
+  //   [7..9]  s1' = s1 + [7] v_a + [8] v_b + [9]                 [10..12] the same for s2
+  Fr sc_pair[SVK_POSEIDON_RP / 2][13];
 };
 
 struct PoseidonState {
@@ -61,25 +62,6 @@ HD void poseidon_mds(PoseidonState& st, const Fr (*m)[3]) {
   st.s[0] = r0;
   st.s[1] = r1;
   st.s[2] = r2;
-}
-
-// s0 after the second round of a pair: one 4-term dot product over (y_b, y_a, s1, s2); c = pair[p]
-#if defined(__CUDA_ARCH__)
-static __device__ __noinline__ Fr poseidon_pair_s0(const Fr* c, Fr yb, Fr ya, Fr s1, Fr s2) {
-#else
-inline Fr poseidon_pair_s0(const Fr* c, Fr yb, Fr ya, Fr s1, Fr s2) {
-#endif
-  Fr a[4] = {c[0], c[1], c[2], c[3]}, b[4] = {yb, ya, s1, s2};
-  return Fr::dot_inline<4>(a, b);
-}
-// s_i after the pair: col_{r+1} y_b + col_r y_a + s_i; c = pair[p] + 4 or + 6
-#if defined(__CUDA_ARCH__)
-static __device__ __noinline__ Fr poseidon_pair_si(const Fr* c, Fr yb, Fr ya, Fr si) {
-#else
-inline Fr poseidon_pair_si(const Fr* c, Fr yb, Fr ya, Fr si) {
-#endif
-  Fr a[2] = {c[0], c[1]}, b[2] = {yb, ya};
-  return Fr::dot_inline<2>(a, b) + si;
 }
 
 HD void poseidon_init(PoseidonState& st, const PoseidonConsts& k) {
@@ -104,33 +86,32 @@ HDN void poseidon_permute(PoseidonState& st, const PoseidonConsts& k, int n_in, 
   }
   for (int i = 0; i < 3; i++) st.s[i] = fr_pow5(st.s[i]) + k.start[SVK_POSEIDON_RF / 2][i];
   poseidon_mds(st, k.pre_sparse_mds);
-  // partial rounds with sparse MDS (poseidon.rs:398-410)
-  // Rounds are taken two at a time: with y_a, y_b the S-box outputs of the pair,
-  //   s0'' = row_b[0] y_b + (row_b[1] col_a[0] + row_b[2] col_a[1]) y_a + row_b[1] s1 + row_b[2] s2     (one dot4)
-  //   s_i'' = col_b[i] y_b + col_a[i] y_a + s_i                                                         (one dot2 each)
-  // = 264 + 328 + 2 x 200 wide MACs per pair instead of 2 x (264 + 2 x 136); the values are those of the round-by-round form.
+  // partial rounds with sparse MDS (poseidon.rs:398-410), in the SCALED form (sc_* above): t with s0 = sigma_r t, so that the
+  // product row_r[0] * x of the reference's round disappears into the constants; two rounds at a time:
+  //   v_a = t^5, t_b = v_a + Q_a (one dot2), v_b = t_b^5, t' = v_b + Q_b (one dot3), s_w' (one dot2 each)
+  // = 2 x 381 + 200 + 264 + 2 x 200 wide MACs per pair against 2 x 381 + 264 + 328 + 2 x 200 of the unscaled pairing.
+  Fr t = st.s[0];
   int r = 0;
   for (; r + 1 < SVK_POSEIDON_RP; r += 2) {
-    const Fr* c = k.pair[r >> 1];
-    Fr ya = fr_pow5(st.s[0]) + k.partial[r];
-    Fr t0 = Fr::dot3(k.sparse_row[r][0], ya, k.sparse_row[r][1], st.s[1], k.sparse_row[r][2], st.s[2]);
-    Fr yb = fr_pow5(t0) + k.partial[r + 1];
-    Fr n0 = poseidon_pair_s0(c, yb, ya, st.s[1], st.s[2]);
-    Fr n1 = poseidon_pair_si(c + 4, yb, ya, st.s[1]);
-    Fr n2 = poseidon_pair_si(c + 6, yb, ya, st.s[2]);
-    st.s[0] = n0;
+    const Fr* c = k.sc_pair[r >> 1];
+    Fr va = fr_pow5(t);
+    Fr tb = va + (Fr::dot2(c[0], st.s[1], c[1], st.s[2]) + c[2]);
+    Fr vb = fr_pow5(tb);
+    Fr qb = Fr::dot3(c[3], va, c[4], st.s[1], c[5], st.s[2]) + c[6];
+    Fr n1 = Fr::dot2(c[7], va, c[8], vb) + (st.s[1] + c[9]);
+    Fr n2 = Fr::dot2(c[10], va, c[11], vb) + (st.s[2] + c[12]);
+    t = vb + qb;
     st.s[1] = n1;
     st.s[2] = n2;
   }
   for (; r < SVK_POSEIDON_RP; r++) {
-    st.s[0] = fr_pow5(st.s[0]) + k.partial[r];
-    Fr n0 = Fr::dot3(k.sparse_row[r][0], st.s[0], k.sparse_row[r][1], st.s[1], k.sparse_row[r][2], st.s[2]);
-    Fr n1 = k.sparse_col_hat[r][0] * st.s[0] + st.s[1];
-    Fr n2 = k.sparse_col_hat[r][1] * st.s[0] + st.s[2];
-    st.s[0] = n0;
-    st.s[1] = n1;
-    st.s[2] = n2;
+    Fr v = fr_pow5(t);
+    Fr q = Fr::dot2(k.sc_r[r][0], st.s[1], k.sc_r[r][1], st.s[2]) + k.sc_k[r];
+    st.s[1] = k.sc_a[r][0] * v + (st.s[1] + k.coop_cc[r][0]);
+    st.s[2] = k.sc_a[r][1] * v + (st.s[2] + k.coop_cc[r][1]);
+    t = v + q;
   }
+  st.s[0] = k.sc_end * t;
   // second half of the full rounds
   for (int r = 0; r < SVK_POSEIDON_RF / 2 - 1; r++) {
     for (int i = 0; i < 3; i++) st.s[i] = fr_pow5(st.s[i]) + k.end[r][i];

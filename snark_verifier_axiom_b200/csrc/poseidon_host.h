@@ -173,17 +173,6 @@ inline bool make_poseidon_consts(PoseidonConsts& k, int secure_mds = 0) {
   Mat pre = mat_transpose(accm);
   for (int i = 0; i < T; i++)
     for (int j = 0; j < T; j++) { k.mds[i][j] = mds[i][j]; k.pre_sparse_mds[i][j] = pre[i][j]; }
-  for (int p = 0; p < SVK_POSEIDON_RP / 2; p++) {  // two partial rounds at a time (poseidon.cuh)
-    const int a = 2 * p, b = 2 * p + 1;
-    k.pair[p][0] = k.sparse_row[b][0];
-    k.pair[p][1] = k.sparse_row[b][1] * k.sparse_col_hat[a][0] + k.sparse_row[b][2] * k.sparse_col_hat[a][1];
-    k.pair[p][2] = k.sparse_row[b][1];
-    k.pair[p][3] = k.sparse_row[b][2];
-    k.pair[p][4] = k.sparse_col_hat[b][0];
-    k.pair[p][5] = k.sparse_col_hat[a][0];
-    k.pair[p][6] = k.sparse_col_hat[b][1];
-    k.pair[p][7] = k.sparse_col_hat[a][1];
-  }
   for (int r = 0; r < SVK_POSEIDON_RP; r++) {
     k.coop_rc[r] = k.sparse_row[r][0] * k.partial[r];
     k.coop_cc[r][0] = k.sparse_col_hat[r][0] * k.partial[r];
@@ -203,6 +192,16 @@ inline bool make_poseidon_consts(PoseidonConsts& k, int secure_mds = 0) {
       k.sc_k[r] = k.coop_rc[r] * inv;
     }
     k.sc_end = sigma;
+    for (int p = 0; p < SVK_POSEIDON_RP / 2; p++) {
+      const int a = 2 * p, b = 2 * p + 1;
+      Fr* c = k.sc_pair[p];
+      c[0] = k.sc_r[a][0]; c[1] = k.sc_r[a][1]; c[2] = k.sc_k[a];
+      c[3] = k.sc_r[b][0] * k.sc_a[a][0] + k.sc_r[b][1] * k.sc_a[a][1];
+      c[4] = k.sc_r[b][0]; c[5] = k.sc_r[b][1];
+      c[6] = k.sc_k[b] + k.sc_r[b][0] * k.coop_cc[a][0] + k.sc_r[b][1] * k.coop_cc[a][1];
+      c[7] = k.sc_a[a][0]; c[8] = k.sc_a[b][0]; c[9] = k.coop_cc[a][0] + k.coop_cc[b][0];
+      c[10] = k.sc_a[a][1]; c[11] = k.sc_a[b][1]; c[12] = k.coop_cc[a][1] + k.coop_cc[b][1];
+    }
   }
   Fr cap = Fr::zero();
   cap.v[2] = 1;  // 2^64
