@@ -611,9 +611,8 @@ def run_ours(args):
         #               (136 IMAD-pipe instructions): squaring 0.86 (117), dot2 1.47 (200), dot3 1.94 (264), measured by
         #               cuobjdump / tools/sqr_probe.cu.  roofline.frac uses EXECUTED work, so it is a utilisation (<= 1).
         S_, D2, D3 = 117 / 136, 200 / 136, 264 / 136
-        D4 = 328 / 136
-        perm_exec = (8 * (3 * (2 * S_ + 1) + 3 * D3) + 28 * (2 * (2 * S_ + 1) + D3 + D4 + 2 * D2)  # optimised Poseidon, T = 3, partial
-                     + ((2 * S_ + 1) + D3 + 2))                                                   # rounds two at a time: 475
+        perm_exec = (8 * (3 * (2 * S_ + 1) + 3 * D3) + 28 * (2 * (2 * S_ + 1) + 3 * D2 + D3)   # optimised Poseidon, T = 3; scaled partial
+                     + ((2 * S_ + 1) + D2 + 2) + 1)                                          # rounds two at a time (poseidon.cuh): ~447
         chain_exec = 253 * S_ + 58                                                      # sliding-window square-root chain: 276
         inv_exec = 80                                                                   # binary-Euclid inversion: ALU work; ~55 IMAD.MOV/IMAD.X per step on the multiply pipe
         n_perm = info["n_poseidon_perms"]
