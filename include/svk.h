@@ -67,6 +67,9 @@ uint64_t svk_launch_count(svk_ctx* ctx);
  * a JSON object {"kernel": {"count": launches, "ms": total device ms}}; reading it resets it. */
 int svk_profile_enable(svk_ctx* ctx, int on);
 int svk_profile_report(svk_ctx* ctx, char* buf, size_t buf_len);
+/* The same launches as a timeline: JSON [["kernel", start_ms, end_ms], ...], times relative to svk_profile_enable(ctx, 1) on the
+ * device clock, so that the timelines of several contexts (streams) enabled back to back can be laid side by side. */
+int svk_profile_timeline(svk_ctx* ctx, char* buf, size_t buf_len);
 
 /* Test hook: out[i] = `Poseidon::new().update(inputs[i]).squeeze()` (util/hash/poseidon.rs:448-467; T = 3, RATE = 2, R_F = 8,
  * R_P = 57, the SDK transcript's hash: snark-verifier-sdk/src/halo2.rs:52-56), n sponges of n_inputs elements each.

@@ -27,6 +27,7 @@ def _load():
     lib.svk_launch_count.restype = ctypes.c_uint64
     lib.svk_profile_enable.argtypes = [vp, i32]
     lib.svk_profile_report.argtypes = [vp, ctypes.c_char_p, sz]
+    lib.svk_profile_timeline.argtypes = [vp, ctypes.c_char_p, sz]
     lib.svk_dk_load.argtypes = [vp, u8p]
     lib.svk_kzg_decide_batch.argtypes = [vp, i32, sz, vp, vp]
     lib.svk_kzg_decide_batch_dev.argtypes = [vp, i32, sz, vp, vp]

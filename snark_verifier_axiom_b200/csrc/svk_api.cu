@@ -177,7 +177,37 @@ uint64_t svk_launch_count(svk_ctx* ctx) { return ctx->launches; }
 int svk_profile_enable(svk_ctx* ctx, int on) {
   SVK_LOCK(ctx);
   ctx->profile = on != 0;
+  if (on) {  // reference point of svk_profile_timeline: an event on the (idle) stream, i.e. "now" on the device clock
+    if (!ctx->profile_ref) SVK_CUDA(ctx, cudaEventCreate(&ctx->profile_ref));
+    SVK_CUDA(ctx, cudaEventRecord(ctx->profile_ref, ctx->stream));
+  }
   return 0;
+}
+
+// JSON list [["kernel", start_ms, end_ms], ...] of every launch since svk_profile_enable(ctx, 1), times relative to that call on the
+// device clock (comparable between contexts enabled back to back); resets the statistics like svk_profile_report.
+int svk_profile_timeline(svk_ctx* ctx, char* buf, size_t buf_len) {
+  SVK_LOCK(ctx);
+  SVK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::string out = "[";
+  bool first = true;
+  for (auto& pe : ctx->pending) {
+    float t0 = 0, t1 = 0;
+    if (ctx->profile_ref && cudaEventElapsedTime(&t0, ctx->profile_ref, pe.e0) == cudaSuccess &&
+        cudaEventElapsedTime(&t1, ctx->profile_ref, pe.e1) == cudaSuccess) {
+      char tmp[160];
+      snprintf(tmp, sizeof tmp, "%s[\"%s\", %.4f, %.4f]", first ? "" : ", ", pe.name, t0, t1);
+      out += tmp;
+      first = false;
+    }
+    cudaEventDestroy(pe.e0);
+    cudaEventDestroy(pe.e1);
+  }
+  ctx->pending.clear();
+  out += "]";
+  if (out.size() + 1 > buf_len) return svk_fail(ctx, "timeline buffer too small");
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return (int)out.size();
 }
 
 // JSON: {"kernel": {"count": c, "ms": total}, ...}; resets the statistics.  Returns bytes written or -1.

@@ -34,6 +34,7 @@ struct PendingEvent {
 
 struct svk_ctx {
   bool profile = false;  // svk_profile_enable: CUDA events around every kernel launch
+  cudaEvent_t profile_ref = nullptr;  // device-clock reference of svk_profile_timeline
   std::vector<PendingEvent> pending;
   std::map<std::string, KernelStat> stats;
   int device = 0;

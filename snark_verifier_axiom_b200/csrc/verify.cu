@@ -205,8 +205,11 @@ __global__ void __launch_bounds__(64) k_fixed_tables(u32 n_fixed, u32 bits, cons
 //                entries prefetched), then the partials and the scalar == 1 bases -> sums[side][proof]
 //   k_to_affine  one proof per thread: one inversion for both sides, canonical accumulator bytes
 #define SVK_VAR_TERMS_MAX 16
+#ifndef SVK_MSMVAR_MINBLOCKS
+#define SVK_MSMVAR_MINBLOCKS 1
+#endif
 template <bool AFFINE>
-__global__ void __launch_bounds__(64) k_msm_var(size_t n_items, const MsmWork* var_items, const u32* var_lane_off, u32 vpl, const G1Affine* pts,
+__global__ void __launch_bounds__(64, SVK_MSMVAR_MINBLOCKS) k_msm_var(size_t n_items, const MsmWork* var_items, const u32* var_lane_off, u32 vpl, const G1Affine* pts,
                                                 const u32* scalars, G1Jac* tables, Fq* prefix, G1Jac* partials) {
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= n_items * vpl) return;
