@@ -21,6 +21,12 @@ SRC = os.path.join(HERE, "host", "hostlib.cpp")
 
 @pytest.fixture(scope="module")
 def lib():
+    if os.environ.get("SVK_HOSTLIB_SANITIZE"):
+        # tests/test_host_asan.py re-runs this file with the address + undefined-behaviour sanitizers compiled into the host build
+        so = os.path.join(HERE, "host", "_hostlib_asan.so")
+        subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-shared", "-fPIC", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+                        "-o", so, SRC], check=True, timeout=900)
+        return ctypes.CDLL(so)
     subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", SO, SRC], check=True, timeout=600)
     return ctypes.CDLL(SO)
 
