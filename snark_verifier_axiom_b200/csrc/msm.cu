@@ -332,16 +332,45 @@ __global__ void __launch_bounds__(REDUCE_T) k_msm_reduce(MsmPlan plan, u32 rb, u
   if (threadIdx.x == 0) partials[(size_t)w * rbt + blockIdx.x] = sm[0];
 }
 
-// warp w adds the rb partials of window w (lanes stride, shuffle butterfly); thread 0 then runs Horner over the windows
-// (c doublings each) + to_affine
-#define COMBINE_MAX_WINDOWS 32
 template <class Fq>
-__global__ void __launch_bounds__(1024) k_msm_combine(MsmPlan plan, u32 rb, u32 rbt, const XyzzT<Fq>* partials, uint8_t* out) {
+__device__ __forceinline__ Fq bcast_fe(const Fq& a, int src) {
+  Fq r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src);
+  return r;
+}
+
+// Jacobian doubling (dbl-2009-l, as JacT::dbl) by a whole warp that holds the SAME point on every lane: the independent products of
+// each level run on lanes 0, 1, 2 and are broadcast -- a lone warp pays per instruction, not per lane, so three products cost one.
+// Depth 3 products (X^2 | Y^2 | YZ ; B^2 | (X+B)^2 | E^2 ; E (D - X3)) instead of 7.  `l3` = lane % 3.
+template <class Fq>
+__device__ __forceinline__ JacT<Fq> dbl_lanes(const JacT<Fq>& p, u32 l3) {
+  Fq a = l3 == 0 ? p.X : p.Y, b = l3 == 2 ? p.Z : a;
+  Fq m = a * b;
+  Fq A = bcast_fe(m, 0), B = bcast_fe(m, 1), YZ = bcast_fe(m, 2);
+  Fq E = A.dbl() + A;
+  Fq s = l3 == 0 ? B : (l3 == 1 ? p.X + B : E);
+  Fq q = s.sqr();
+  Fq C = bcast_fe(q, 0), t = bcast_fe(q, 1), EE = bcast_fe(q, 2);
+  Fq D = (t - A - C).dbl();
+  JacT<Fq> r;
+  r.X = EE - D.dbl();
+  r.Y = E * (D - r.X) - C.dbl().dbl().dbl();
+  r.Z = YZ.dbl();  // an identity stays one (Z = 0)
+  return r;
+}
+
+// warp w adds the rb partials of window w (lanes stride, shuffle butterfly); warp 0 then runs Horner over the windows
+// (c lane-parallel doublings each, `dbl_lanes`) + to_affine
+#define COMBINE_MAX_WINDOWS 32
+#define COMBINE_T 256
+template <class Fq>
+__global__ void __launch_bounds__(COMBINE_T) k_msm_combine(MsmPlan plan, u32 rb, u32 rbt, const XyzzT<Fq>* partials, uint8_t* out) {
   typedef AffT<Fq> G1Affine;
   typedef XyzzT<Fq> G1Xyzz;
   __shared__ G1Xyzz wsum[COMBINE_MAX_WINDOWS];
-  u32 w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (w < plan.windows) {
+  u32 lane = threadIdx.x & 31;
+  for (u32 w = threadIdx.x >> 5; w < plan.windows; w += COMBINE_T / 32) {
     G1Xyzz sacc = G1Xyzz::identity();
     u32 nblk = w == plan.windows - 1 ? rbt : rb;
     for (u32 i = lane; i < nblk; i += 32) sacc = sacc.add(partials[(size_t)w * rbt + i]);
@@ -352,13 +381,16 @@ __global__ void __launch_bounds__(1024) k_msm_combine(MsmPlan plan, u32 rb, u32 
     if (lane == 0) wsum[w] = sacc;
   }
   __syncthreads();
-  if (threadIdx.x != 0) return;
-  // Horner in Jacobian coordinates: its doubling is 2M + 5S against 6M + 3S + a dot product for XYZZ
-  JacT<Fq> acc = JacT<Fq>::identity();
-  for (int ww = (int)plan.windows - 1; ww >= 0; ww--) {
-    for (u32 k = 0; k < plan.c; k++) acc = acc.dbl();
+  if (threadIdx.x >= 32) return;
+  // Horner in Jacobian coordinates (its doubling is 2M + 5S against 6M + 3S + a dot product for XYZZ); every lane of warp 0 carries
+  // the same accumulator, the additions run redundantly
+  const u32 l3 = lane % 3;
+  JacT<Fq> acc = wsum[plan.windows - 1].to_jac();
+  for (int ww = (int)plan.windows - 2; ww >= 0; ww--) {
+    for (u32 k = 0; k < plan.c; k++) acc = dbl_lanes(acc, l3);
     acc = acc.add(wsum[ww].to_jac());
   }
+  if (lane != 0) return;
   G1Affine a = acc.to_affine();
   Fq x = a.x.from_mont(), y = a.y.from_mont();
   uint4* o = reinterpret_cast<uint4*>(out);
@@ -428,7 +460,7 @@ static int msm_launch_t(svk_ctx* ctx, size_t n, const uint8_t* d_scalars, const 
   SVK_LAUNCH(ctx, "k_msm_heavy", k_msm_heavy<F><<<ctx->sm_count * 8, 32, 0, s>>>(nv, plan, heavy_list, n_heavy, heavy_cap, hist, offs, sorted, pts_m, heavy_part));
   SVK_LAUNCH(ctx, "k_msm_heavy", k_msm_heavy_sum<F><<<ctx->sm_count * 2, 32, 0, s>>>(heavy_list, n_heavy, heavy_cap, heavy_part, buckets));
   SVK_LAUNCH(ctx, "k_msm_reduce", k_msm_reduce<F><<<dim3(rbt, plan.windows), REDUCE_T, 0, s>>>(plan, rb, rbt, buckets, wsums));
-  SVK_LAUNCH(ctx, "k_msm_combine", k_msm_combine<F><<<1, 32 * plan.windows, 0, s>>>(plan, rb, rbt, wsums, d_out));
+  SVK_LAUNCH(ctx, "k_msm_combine", k_msm_combine<F><<<1, COMBINE_T, 0, s>>>(plan, rb, rbt, wsums, d_out));
   SVK_CUDA(ctx, cudaGetLastError());
   return 0;
 }
