@@ -17,6 +17,20 @@ struct Fq2 {
   HD Fq2 conj() const { return {c0, c1.neg()}; }
   // Two fused dot products (field.cuh `dot2`): 4 limb products + 2 reductions = 400 wide MACs against 417 for Karatsuba's
   // three Montgomery products, and none of Karatsuba's five additions/subtractions (~125 instructions).
+#if defined(__CUDA_ARCH__)
+  // Device: ONE out-of-line function per Fq2 operation with both of its Fq products inlined -- two independent multiply-accumulate
+  // chains for the scheduler to interleave and one call instead of two (batched k_decide: 35.9 -> 33.8 ms for 2^16 accumulators)
+  static __device__ __noinline__ Fq2 mul_call(Fq2 a, Fq2 b) {
+    Fq x[2] = {a.c0, a.c1.neg_lazy()}, y[2] = {b.c0, b.c1}, z[2] = {a.c0, a.c1}, w[2] = {b.c1, b.c0};
+    return {Fq::template dot_inline<2>(x, y), Fq::template dot_inline<2>(z, w)};
+  }
+  static __device__ __noinline__ Fq2 sqr_call(Fq2 a) {
+    Fq t = Fq::mul_inline(a.c0, a.c1);
+    return {Fq::mul_inline(a.c0 + a.c1, a.c0 - a.c1), t.dbl()};
+  }
+  __device__ friend Fq2 operator*(const Fq2& a, const Fq2& b) { return mul_call(a, b); }
+  __device__ Fq2 sqr() const { return sqr_call(*this); }
+#else
   HD friend Fq2 operator*(const Fq2& a, const Fq2& b) {
     return {Fq::dot2(a.c0, b.c0, a.c1.neg_lazy(), b.c1), Fq::dot2(a.c0, b.c1, a.c1, b.c0)};
   }
@@ -25,6 +39,7 @@ struct Fq2 {
     Fq t = c0 * c1;
     return {(c0 + c1) * (c0 - c1), t.dbl()};
   }
+#endif
   HD Fq2 mul_fq(const Fq& s) const { return {c0 * s, c1 * s}; }
   // * xi = (9 + u): (9a - b) + (9b + a) u
   HD Fq2 mul_xi() const {
