@@ -563,20 +563,25 @@ def run_ours(args):
         list(pool.map(e2e_worker, range(S)))  # warm
     else:
         e2e_async(S)
-    barrier()
-    t0 = time.perf_counter()
-    if pool:
-        results = list(pool.map(e2e_worker, range(S)))
-    else:
-        results = e2e_async(e2e_launches)
-    barrier()
-    dt = time.perf_counter() - t0
-    for ok, status in results:
-        assert ok and (status == 0).all()
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = world * nb1 * e2e_steps / float(t.item())
+    # the e2e region is short (tens of ms of host threads, pinned copies and kernels): it is run three times, every pass
+    # max-reduced over the ranks, and the MEDIAN pass is reported (all three are in the line)
+    e2e_passes = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        if pool:
+            results = list(pool.map(e2e_worker, range(S)))
+        else:
+            results = e2e_async(e2e_launches)
+        barrier()
+        dt = time.perf_counter() - t0
+        for ok, status in results:
+            assert ok and (status == 0).all()
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_passes.append(world * nb1 * e2e_steps / float(t.item()))
+    e2e_val = sorted(e2e_passes)[1]
     h2d = int(h_i.nbytes + h_p.nbytes + h_l.nbytes) // B   # per step (= per 4096-proof batch)
     d2h = int(nb1 * 4 + 256)
 
@@ -685,7 +690,8 @@ def run_ours(args):
                        "parallelism": f"proof-sharded x{world}, NCCL all_gather of {world} folded accumulators" if world > 1 else "single GPU",
                        "preflight_vs_oracle": preflight},
             "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "passes": e2e_passes, "reported": "median of three passes of the same region"},
             "roofline": roofline, "cpu_baseline": base, "secondary": secondary,
         }
         json_out.write(json.dumps(out) + "\n")
