@@ -46,6 +46,7 @@ def profile(ctx, fn, reps=1):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--max-log-n", type=int, default=24)
+    ap.add_argument("--min-log-n", type=int, default=16)
     ap.add_argument("--decide-n", type=int, default=65536)
     ap.add_argument("--only", choices=["all", "msm", "latency", "decide", "ipa"], default="all")
     args = ap.parse_args()
@@ -79,7 +80,7 @@ def main():
     stream.synchronize()
     out = torch.zeros(64, dtype=torch.uint8, device=dev)
     st = torch.zeros(1, dtype=torch.int32, device=dev)
-    for lg in range(16, args.max_log_n + 1, 2) if args.only in ("all", "msm") else []:
+    for lg in range(args.min_log_n, args.max_log_n + 1, 2) if args.only in ("all", "msm") else []:
         n = 1 << lg
         with torch.cuda.stream(stream):
             sc = rand_scalars(n, dev, 1000 + lg)
@@ -90,11 +91,11 @@ def main():
         ms = timed(run, 3 if lg <= 22 else 1)
         assert int(st.item()) == 0
         prof = profile(ctx, run)
-        cbits = 16 if lg >= 18 else (15 if lg >= 13 else 8)
-        windows = -(-255 // cbits)
-        work = n * windows * 10  # XYZZ mixed additions, 8M + 2S each (bucket accumulation only)
-        print(json.dumps({"config": "msm_g1_sweep", "log_n": lg, "n": n, "ms": ms, "points_per_s": n / (ms * 1e-3), "window_bits": cbits, "windows": windows,
-                          "modmul_frac_bucket_adds_only": work / (ms * 1e-3) / peak, "hbm_gbs_algorithmic": n * 96 / (ms * 1e-3) / 1e9,
+        # msm.cu msm_plan: GLV halves over 2n virtual points, 8 windows of 16 bits from 2^16 points up = 16 bucket additions per point
+        work = n * 16 * 10  # XYZZ mixed additions, 8M + 2S each (bucket accumulation only)
+        print(json.dumps({"config": "msm_g1_sweep", "log_n": lg, "n": n, "ms": ms, "points_per_s": n / (ms * 1e-3), "window_bits": 16, "windows": "8 x 2n (GLV)",
+                          "modmul_frac_bucket_adds_only": work / (ms * 1e-3) / peak, "modmul_frac_canonical_176": n * 176 / (ms * 1e-3) / peak,
+                          "hbm_gbs_algorithmic": n * 96 / (ms * 1e-3) / 1e9,
                           "kernels_ms": {k: round(v, 3) for k, v in prof.items()}}))
     del pts, dl
 
