@@ -16,8 +16,13 @@ Parity pinning status
 * Everything that bottoms out in the un-vendored `halo2curves 0.3.1`
   (Cargo.lock:1803-1826; BN254 Fr/Fq/G1/G2/pairing, point encodings): the
   reference ships no golden vectors and cannot be built here (no Rust toolchain)
-  => "parity unpinned".  The restatement follows the published BN254 definition
-  and is self-checked by exact algebra (bilinearity, trapdoor-forged proofs
-  accept, mutations reject).  The compressed-G1 byte format is isolated in
-  `bn254.g1_from_bytes / g1_to_bytes`.
+  => "parity unpinned" BY THE REFERENCE.  The restatement follows the published
+  BN254 definition and is self-checked by exact algebra (bilinearity,
+  trapdoor-forged proofs accept, mutations reject).  The group law and the
+  pairing are additionally pinned from OUTSIDE the repository by the public
+  EIP-196 / EIP-197 precompile test vectors (ecAdd, ecMul, ecPairing:
+  `tests/golden/eip196_197_vectors.py`, checked at every layer -- this oracle, oracle/c,
+  the device headers built for the host, the CUDA kernels).  What stays unpinned:
+  halo2curves' compressed-G1 byte format (isolated in `bn254.g1_from_bytes /
+  g1_to_bytes`) and the bincode layout of `Snark` files.
 """

@@ -174,6 +174,27 @@ def test_pairing_exact(lib):
         assert rd12(ml) == mlo and rd12(gt) == bn254.final_exponentiation(mlo) and rc == exp
 
 
+def test_public_precompile_vectors_on_device_headers(lib):
+    """EIP-196 / EIP-197 client test vectors (tests/golden/eip196_197_vectors.py) through the DEVICE headers built for the host: the
+    Jacobian and XYZZ group laws, the signed-window scalar multiplication, both pairing programs (tower and block-cooperative)."""
+    from .golden import eip196_197_vectors as E
+
+    def g2l(q):
+        return limbs([q[0][0], q[0][1], q[1][0], q[1][1]])
+
+    for repr_ in (0, 1):
+        out = (ctypes.c_uint32 * 16)()
+        lib.host_g1_muladd(repr_, g1l(E.ADD_A), limbs([1]), g1l(E.ADD_B), out)   # 1 * A + B
+        assert rd_g1(out) == E.ADD_C
+        lib.host_g1_muladd(repr_, g1l(E.MUL_P), limbs([E.MUL_K]), g1l(None), out)  # K * P + O
+        assert rd_g1(out) == E.MUL_Q
+    for fn in (lib.host_pairing, lib.host_pairing_coop):
+        gt, ml = (ctypes.c_uint32 * 96)(), (ctypes.c_uint32 * 96)()
+        assert fn(g1l(E.PAIR_P1), g2l(E.PAIR_Q1), g1l(E.PAIR_P2), g2l(E.PAIR_Q2), gt, ml) == 1
+        assert fn(g1l(E.PAIR_P1), g2l(E.PAIR_Q1), g1l(bn254.g1_neg(E.PAIR_P2)), g2l(E.PAIR_Q2), gt, ml) == 0
+        assert fn(g1l(E.ADD_A), g2l(E.PAIR_Q1), g1l(E.PAIR_P2), g2l(E.PAIR_Q2), gt, ml) == 0
+
+
 def test_coop_pairing_matches_tower(lib):
     """The block-cooperative pairing (csrc/coop_pairing.cuh: 48 dot3 lanes + 12 combine lanes per Fq12 product), executed
     lane by lane on the host, gives the oracle's exact Miller and GT values (decider.rs:60-68)."""

@@ -27,6 +27,20 @@ def test_public_known_answers():
     assert B.G2_GEN[0][0] == 10857046999023057135944570762232829481370756359578518086990519993285655852781
 
 
+def test_public_precompile_vectors():
+    """EIP-196 / EIP-197 client test vectors (tests/golden/eip196_197_vectors.py): external pins of the group law and the pairing."""
+    from .golden import eip196_197_vectors as E
+
+    for pt in (E.ADD_A, E.ADD_B, E.ADD_C, E.MUL_P, E.MUL_Q, E.PAIR_P1, E.PAIR_P2):
+        assert B.g1_is_on_curve(pt)
+    assert B.g1_add(E.ADD_A, E.ADD_B) == E.ADD_C
+    assert B.g1_mul(E.MUL_P, E.MUL_K) == E.MUL_Q and B.g1_msm_naive([(E.MUL_K, E.MUL_P)]) == E.MUL_Q
+    assert B.g2_is_on_curve(E.PAIR_Q1) and E.PAIR_Q2 == B.G2_GEN and B.g2_mul(E.PAIR_Q1, B.R) is None
+    assert B.pairing_check([(E.PAIR_P1, E.PAIR_Q1), (E.PAIR_P2, E.PAIR_Q2)])
+    assert not B.pairing_check([(E.PAIR_P1, E.PAIR_Q1), (B.g1_neg(E.PAIR_P2), E.PAIR_Q2)])
+    assert not B.pairing_check([(E.ADD_A, E.PAIR_Q1), (E.PAIR_P2, E.PAIR_Q2)])
+
+
 def test_g1_encoding_roundtrip():
     rng = random.Random(1)
     for _ in range(20):

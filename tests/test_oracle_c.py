@@ -67,3 +67,26 @@ def test_c_pippenger_matches_naive_msm():
     for th in (1, 4):
         assert g1_from(cref.msm(S_, P_, th).tobytes()) == exp
     assert g1_from(cref.msm(S_[:1], P_[:1], 8).tobytes()) is None  # 0 * P
+
+
+def test_public_precompile_vectors_through_the_c_oracle():
+    """EIP-196 / EIP-197 client test vectors (tests/golden/eip196_197_vectors.py): the C restatement's scalar multiplication, Pippenger
+    and pairing against values from outside this repository.  e(P1, Q1) e(P2, Q2) = 1 is `decide((P1, P2))` under the key
+    (g2, s_g2) = (Q1, -Q2) (decider.rs:60-68)."""
+    from types import SimpleNamespace
+
+    from oracle import bn254
+
+    from .golden import eip196_197_vectors as E
+
+    le = lambda v: v.to_bytes(32, "little")  # noqa: E731
+    acc = lambda l, r: np.frombuffer(le(l[0]) + le(l[1]) + le(r[0]) + le(r[1]), np.uint8).copy()  # noqa: E731
+    dk = SimpleNamespace(g2=E.PAIR_Q1, s_g2=bn254.g2_neg(E.PAIR_Q2))
+    assert cref.decide(acc(E.PAIR_P1, E.PAIR_P2), dk) is True
+    assert cref.decide(acc(E.PAIR_P1, bn254.g1_neg(E.PAIR_P2)), dk) is False
+    assert cref.decide(acc(E.ADD_A, E.PAIR_P2), dk) is False
+    sc = lambda ks: np.frombuffer(b"".join(le(k) for k in ks), np.uint8).copy()  # noqa: E731
+    pt = lambda ps: np.frombuffer(b"".join(le(x) + le(y) for x, y in ps), np.uint8).copy()  # noqa: E731
+    xy = lambda o: (int.from_bytes(o[:32].tobytes(), "little"), int.from_bytes(o[32:].tobytes(), "little"))  # noqa: E731
+    assert xy(cref.msm(sc([1, 1]), pt([E.ADD_A, E.ADD_B]))) == E.ADD_C
+    assert xy(cref.msm(sc([E.MUL_K]), pt([E.MUL_P]))) == E.MUL_Q
