@@ -6,6 +6,8 @@
   config 5  2^16 accumulators, 1/64 corrupted: constructed expectation + a sample through the oracle's pairing
   config 3  BN254 MSM at 2^18 and 2^20 (the c = 16 window plan): in-the-exponent equality, uniform and powers-of-r scalars
             (util/msm.rs:238-317)
+  config 4  the per-rank shard, 2048 GWC proofs with 21 corrupted, against oracle/c (the cross-rank half is
+            tests/test_gpu_multi_rank.py and bench.py's pre-flight)
 """
 import ctypes
 import os
@@ -201,3 +203,65 @@ def test_config3_msm_in_the_exponent(env, log_n):
         pw.append(cur)
         cur = cur * r % R
     assert msm(_scalars_le(pw).reshape(n, 32)) == g_mul(sum(x * y for x, y in zip(pw, d)) % R)
+
+
+def test_config4_gwc_2048_proofs_per_rank():
+    """BASELINE config 4's per-rank shard: 2048 GWC (Gwc19) proofs -- the 64 golden ones tiled, 21 of them corrupted -- against the C
+    restatement: statuses, accumulators, the fold tree, the verdict (pcs/kzg/multiopen/gwc19.rs:21-81, accumulation.rs:29-62)."""
+    from snark_verifier_axiom_b200 import verifier as V
+    from snark_verifier_axiom_b200.standard_plonk import load_golden
+
+    g = load_golden()
+    S = forge.Setup(0)
+    ctx = V.Context(0)
+    try:
+        pv = V.PlonkVerifier(ctx, g["dk"], g["protocol"], V.GWC)
+        n, m = 2048, 4
+        threads = os.cpu_count() or 1
+        sn = g["schemes"]["gwc19"]["snarks"]
+        inst, n_inst, base, lens = pv.pack([sn[i % len(sn)] for i in range(n)])
+        assert n_inst == 1
+        rng = np.random.default_rng(11)
+        idx = rng.choice(n, 21, replace=False)
+        ev, pt_id, sc_bad = idx[:13], idx[13:17], idx[17:]
+        evalbad = base.copy()
+        for k, i in enumerate(ev):  # an evaluation flipped: still decodes, another accumulator, the pairing rejects
+            evalbad[i, 9 * 32 + (k % 17) * 32 + (k % 31)] ^= 1 << (k % 7)
+        mixed = evalbad.copy()
+        w_points = (9 + 17) * 32                             # 9 commitments, 17 evaluations, then W_0..W_2 (gwc19.rs:62-81)
+        for k, i in enumerate(pt_id):
+            off = 32 * (2 * k) if k < 3 else w_points + 32   # identity among the commitments / as W_1
+            mixed[i, off : off + 32] = 0
+        for i in sc_bad:
+            mixed[i, 9 * 32 : 10 * 32] = 0xFF              # scalar >= r
+        tr = cref.Trace(S, "gwc19")
+        ilens = lens.astype(np.int32)
+        inp = _inputs(inst)
+        ref_accs, ref_st = cref.replay_packed(tr, np.ascontiguousarray(mixed), ilens, inp, threads)
+        assert sorted(np.nonzero(ref_st)[0]) == sorted(np.concatenate([pt_id, sc_bad]))
+        L, c = ctx._L, ctx._c
+        out_acc = np.zeros((n, 128), np.uint8)
+        out_st = np.full(n, -7, np.int32)
+        rc = L.svk_plonk_succinct_verify_batch(c, pv.pid, n, ptr(inst), 1, ptr(mixed), mixed.shape[1], ptr(lens), ptr(out_acc), None, ptr(out_st))
+        assert rc == 0, L.svk_last_error(c)
+        assert ((out_st & 0xFF) == (ref_st & 0xFF)).all()
+        ok_rows = ref_st == 0
+        assert (out_acc[ok_rows] == ref_accs[ok_rows]).all() and not out_acc[~ok_rows].any()
+        # the batch whose corrupted proofs all decode: fold tree bit-exact, one pairing rejects, decide_all names the culprits
+        acc_evalbad, st_e = cref.replay_packed(tr, np.ascontiguousarray(evalbad), ilens, inp, threads)
+        assert (st_e == 0).all()
+        st2, folded, okb = np.zeros(n, np.int32), np.zeros(128, np.uint8), np.zeros(1, np.uint8)
+        rc = L.svk_plonk_verify_batch(c, pv.pid, n, ptr(inst), 1, ptr(evalbad), evalbad.shape[1], ptr(lens), m, 1, ptr(st2), ptr(folded), ptr(okb))
+        assert rc == 0, L.svk_last_error(c)
+        facc, _, fst = cref.fold(acc_evalbad, m, threads=threads)
+        assert fst == 0 and not okb[0] and cref.decide(facc, S.dk) is False
+        assert sorted(np.nonzero(st2)[0]) == sorted(ev) and all(st2[i] == 3 for i in ev)
+        # all valid: accepted, the oracle's fold
+        acc_valid, st_v = cref.replay_packed(tr, np.ascontiguousarray(base), ilens, inp, threads)
+        assert (st_v == 0).all()
+        rc = L.svk_plonk_verify_batch(c, pv.pid, n, ptr(inst), 1, ptr(base), base.shape[1], ptr(lens), m, 1, ptr(st2), ptr(folded), ptr(okb))
+        assert rc == 0, L.svk_last_error(c)
+        facc, _, fst = cref.fold(acc_valid, m, threads=threads)
+        assert fst == 0 and okb[0] == 1 and (st2 == 0).all() and (folded == facc).all() and cref.decide(facc, S.dk) is True
+    finally:
+        ctx.close()
