@@ -643,10 +643,11 @@ def run_ours(args):
         ms_launch = prof[name]["ms"] / prof[name]["count"]
         ach = work_exec[name] / (ms_launch * 1e-3)
         ach_canon = work[name] / (ms_launch * 1e-3)
-        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/r1_traffic.json), per proof x proofs per launch
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/r2_traffic.json, derived from
+        # profiles/r2_ncu_full_summary.json), per proof x proofs per launch
         traffic, traffic_src = None, None
         try:
-            tr = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")))
+            tr = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_traffic.json")))
             if name in tr:
                 traffic = tr[name]["dram_bytes_per_launch"] / tr[name]["proofs_per_launch"] * n
                 traffic_src = tr[name].get("source")
