@@ -8,9 +8,11 @@
 // as aggregation.rs:216 constructs one per aggregation) and the group results are folded again until
 // one accumulator remains -- the same tree the oracle's `api.fold` performs.
 //
-//   k_fold_sponge : one group per thread: Poseidon sponge -> r, then the scalars r^j (canonical)
-//   k_group_var / k_group_sum : the group MSMs (see below)
-//                   block's threads, shared-memory tree reduction of the partial sums, to_affine
+// Per tree level, by its size (thresholds in svk_ctx.h; both forms give the same bytes, tests/test_gpu_schedules.py):
+//   wide    k_fold_sponge (one group per thread) or k_fold_sponge_coop (32 groups per block of three warps): sponge -> r, scalars r^j;
+//           k_group_var: the group MSMs as interleaved (Straus) multiplications; k_group_sum: base_0 + partial sums, to_affine
+//   narrow  k_fold_sponge_dbl: the sponge blocks, and beside them blocks that double every base 255 times; k_fold_add: r^j A_j as
+//           additions of those doublings over the NAF of r^j, 8 or 32 lanes per point; k_group_sum
 #include "straus.cuh"
 #include "poseidon_coop.cuh"
 #include "svk_ctx.h"
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(32) k_fold_sponge(size_t n_seg, size_t n, size
 }
 
 // Latency form (poseidon_coop.cuh): 32 groups per block of three warps.  The levels of the fold tree of a 4096-proof batch
-// have 512, 64, 8 and 1 groups, each a lone serial chain of 2m + 1 permutations.  The permutation count is made uniform
+// (groups of 4) have 1024, 256, 64, 16, 4 and 1 groups, each a lone serial chain of 2m + 1 permutations.  The permutation count is made uniform
 // across the warp (named barriers need whole warps): a lane whose group is shorter than the longest of its warp (the last
 // group of a segment, lanes past the end) captures its r after its own 2 len + 1 permutations and keeps permuting a dead state.
 __device__ __forceinline__ void fold_sponge_coop_block(PoseidonCoopShared& sh, size_t n_seg, size_t n, size_t m, const uint8_t* accs,
