@@ -1,6 +1,8 @@
-// K5/K6 kernel: batched KzgAs::decide (snark-verifier/src/pcs/kzg/decider.rs:60-81).
-// v1 mapping: one accumulator per thread; the G2 line tables and Frobenius constants are read
-// uniformly by all threads (broadcast loads, L1/L2 resident: 2 x 102 x 128 B).
+// K5/K6 kernels: KzgAs::decide (snark-verifier/src/pcs/kzg/decider.rs:60-81), two schedules (svk_ctx.h decide_coop_max):
+//   k_decide       one accumulator per thread (throughput form: batches of thousands); the G2 line tables and Frobenius
+//                  constants are read uniformly by all threads (broadcast loads, L1/L2 resident: 2 x 102 x 128 B)
+//   k_decide_coop  one accumulator per BLOCK of 128 threads (latency form: the single pairing of a folded batch), the
+//                  block-cooperative program of coop_pairing.cuh
 #include "svk_ctx.h"
 
 __device__ __forceinline__ G1Affine load_g1_canon(const uint8_t* p) {

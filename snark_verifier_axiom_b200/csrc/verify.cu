@@ -3,9 +3,12 @@
 //
 //   k_decompress   : every G1 point of every proof: halo2curves `G1Affine::from_bytes` (Fq sqrt) +
 //                    the [x mod r, y mod r] transcript encoding (transcript/halo2.rs:214-226, 247-260)
-//   k_tape         : one proof per thread runs the compiled verifier tape (tape.cuh)
+//   k_tape         : one proof per thread runs the compiled verifier tape (tape.cuh); k_tape_coop: the same tape with the
+//                    Poseidon sponge spread over three warps per 32 proofs (poseidon_coop.cuh) for small launches
 //   k_msm_var / k_msm_sum / k_to_affine : the final `lhs.evaluate(Some(g))` / `rhs.evaluate(Some(g))`
-//                    (util/msm.rs:70-77 -> NativeLoader::multi_scalar_multiplication, loader/native.rs:61-71)
+//                    (util/msm.rs:70-77 -> NativeLoader::multi_scalar_multiplication, loader/native.rs:61-71); two schedules
+//                    (svk_protocol.h MsmSched): all variable-base terms of a proof on one thread (Straus, shared doublings),
+//                    or one thread per term (GLV halves, 125 doublings) + 8 summing lanes when the launch is small
 //   k_status       : per-proof `Result` -> status word (include/svk.h)
 #include "compiler.h"
 #include "poseidon_coop.cuh"
