@@ -30,6 +30,27 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, s), f"libsvk.so does not export {s}"
 
 
+def test_rust_ffi_declares_the_header():
+    """rust/snark-verifier-cuda/src/ffi.rs (the binding a snark-verifier maintainer links) declares every entry point
+    of include/svk.h with the same number of parameters, and nothing the header does not have."""
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "svk.h")).read(), flags=re.S)
+    header = {}
+    for _ret, name, params in re.findall(r"^(int|void|const char\*|uint64_t)\s+(svk_[a-z0-9_]+)\s*\((.*?)\);", src, flags=re.S | re.M):
+        params = params.strip()
+        header[name] = 0 if params in ("", "void") else params.count(",") + 1
+    assert sorted(header) == declared_symbols()
+    rs = open(os.path.join(ROOT, "rust", "snark-verifier-cuda", "src", "ffi.rs")).read()
+    rs = re.sub(r"/\*.*?\*/", "", rs, flags=re.S)
+    rs = re.sub(r"//[^\n]*", "", rs)
+    rust = {}
+    for name, params in re.findall(r"pub fn\s+(svk_[a-z0-9_]+)\s*\((.*?)\)\s*(?:->[^;]*)?;", rs, flags=re.S):
+        assert name not in rust, f"{name} declared twice in ffi.rs"
+        rust[name] = len([x for x in params.split(",") if x.strip()])
+    assert sorted(rust) == sorted(header), (sorted(set(header) - set(rust)), sorted(set(rust) - set(header)))
+    for name, n in header.items():
+        assert rust[name] == n, f"{name}: {n} parameters in svk.h, {rust[name]} in ffi.rs"
+
+
 def test_no_cpu_fallback():
     import torch
 
