@@ -417,6 +417,8 @@ static int protocol_upload(svk_ctx* ctx, svk_host::CompiledProtocol& cp, int mos
     std::vector<u32> ol, orr;
     std::vector<FixedSlot> fl, fr;
     sc.msm_lanes = which == 0 ? 1 : SVK_MSM_LANES_LATENCY;
+    if (which == 0)
+      if (const char* e = getenv("SVK_MSM_LANES")) { int v = atoi(e); sc.msm_lanes = (v == 2 || v == 4) ? (u32)v : 1; }
     sc.msm_work_modmul = schedule_msm(lhs, vlanes, 0, ll, wl, ol, fl, sc.fixed_per_lhs, pd->fixed_bits, (int)sc.msm_lanes) +
                          schedule_msm(rhs, vlanes, ll, std::max<u32>(rl, 1), wr, orr, fr, sc.fixed_per_rhs, pd->fixed_bits, (int)sc.msm_lanes);
     if (upload(ctx, &sc.d_fixed_lhs, fl) || upload(ctx, &sc.d_fixed_rhs, fr)) return fail(-1);

@@ -561,11 +561,15 @@ int svk_succinct_verify_launch(svk_ctx* ctx, ProtocolDevice* pd, size_t n, const
       }
     }
     dim3 grid((unsigned)((n * sc.msm_lanes + 127) / 128), 2);
+#define SVK_MSM_SUM_ARGS                                                                                                                \
+  n, sc.d_work_lhs, sc.d_lane_off_lhs, sc.d_work_rhs, sc.d_lane_off_rhs, sc.d_fixed_lhs, sc.fixed_per_lhs, sc.d_fixed_rhs, sc.fixed_per_rhs, \
+      pd->fixed_bits, pd->d_fixed, pd->d_fixed_tables, d_pts, d_scalars, d_partials, d_sums
     if (sc.msm_lanes == 1)
-      SVK_LAUNCH(ctx, "k_msm_sum",
-                 k_msm_sum<1><<<grid, 128, 0, s>>>(n, sc.d_work_lhs, sc.d_lane_off_lhs, sc.d_work_rhs, sc.d_lane_off_rhs, sc.d_fixed_lhs,
-                                                   sc.fixed_per_lhs, sc.d_fixed_rhs, sc.fixed_per_rhs, pd->fixed_bits, pd->d_fixed,
-                                                   pd->d_fixed_tables, d_pts, d_scalars, d_partials, d_sums));
+      SVK_LAUNCH(ctx, "k_msm_sum", k_msm_sum<1><<<grid, 128, 0, s>>>(SVK_MSM_SUM_ARGS));
+    else if (sc.msm_lanes == 2)
+      SVK_LAUNCH(ctx, "k_msm_sum", k_msm_sum<2><<<grid, 128, 0, s>>>(SVK_MSM_SUM_ARGS));
+    else if (sc.msm_lanes == 4)
+      SVK_LAUNCH(ctx, "k_msm_sum", k_msm_sum<4><<<grid, 128, 0, s>>>(SVK_MSM_SUM_ARGS));
     else
       SVK_LAUNCH(ctx, "k_msm_sum",
                  k_msm_sum<SVK_MSM_LANES_LATENCY><<<grid, 128, 0, s>>>(n, sc.d_work_lhs, sc.d_lane_off_lhs, sc.d_work_rhs, sc.d_lane_off_rhs,
