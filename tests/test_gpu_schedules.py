@@ -15,15 +15,22 @@ from .util import to_product_protocol
 pytestmark = pytest.mark.gpu
 
 KNOBS = ("SVK_TAPE_COOP_MAX", "SVK_MSM_LATENCY_THREADS_MAX", "SVK_FOLD_DBL_THREADS_MAX", "SVK_DECIDE_COOP_MAX")
+# "throughput-2-lanes": the throughput forms with two threads per proof in k_msm_var and k_msm_sum (SVK_VAR_LANES, SVK_MSM_LANES)
+LANES = ("SVK_VAR_LANES", "SVK_MSM_LANES")
 
 
-@pytest.fixture(scope="module", params=["throughput", "latency"])
+@pytest.fixture(scope="module", params=["throughput", "latency", "throughput-2-lanes"])
 def env(request):
     from snark_verifier_axiom_b200 import verifier as V
 
-    saved = {k: os.environ.get(k) for k in KNOBS}
+    saved = {k: os.environ.get(k) for k in KNOBS + LANES}
     for k in KNOBS:
-        os.environ[k] = "0" if request.param == "throughput" else "1000000"
+        os.environ[k] = "1000000" if request.param == "latency" else "0"
+    for k in LANES:
+        if request.param == "throughput-2-lanes":
+            os.environ[k] = "2"
+        else:
+            os.environ.pop(k, None)
     try:
         S = forge.Setup(0)
         ctx = V.Context(0)
@@ -93,7 +100,7 @@ def test_schedules_really_differ(env):
     L.svk_profile_report(c, buf, len(buf))
     L.svk_profile_enable(c, 0)
     names = set(json.loads(buf.value.decode()))
-    if which == "throughput":
+    if which.startswith("throughput"):
         assert {"k_tape", "k_fold_sponge", "k_group_var", "k_decide"} <= names and not names & {"k_tape_coop", "k_decide_coop", "k_fold_sponge_dbl"}
     else:
         assert {"k_tape_coop", "k_fold_sponge_dbl", "k_fold_add", "k_decide_coop"} <= names and not names & {"k_tape", "k_decide", "k_fold_sponge"}
