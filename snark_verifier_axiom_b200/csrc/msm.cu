@@ -421,7 +421,6 @@ static int msm_launch_t(svk_ctx* ctx, size_t n, const uint8_t* d_scalars, const 
   G1Affine* pts_m;
   u32 *keys, *sorted, *hist;
   G1Xyzz* buckets;
-  u32 maxB = plan.buckets > plan.top_buckets ? plan.buckets : plan.top_buckets;
   // <= 4 buckets per thread of the reduction while all its blocks are resident at once (one per SM); the top window gets blocks
   // in proportion to its buckets
   u32 ratio = plan.top_buckets > plan.buckets ? plan.top_buckets / plan.buckets : 1;
