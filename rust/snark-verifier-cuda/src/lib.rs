@@ -1,6 +1,6 @@
 //! `snark-verifier-cuda`: the NativeLoader KZG/PLONK verification path of `snark-verifier` on a B200 through libsvk.
 //!
-//! * [`CudaPlonkVerifier`]: batch API (`succinct_verify_batch`, `verify_batch`, `kzg_as_create_proof`, `decide_all`).
+//! * [`CudaPlonkVerifier`]: batch API (`succinct_verify_batch`, `verify_batch`, `kzg_as_create_proof`, `kzg_as_verify_zk`, `decide_all`).
 //! * `impl SnarkVerifier<G1Affine, NativeLoader> for CudaPlonkVerifier<MOS>`: the reference's single-proof interface
 //!   (`snark-verifier/src/verifier.rs:13-44`); `Proof` is the raw transcript bytes, parsing happens on the device.
 //!
@@ -271,6 +271,20 @@ impl<MOS: Mos> CudaPlonkVerifier<MOS> {
         let packed = accs.iter().map(|a| ffi::svk_acc { lhs: g1(&a.lhs), rhs: g1(&a.rhs) }).collect_vec();
         let (mut out, mut r, mut status) = (ffi::svk_acc::default(), ffi::svk_fe::default(), 0i32);
         let rc = unsafe { ffi::svk_kzg_as_fold(self.ctx.0, packed.len(), packed.as_ptr(), group_size, &mut out, &mut r, &mut status) };
+        assert_eq!(rc, 0, "libsvk: {}", last_error(self.ctx.0));
+        status_to_result(status)?;
+        Ok((KzgAccumulator::new(g1_from(&out.lhs), g1_from(&out.rhs)), Fr::from_repr(r.b).unwrap()))
+    }
+
+    /// `KzgAs::{read_proof, verify}` with `KzgAsVerifyingKey(true)` (zk accumulation, `pcs/kzg/accumulation.rs:29-62, 124-133`):
+    /// `as_proof` = the two compressed blind points a zk `create_proof` wrote; they are absorbed after the instances and folded
+    /// in with r^n.  A short proof, a bad or an identity point come back as `Error::Transcript`, like `read_ec_point`.
+    pub fn kzg_as_verify_zk(&self, accs: &[KzgAccumulator<G1Affine, NativeLoader>], as_proof: &[u8]) -> Result<(KzgAccumulator<G1Affine, NativeLoader>, Fr), Error> {
+        let packed = accs.iter().map(|a| ffi::svk_acc { lhs: g1(&a.lhs), rhs: g1(&a.rhs) }).collect_vec();
+        let (mut out, mut r, mut status) = (ffi::svk_acc::default(), ffi::svk_fe::default(), 0i32);
+        let rc = unsafe {
+            ffi::svk_kzg_as_fold_zk(self.ctx.0, packed.len(), packed.as_ptr(), as_proof.as_ptr(), as_proof.len(), &mut out, &mut r, &mut status)
+        };
         assert_eq!(rc, 0, "libsvk: {}", last_error(self.ctx.0));
         status_to_result(status)?;
         Ok((KzgAccumulator::new(g1_from(&out.lhs), g1_from(&out.rhs)), Fr::from_repr(r.b).unwrap()))
